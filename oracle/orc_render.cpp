@@ -1,0 +1,238 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.h). Never linked into the product.
+#include "orc_render.h"
+#include <algorithm>
+#include <cstdio>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+static const uint32_t kKey1 = 0x43525431u;          // "CRT1"
+static const uint32_t kCameraBounce = 0xFFFFFFFFu;
+static const float kEps = 0.00001f;                 // Global.h:11
+static const float kPi = 3.14159265358979323846f;   // static_cast<float>(M_PI)
+static const float kTwoPi = 6.2831853071795864769f; // get_cuda_sphere_sample_inv_pdf(), Global.h:96-99
+
+// Philox draw for (pixel, sample, bounce, dim)
+static inline U4 draw(uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t dim, uint32_t seed) {
+    return philox4x32_10(U4{pixel, sample, bounce, dim}, seed, kKey1);
+}
+
+static inline V3 mat3_mul(const float* M, V3 v) {
+    return V3{dot(V3{M[0], M[1], M[2]}, v), dot(V3{M[3], M[4], M[5]}, v), dot(V3{M[6], M[7], M[8]}, v)};
+}
+
+Ray primary_ray(const Camera& cam, int width, int height, int i, int j, float u1, float u2) {
+    // Render.cuh:338-339,344-347
+    float ar = (float)width / (float)height;
+    float x = (2.0f * ((float)i + u1) / (float)width - 1.0f) * cam.tan_half * ar;
+    float y = (1.0f - 2.0f * ((float)j + u2) / (float)height) * cam.tan_half;
+    V3 d = mat3_mul(cam.M, normalize(V3{-x, y, 1.0f}));
+    return Ray{cam.eye, normalize(d), FLT_MAX};           // Ray.cuh:12-15 normalises again
+}
+
+// Global.h:35-50
+static inline V3 to_world(V3 a, V3 N) {
+    V3 C;
+    if (fabsf(N.x) > fabsf(N.y)) {
+        float inv = 1.0f / sqrtf(fmaf(N.z, N.z, N.x * N.x));
+        C = V3{N.z * inv, 0.0f, -N.x * inv};
+    } else {
+        float inv = 1.0f / sqrtf(fmaf(N.z, N.z, N.y * N.y));
+        C = V3{0.0f, N.z * inv, -N.y * inv};
+    }
+    V3 B = cross(C, N);
+    return (a.x * B + a.y * C) + a.z * N;
+}
+
+// Global.h:57-66 : uniform hemisphere about N, pdf 1/2pi
+static inline V3 sample_hemisphere(V3 N, float u1, float u2) {
+    float z = fabsf(1.0f - 2.0f * u1);
+    float r = sqrtf(1.0f - z * z);
+    float sn, cs;
+    sincos_2pi(u2, &sn, &cs);
+    return to_world(V3{r * cs, r * sn, z}, N);
+}
+
+// Global.h:68-94 : box in (theta, phi) around `out`; trigonometry by angle addition so that no
+// inverse functions are needed (cos/sin of theta0, phi0 come straight from the components).
+static inline V3 sample_probe_lobe(V3 out, float dtheta, float dphi, float u1, float u2) {
+    float eta1 = 2.0f * u1 - 1.0f, eta2 = 2.0f * u2 - 1.0f;
+    float r = length(out);
+    float ct0 = out.z / r;
+    ct0 = fminf(1.0f, fmaxf(-1.0f, ct0));
+    float st0 = sqrtf(fmaxf(0.0f, 1.0f - ct0 * ct0));
+    float cp0, sp0;
+    if (fabsf(out.x) < 1e-5f) {                           // Global.h:77-80
+        cp0 = 0.0f;
+        sp0 = out.y > 0.0f ? 1.0f : -1.0f;
+    } else {
+        float rho = sqrtf(fmaf(out.y, out.y, out.x * out.x));
+        cp0 = out.x / rho;
+        sp0 = out.y / rho;
+    }
+    float sa, ca, sb, cb;
+    sincos_rad(eta1 * dtheta, &sa, &ca);
+    sincos_rad(eta2 * dphi, &sb, &cb);
+    float st = fmaf(st0, ca, ct0 * sa), ct = fmaf(ct0, ca, -(st0 * sa));
+    float sp = fmaf(sp0, cb, cp0 * sb), cp = fmaf(cp0, cb, -(sp0 * sb));
+    return V3{st * cp, st * sp, ct};
+}
+
+static inline int64_t quantize(float c) {
+    if (!(fabsf(c) < 1073741824.0f)) return 0;            // drops NaN/inf/absurd values, both sides
+    return (int64_t)llrint((double)c * kFixedScale);
+}
+
+static inline void add_contrib(int64_t* px, V3 c) {
+    px[0] += quantize(c.x);
+    px[1] += quantize(c.y);
+    px[2] += quantize(c.z);
+}
+
+namespace {
+struct Ctx {
+    const Scene& s;
+    const NewBVH& b;
+    const Camera& cam;
+    const RenderParams& p;
+};
+}  // namespace
+
+// One camera path of the compat estimator. Reference: cast_ray_v2, Render.cuh:199-328.
+// The reference builds the vertex list forward and shades it backward; this is the same sum
+// written forward:  L = sum_k T_k (x) D_k,  T_{k+1} = T_k (x) kd_k/pi * cos_k * 2pi / P_RR
+// (Render.cuh:288-293), D_k = NEE of vertex k (:262-286) + the SPECULAR probe term (:294-314),
+// D_0 = Ke when the first vertex is emissive (:249-255).
+static void path_compat(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sample, int64_t* px, RenderStats* st) {
+    const Scene& s = c.s;
+    const RenderParams& p = c.p;
+    U4 r = draw(pixel, sample, kCameraBounce, 0, p.seed);
+    Ray ray = primary_ray(c.cam, p.width, p.height, i, j, u01(r.x), u01(r.y));
+    V3 T{1.0f, 1.0f, 1.0f};
+    bool have_probe = false;
+    Ray probe_ray{};
+    V3 probe_w{};
+    const float lsn_f = (float)p.light_sample_n;
+    for (int bnc = 0; bnc < p.max_vertices; ++bnc) {
+        Hit h = new_intersect(s, c.b, ray, 0, &st->closest);
+        st->extend_rays++;
+        if (have_probe) {
+            // Render.cuh:294-314 — evaluated only when the path continued to a real hit
+            if (h.face >= 0) {
+                Hit ph = new_intersect(s, c.b, probe_ray, 0, &st->closest);
+                st->probe_rays++;
+                if (ph.face >= 0) {
+                    const Material& pm = s.mats[s.tris[ph.face].mat];
+                    if (pm.has_emit) add_contrib(px, cmul(probe_w, pm.ke));
+                }
+            }
+            have_probe = false;
+        }
+        if (h.face < 0) break;                                            // :210
+        const Tri& tri = s.tris[h.face];
+        const Material& m = s.mats[tri.mat];
+        if (m.has_emit) {                                                 // :210,249-255
+            if (bnc == 0) add_contrib(px, m.ke);
+            break;
+        }
+        V3 pos = ray.o + h.t * ray.d;                                     // DeviceTriangle.cuh:50
+        V3 n = tri.normal;
+        V3 f_r = m.kd / kPi;                                              // :259
+        V3 Tf = cmul(T, f_r);
+        // next-event estimation, :262-286
+        for (int li = 0; li < (int)s.lights.size(); ++li) {
+            const LightObj& L = s.lights[li];
+            for (int sj = 0; sj < p.light_sample_n; ++sj) {
+                U4 q = draw(pixel, sample, (uint32_t)bnc, 2u + (uint32_t)(li * p.light_sample_n + sj), p.seed);
+                const Tri& lt = s.tris[L.tris[q.x % (uint32_t)L.tris.size()]];   // DeviceLights.cuh:35
+                float alpha = u01(q.y);                                   // DeviceTriangle.cuh:69-72
+                float beta = u01(q.z) * (1.0f - alpha);
+                float gamma = (1.0f - alpha) - beta;
+                V3 lp = (alpha * lt.v1 + beta * lt.v2) + gamma * lt.v3;
+                V3 dist = lp - pos;
+                V3 dir = normalize(dist);
+                float t_to_light = dist.x / dir.x;                        // :272
+                bool blocked = false;
+                if (t_to_light == t_to_light) {                           // NaN => never "blocked" (:19-27)
+                    Ray sh{pos, normalize(dir), t_to_light};
+                    Hit bh = new_intersect(s, c.b, sh, 1, &st->any);
+                    st->shadow_rays++;
+                    blocked = bh.face >= 0;
+                }
+                if (blocked) continue;
+                float d1 = length(dist);
+                float d2 = d1 * d1;
+                float cos1 = fmaxf(0.0f, dot(dir, n));
+                float cos2 = fmaxf(0.0f, -dot(dir, lt.normal));
+                const Material& lm = s.mats[lt.mat];
+                V3 contrib = cmul(lm.ke, Tf) * cos1 * cos2 * L.area / d2 / lsn_f;   // :283
+                add_contrib(px, contrib);
+            }
+        }
+        if (bnc == p.max_vertices - 1) break;                             // bounce stack full, :210
+        U4 q = draw(pixel, sample, (uint32_t)bnc, 0, p.seed);
+        if (u01(q.x) > p.p_rr) break;                                     // :216-221
+        V3 wdir = normalize(normalize(sample_hemisphere(n, u01(q.y), u01(q.z))));   // :225-227 + Ray ctor
+        if (m.mode == SPECULAR) {                                         // :294-303
+            V3 in = normalize(ray.d);
+            V3 out = in - (2.0f * dot(in, n)) * n;
+            U4 e = draw(pixel, sample, (uint32_t)bnc, 1, p.seed);
+            V3 pd = normalize(normalize(sample_probe_lobe(out, m.probe_dtheta, m.probe_dphi, u01(e.x), u01(e.y))));
+            probe_ray = Ray{pos, pd, FLT_MAX};
+            float pc = fmaxf(0.0f, dot(pd, n));
+            // :306-312 : (0.5*log10(Ns)+1) * Ke (x) kd * cos * 2pi/8, carried with the path throughput
+            probe_w = cmul(T, m.kd) * m.probe_shin * pc * (kTwoPi / 8.0f);
+            have_probe = true;
+        }
+        float cosn = fmaxf(0.0f, dot(wdir, n));
+        T = Tf * cosn * kTwoPi / p.p_rr;                                  // :288-293
+        ray = Ray{pos, wdir, FLT_MAX};
+    }
+}
+
+void render(const Scene& s, const NewBVH& b, const Camera& cam, const RenderParams& p, int64_t* accum,
+            RenderStats* stats, int n_threads) {
+    Ctx c{s, b, cam, p};
+    const int npix = p.width * p.height;
+    if (n_threads < 1) n_threads = 1;
+    std::vector<RenderStats> tls(n_threads);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads)
+    for (int pix = 0; pix < npix; ++pix) {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        int i = pix % p.width, j = pix / p.width;
+        for (uint32_t sm = p.s_begin; sm < p.s_end; ++sm) {
+            path_compat(c, (uint32_t)pix, i, j, sm, accum + 3 * (size_t)pix, &tls[tid]);
+            tls[tid].samples++;
+        }
+    }
+    if (stats) {
+        for (auto& t : tls) {
+            stats->samples += t.samples; stats->extend_rays += t.extend_rays;
+            stats->shadow_rays += t.shadow_rays; stats->probe_rays += t.probe_rays;
+            auto acc = [](TraceStats& a, const TraceStats& x) {
+                a.inner += x.inner; a.boxes += x.boxes; a.tris += x.tris; a.rays += x.rays;
+                a.max_stack = std::max(a.max_stack, x.max_stack);
+            };
+            acc(stats->closest, t.closest);
+            acc(stats->any, t.any);
+        }
+    }
+}
+
+void resolve(const int64_t* accum, int n_pixels, uint32_t spp, float* linear_rgb, uint8_t* rgb8) {
+    for (int k = 0; k < 3 * n_pixels; ++k) {
+        float v = (float)((double)accum[k] / kFixedScale / (double)spp);
+        if (linear_rgb) linear_rgb[k] = v;
+        if (rgb8) {
+            float cl = fmaxf(0.0f, fminf(1.0f, v));                       // Global.h:121-124
+            rgb8[k] = (uint8_t)(255.0f * powf(cl, 0.6f));                 // Render.cuh:350
+        }
+    }
+}
+
+}  // namespace orc
