@@ -1,0 +1,354 @@
+// crt_api.cu — the C-ABI of include/crt.h. Thin glue: argument checks, handle state, error slot.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "crt_gpu.h"
+
+using namespace crt;
+
+struct crt_scene {
+    HostScene host;
+    DeviceScene dev;
+    bool built = false;
+    uint32_t thresh_n = 0;
+};
+
+struct crt_render {
+    crt_scene* scene = nullptr;
+    Wavefront* wf = nullptr;
+    RenderSettings rs;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool rendered = false;
+    float* d_linear = nullptr;
+    uint8_t* d_rgb8 = nullptr;
+    crt_render_stats stats{};
+};
+
+namespace crt {
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+    cudaGetLastError();   // clear sticky-free errors
+    return CRT_ERR_CUDA;
+}
+}  // namespace crt
+
+#define CHECK_ARG(cond, msg)                         \
+    do {                                             \
+        if (!(cond)) { set_error(msg); return CRT_ERR_INVALID; } \
+    } while (0)
+
+extern "C" {
+
+const char* crt_last_error(void) { return get_error(); }
+int crt_abi_version(void) { return CRT_ABI_VERSION; }
+int crt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int crt_config_load(const char* json_path, crt_config* out) {
+    CHECK_ARG(json_path && out, "crt_config_load: null argument");
+    return load_config(json_path, out);
+}
+
+int crt_inverse_view_matrix(const float eye[3], const float lookat[3], const float up[3], float out9[9]) {
+    CHECK_ARG(eye && lookat && up && out9, "crt_inverse_view_matrix: null argument");
+    inverse_view_matrix(eye, lookat, up, out9);
+    return CRT_OK;
+}
+
+int crt_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height) {
+    return write_png(path, rgb8, width, height);
+}
+
+// ---- scene -------------------------------------------------------------------------------
+int crt_scene_create(crt_scene** out) {
+    CHECK_ARG(out, "crt_scene_create: null argument");
+    *out = new (std::nothrow) crt_scene();
+    if (!*out) { set_error("out of memory"); return CRT_ERR_NOMEM; }
+    return CRT_OK;
+}
+
+int crt_scene_add_obj(crt_scene* s, const char* obj_path, const char* mtl_dir) {
+    CHECK_ARG(s && obj_path && mtl_dir, "crt_scene_add_obj: null argument");
+    if (s->built) { set_error("crt_scene_add_obj: BVH already built"); return CRT_ERR_STATE; }
+    return load_obj(s->host, obj_path, mtl_dir);
+}
+
+int crt_scene_add_triangles(crt_scene* s, const float* verts, const uint32_t* mat_id, const uint32_t* obj_id, uint64_t n_tris,
+                            const crt_material* mats, uint32_t n_mats) {
+    CHECK_ARG(s && (n_tris == 0 || (verts && mat_id && obj_id)) && (n_mats == 0 || mats), "crt_scene_add_triangles: null argument");
+    if (s->built) { set_error("crt_scene_add_triangles: BVH already built"); return CRT_ERR_STATE; }
+    HostScene& h = s->host;
+    const int mat0 = (int)h.mats.size(), obj0 = h.n_objects;
+    for (uint64_t t = 0; t < n_tris; ++t) CHECK_ARG(mat_id[t] < n_mats, "crt_scene_add_triangles: mat_id out of range");
+    for (uint32_t m = 0; m < n_mats; ++m) {
+        HostMaterial hm;
+        memcpy(hm.kd, mats[m].kd, sizeof(hm.kd));
+        memcpy(hm.ks, mats[m].ks, sizeof(hm.ks));
+        memcpy(hm.ke, mats[m].ke, sizeof(hm.ke));
+        hm.ns = mats[m].ns;
+        finish_material(hm);
+        h.mats.push_back(hm);
+    }
+    uint32_t max_obj = 0;
+    for (uint64_t t = 0; t < n_tris; ++t) {
+        if (!push_triangle(h, verts + 9 * t, mat0 + (int)mat_id[t], obj0 + (int)obj_id[t])) {
+            set_error("crt_scene_add_triangles: non-finite vertex coordinate");
+            return CRT_ERR_INVALID;
+        }
+        if (obj_id[t] > max_obj) max_obj = obj_id[t];
+    }
+    if (n_tris) h.n_objects = obj0 + (int)max_obj + 1;
+    finish_objects(h);
+    return CRT_OK;
+}
+
+int crt_scene_build_bvh(crt_scene* s, uint32_t thresh_n, int builder, int device, float* build_ms) {
+    CHECK_ARG(s, "crt_scene_build_bvh: null scene");
+    CHECK_ARG(builder == CRT_BUILDER_LBVH, "crt_scene_build_bvh: unknown builder");
+    int n = crt_device_count();
+    if (n <= 0) { set_error("crt_scene_build_bvh: no CUDA device (there is no CPU fallback)"); return CRT_ERR_CUDA; }
+    CHECK_ARG(device >= 0 && device < n, "crt_scene_build_bvh: device out of range");
+    int rc = upload_scene(s->host, thresh_n, device, s->dev, build_ms);
+    s->built = rc == CRT_OK;
+    s->thresh_n = thresh_n;
+    return rc;
+}
+
+int crt_scene_counts(crt_scene* s, uint64_t* n_tris, uint32_t* n_mats, uint32_t* n_lights, uint64_t* n_nodes) {
+    CHECK_ARG(s, "crt_scene_counts: null scene");
+    if (n_tris) *n_tris = s->host.n_tris();
+    if (n_mats) *n_mats = (uint32_t)s->host.mats.size();
+    if (n_lights) *n_lights = (uint32_t)s->host.lights.size();
+    if (n_nodes) *n_nodes = s->built ? s->dev.n_nodes : 0;
+    return CRT_OK;
+}
+
+int crt_scene_export_tris(crt_scene* s, float* verts, float* normal, float* area, float* area_of_obj, int32_t* mat, int32_t* obj) {
+    CHECK_ARG(s, "crt_scene_export_tris: null scene");
+    const HostScene& h = s->host;
+    const size_t n = h.n_tris();
+    if (verts) memcpy(verts, h.verts.data(), sizeof(float) * 9 * n);
+    if (normal) memcpy(normal, h.normal.data(), sizeof(float) * 3 * n);
+    if (area) memcpy(area, h.area.data(), sizeof(float) * n);
+    if (area_of_obj) memcpy(area_of_obj, h.area_of_obj.data(), sizeof(float) * n);
+    if (mat) memcpy(mat, h.mat.data(), sizeof(int32_t) * n);
+    if (obj) memcpy(obj, h.obj.data(), sizeof(int32_t) * n);
+    return CRT_OK;
+}
+
+int crt_scene_export_mats(crt_scene* s, float* out) {
+    CHECK_ARG(s && out, "crt_scene_export_mats: null argument");
+    for (size_t m = 0; m < s->host.mats.size(); ++m) {
+        const HostMaterial& hm = s->host.mats[m];
+        float* o = out + 9 * m;
+        o[0] = hm.kd[0]; o[1] = hm.kd[1]; o[2] = hm.kd[2]; o[3] = hm.ke[0]; o[4] = hm.ke[1]; o[5] = hm.ke[2];
+        o[6] = hm.ns; o[7] = (float)hm.has_emit; o[8] = (float)hm.mode;
+    }
+    return CRT_OK;
+}
+
+int crt_scene_export_light(crt_scene* s, uint32_t li, int32_t* faces, uint32_t* n, float* area) {
+    CHECK_ARG(s && n, "crt_scene_export_light: null argument");
+    CHECK_ARG(li < s->host.lights.size(), "crt_scene_export_light: light index out of range");
+    const HostLight& L = s->host.lights[li];
+    if (faces) {
+        CHECK_ARG(*n >= L.faces.size(), "crt_scene_export_light: buffer too small");
+        memcpy(faces, L.faces.data(), sizeof(int32_t) * L.faces.size());
+    }
+    *n = (uint32_t)L.faces.size();
+    if (area) *area = L.area;
+    return CRT_OK;
+}
+
+int crt_scene_export_bvh(crt_scene* s, crt_bvh_node* nodes, int32_t* tri_order, uint8_t* last, float bounds[6]) {
+    CHECK_ARG(s, "crt_scene_export_bvh: null scene");
+    if (!s->built) { set_error("crt_scene_export_bvh: BVH not built"); return CRT_ERR_STATE; }
+    CRT_CUDA(cudaSetDevice(s->dev.device));
+    if (nodes && s->dev.n_nodes) CRT_CUDA(cudaMemcpy(nodes, s->dev.nodes, sizeof(crt_bvh_node) * s->dev.n_nodes, cudaMemcpyDeviceToHost));
+    if (tri_order && s->dev.n_tris) CRT_CUDA(cudaMemcpy(tri_order, s->dev.order, sizeof(int32_t) * s->dev.n_tris, cudaMemcpyDeviceToHost));
+    if (last && s->dev.n_tris) CRT_CUDA(cudaMemcpy(last, s->dev.last, s->dev.n_tris, cudaMemcpyDeviceToHost));
+    if (bounds) memcpy(bounds, s->dev.bounds, sizeof(float) * 6);
+    return CRT_OK;
+}
+
+int crt_scene_destroy(crt_scene* s) {
+    if (!s) return CRT_OK;
+    if (s->built) { cudaSetDevice(s->dev.device); s->dev.release(); }
+    delete s;
+    return CRT_OK;
+}
+
+// ---- ray batches ---------------------------------------------------------------------------
+int crt_trace_rays_device(crt_scene* s, const void* d_rays, uint64_t n, int mode, void* d_t_out, void* d_face_out, void* stream,
+                          float* kernel_ms) {
+    CHECK_ARG(s && (n == 0 || d_rays), "crt_trace_rays_device: null argument");
+    CHECK_ARG(mode == CRT_RAY_CLOSEST || mode == CRT_RAY_ANY, "crt_trace_rays_device: unknown mode");
+    if (!s->built) { set_error("crt_trace_rays: BVH not built"); return CRT_ERR_STATE; }
+    CRT_CUDA(cudaSetDevice(s->dev.device));
+    if (n == 0) { if (kernel_ms) *kernel_ms = 0; return CRT_OK; }
+    return trace_rays_device(s->dev, (const float4*)d_rays, n, mode, (float*)d_t_out, (int*)d_face_out, (cudaStream_t)stream, kernel_ms);
+}
+
+int crt_trace_rays(crt_scene* s, const float* rays, uint64_t n, int mode, float* t_out, int32_t* face_out, float* kernel_ms) {
+    CHECK_ARG(s && (n == 0 || rays), "crt_trace_rays: null argument");
+    if (!s->built) { set_error("crt_trace_rays: BVH not built"); return CRT_ERR_STATE; }
+    CRT_CUDA(cudaSetDevice(s->dev.device));
+    if (n == 0) { if (kernel_ms) *kernel_ms = 0; return CRT_OK; }
+    float4* d_rays = nullptr;
+    float* d_t = nullptr;
+    int* d_face = nullptr;
+    CRT_CUDA(cudaMalloc(&d_rays, sizeof(float) * 8 * n));
+    cudaError_t e1 = cudaMalloc(&d_t, sizeof(float) * n), e2 = cudaMalloc(&d_face, sizeof(int) * n);
+    int rc = CRT_OK;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) rc = cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaMalloc ray outputs");
+    if (rc == CRT_OK) {
+        cudaMemcpy(d_rays, rays, sizeof(float) * 8 * n, cudaMemcpyHostToDevice);
+        rc = crt_trace_rays_device(s, d_rays, n, mode, d_t, d_face, nullptr, kernel_ms);
+    }
+    if (rc == CRT_OK) {
+        if (t_out) cudaMemcpy(t_out, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost);
+        if (face_out) cudaMemcpy(face_out, d_face, sizeof(int) * n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_rays); cudaFree(d_t); cudaFree(d_face);
+    return rc;
+}
+
+// ---- render ----------------------------------------------------------------------------------
+int crt_render_create(crt_scene* s, uint32_t width, uint32_t height, crt_render** out) {
+    CHECK_ARG(s && out, "crt_render_create: null argument");
+    CHECK_ARG(width > 0 && height > 0 && (uint64_t)width * height <= (1ull << 28), "crt_render_create: bad image size");
+    if (!s->built) { set_error("crt_render_create: build the BVH first (crt_scene_build_bvh)"); return CRT_ERR_STATE; }
+    CRT_CUDA(cudaSetDevice(s->dev.device));
+    crt_render* r = new (std::nothrow) crt_render();
+    if (!r) { set_error("out of memory"); return CRT_ERR_NOMEM; }
+    r->scene = s;
+    r->rs.width = width; r->rs.height = height;
+    int rc = wavefront_create(s->dev, width, height, &r->wf);
+    if (rc == CRT_OK && cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamCreate");
+    r->own_stream = true;
+    if (rc == CRT_OK) {
+        cudaError_t e = cudaMalloc(&r->d_linear, sizeof(float) * 3 * (size_t)width * height);
+        if (e == cudaSuccess) e = cudaMalloc(&r->d_rgb8, 3 * (size_t)width * height);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc frame buffers");
+    }
+    if (rc != CRT_OK) { crt_render_destroy(r); return rc; }
+    *out = r;
+    return CRT_OK;
+}
+
+int crt_render_set_spp(crt_render* r, uint32_t spp) {
+    CHECK_ARG(r && spp > 0, "crt_render_set_spp: invalid argument");
+    r->rs.spp = spp;
+    return CRT_OK;
+}
+int crt_render_set_p_rr(crt_render* r, float p_rr) {
+    CHECK_ARG(r && p_rr >= 0.0f && p_rr <= 1.0f, "crt_render_set_p_rr: P_RR must be in [0,1]");
+    r->rs.p_rr = p_rr;
+    return CRT_OK;
+}
+int crt_render_set_light_sample_n(crt_render* r, uint32_t n) {
+    CHECK_ARG(r && n > 0 && n <= 4096, "crt_render_set_light_sample_n: invalid argument");
+    r->rs.light_sample_n = n;
+    return CRT_OK;
+}
+int crt_render_set_seed(crt_render* r, uint32_t seed) {
+    CHECK_ARG(r, "crt_render_set_seed: null handle");
+    r->rs.seed = seed;
+    return CRT_OK;
+}
+int crt_render_set_estimator(crt_render* r, int estimator) {
+    CHECK_ARG(r && (estimator == CRT_ESTIMATOR_COMPAT || estimator == CRT_ESTIMATOR_MIS), "crt_render_set_estimator: unknown estimator");
+    r->rs.estimator = estimator;
+    return CRT_OK;
+}
+int crt_render_set_sample_range(crt_render* r, uint32_t begin, uint32_t end) {
+    CHECK_ARG(r && begin <= end, "crt_render_set_sample_range: invalid range");
+    r->rs.s_begin = begin; r->rs.s_end = end; r->rs.range_set = true;
+    return CRT_OK;
+}
+int crt_render_set_stream(crt_render* r, void* cuda_stream) {
+    CHECK_ARG(r, "crt_render_set_stream: null handle");
+    if (r->own_stream && r->stream) cudaStreamDestroy(r->stream);
+    r->stream = (cudaStream_t)cuda_stream;
+    r->own_stream = false;
+    return CRT_OK;
+}
+int crt_render_set_stage_timing(crt_render* r, int on) {
+    CHECK_ARG(r, "crt_render_set_stage_timing: null handle");
+    r->rs.stage_timing = on != 0;
+    return CRT_OK;
+}
+
+int crt_render_run_view(crt_render* r, const float eye[3], const float inv_view[9], float fovy_rad) {
+    CHECK_ARG(r && eye && inv_view, "crt_render_run_view: null argument");
+    if (r->rs.range_set) CHECK_ARG(r->rs.s_end <= r->rs.spp, "crt_render_run_view: sample range exceeds spp");
+    CRT_CUDA(cudaSetDevice(r->scene->dev.device));
+    float tan_half = tanf(fovy_rad / 2);                          // Render.cuh:338, evaluated on the host
+    int rc = wavefront_render(r->wf, r->scene->dev, r->rs, eye, inv_view, tan_half, r->stream, &r->stats);
+    r->rendered = rc == CRT_OK;
+    return rc;
+}
+
+int crt_render_device_accum(crt_render* r, void** d_accum) {
+    CHECK_ARG(r && d_accum, "crt_render_device_accum: null argument");
+    *d_accum = wavefront_accum(r->wf);
+    return CRT_OK;
+}
+
+int crt_render_get_accum_i64(crt_render* r, int64_t* out) {
+    CHECK_ARG(r && out, "crt_render_get_accum_i64: null argument");
+    CRT_CUDA(cudaSetDevice(r->scene->dev.device));
+    CRT_CUDA(cudaMemcpy(out, wavefront_accum(r->wf), sizeof(int64_t) * 3 * (size_t)r->rs.width * r->rs.height, cudaMemcpyDeviceToHost));
+    return CRT_OK;
+}
+
+static int resolve_to(crt_render* r, float* lin_host, uint8_t* rgb_host) {
+    CRT_CUDA(cudaSetDevice(r->scene->dev.device));
+    const uint32_t npix = r->rs.width * r->rs.height;
+    int rc = resolve_device(wavefront_accum(r->wf), npix, r->rs.spp, r->d_linear, r->d_rgb8, r->stream);
+    if (rc != CRT_OK) return rc;
+    if (lin_host) CRT_CUDA(cudaMemcpyAsync(lin_host, r->d_linear, sizeof(float) * 3 * (size_t)npix, cudaMemcpyDeviceToHost, r->stream));
+    if (rgb_host) CRT_CUDA(cudaMemcpyAsync(rgb_host, r->d_rgb8, 3 * (size_t)npix, cudaMemcpyDeviceToHost, r->stream));
+    CRT_CUDA(cudaStreamSynchronize(r->stream));
+    return CRT_OK;
+}
+
+int crt_render_get_accum(crt_render* r, float* rgb) {
+    CHECK_ARG(r && rgb, "crt_render_get_accum: null argument");
+    return resolve_to(r, rgb, nullptr);
+}
+int crt_render_get_rgb8(crt_render* r, uint8_t* out) {
+    CHECK_ARG(r && out, "crt_render_get_rgb8: null argument");
+    return resolve_to(r, nullptr, out);
+}
+int crt_render_save_png(crt_render* r, const char* path) {
+    CHECK_ARG(r && path, "crt_render_save_png: null argument");
+    std::vector<uint8_t> rgb(3 * (size_t)r->rs.width * r->rs.height);
+    int rc = resolve_to(r, nullptr, rgb.data());
+    if (rc != CRT_OK) return rc;
+    return write_png(path, rgb.data(), r->rs.width, r->rs.height);
+}
+int crt_render_get_stats(crt_render* r, crt_render_stats* out) {
+    CHECK_ARG(r && out, "crt_render_get_stats: null argument");
+    *out = r->stats;
+    return CRT_OK;
+}
+
+int crt_render_destroy(crt_render* r) {
+    if (!r) return CRT_OK;
+    if (r->scene) cudaSetDevice(r->scene->dev.device);
+    wavefront_destroy(r->wf);
+    cudaFree(r->d_linear);
+    cudaFree(r->d_rgb8);
+    if (r->own_stream && r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+    return CRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,493 @@
+// crt_bvh_build.cu — GPU BVH construction (replaces the host builder, reference include/BVH.h:37-84).
+//
+// Algorithm (DESIGN.md "BVH build"; the CPU statement of the same algorithm is oracle/orc_bvh.cpp
+// build_new_bvh, and tests demand byte equality of nodes / order / leaf terminators):
+//   1. per-triangle boxes, scene box by exact min/max reduction;
+//   2. 63-bit Morton key of the box centre (21 bits/axis);
+//   3. stable LSD radix sort of (key, face id), 8 passes x 8 bits;
+//   4. Karras binary radix tree over the sorted keys (duplicates disambiguated by index);
+//   5. bottom-up box refit with one atomic flag per internal node;
+//   6. subtrees with <= thresh_n triangles become leaves (the reference's rule, BVH.h:57);
+//      kept nodes are numbered by the rank of their radix index (exclusive scan of the keep flags);
+//   7. emit 64-byte child-pair nodes and the per-slot triangle records.
+// Every float operation is exact (min/max) or a single rounding shared with the CPU statement
+// (this file is compiled with -fmad=false), so the result does not depend on thread scheduling.
+#include "crt_gpu.h"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace crt {
+
+// ------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.0f) atomicMin((int*)addr, __float_as_int(v));
+    else atomicMax((unsigned int*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.0f) atomicMax((int*)addr, __float_as_int(v));
+    else atomicMin((unsigned int*)addr, __float_as_uint(v));
+}
+
+// exclusive scan of uint32, three phases; block = 256 threads x 4 items
+static constexpr int kScanTile = 1024;
+
+__global__ void k_scan_reduce(const uint32_t* __restrict__ in, uint32_t* __restrict__ block_sums, uint32_t n) {
+    __shared__ uint32_t warp_sums[8];
+    uint32_t base = blockIdx.x * kScanTile;
+    uint32_t s = 0;
+    for (int k = 0; k < 4; ++k) {
+        uint32_t i = base + k * 256 + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_sums[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// single block: exclusive scan of block_sums in place, total written to *total (optional)
+__global__ void k_scan_sums(uint32_t* __restrict__ sums, uint32_t n_blocks, uint32_t* __restrict__ total) {
+    __shared__ uint32_t buf[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n_blocks ? sums[i] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive
+            uint32_t add = threadIdx.x >= (unsigned)o ? buf[threadIdx.x - o] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += add;
+            __syncthreads();
+        }
+        uint32_t incl = buf[threadIdx.x];
+        uint32_t c = carry;
+        if (i < n_blocks) sums[i] = c + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + incl;
+        __syncthreads();
+    }
+    if (total && threadIdx.x == 0) *total = carry;
+}
+
+__global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                             const uint32_t* __restrict__ block_offsets, uint32_t n) {
+    __shared__ uint32_t buf[kScanTile];
+    __shared__ uint32_t tsum[256];
+    uint32_t base = blockIdx.x * kScanTile;
+    // blocked arrangement: thread t owns items 4t..4t+3 of the tile
+    uint32_t v[4];
+    uint32_t s = 0;
+    for (int k = 0; k < 4; ++k) {
+        uint32_t i = base + threadIdx.x * 4 + k;
+        v[k] = i < n ? in[i] : 0;
+        s += v[k];
+    }
+    tsum[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        uint32_t add = threadIdx.x >= (unsigned)o ? tsum[threadIdx.x - o] : 0;
+        __syncthreads();
+        tsum[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t run = block_offsets[blockIdx.x] + tsum[threadIdx.x] - s;
+    for (int k = 0; k < 4; ++k) {
+        uint32_t i = base + threadIdx.x * 4 + k;
+        if (i < n) out[i] = run;
+        run += v[k];
+    }
+    (void)buf;
+}
+
+// out may alias in. scratch must hold ceil(n/1024) uint32. total (device pointer) optional.
+static cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch, uint32_t* total,
+                                      cudaStream_t st) {
+    if (n == 0) {
+        if (total) return cudaMemsetAsync(total, 0, sizeof(uint32_t), st);
+        return cudaSuccess;
+    }
+    uint32_t nb = (n + kScanTile - 1) / kScanTile;
+    k_scan_reduce<<<nb, 256, 0, st>>>(in, scratch, n);
+    k_scan_sums<<<1, 1024, 0, st>>>(scratch, nb, total);
+    k_scan_apply<<<nb, 256, 0, st>>>(in, out, scratch, n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// stable LSD radix sort of (uint64 key, uint32 value), 8 bits per pass
+// ------------------------------------------------------------------------------------------
+static constexpr int kSortTile = 1024;   // 256 threads x 4 keys, striped: item r*256 + tid
+
+__global__ void k_sort_hist(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ ghist,
+                            uint32_t n_tiles) {
+    __shared__ uint32_t hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * kSortTile;
+    for (int r = 0; r < 4; ++r) {
+        uint32_t i = base + r * 256 + threadIdx.x;
+        if (i < n) atomicAdd(&hist[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    ghist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = hist[threadIdx.x];   // digit-major
+}
+
+__global__ void k_sort_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                               uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                               const uint32_t* __restrict__ ghist_scanned, uint32_t n_tiles) {
+    __shared__ uint32_t cnt[4][8][256];      // [round][warp][digit] -> count, then start offset
+    for (int k = threadIdx.x; k < 4 * 8 * 256; k += 256) ((uint32_t*)cnt)[k] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kSortTile;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t key[4];
+    uint32_t val[4], rank[4], digit[4];
+    bool valid[4];
+    for (int r = 0; r < 4; ++r) {
+        uint32_t i = base + r * 256 + threadIdx.x;
+        valid[r] = i < n;
+        key[r] = valid[r] ? keys_in[i] : 0;
+        val[r] = valid[r] ? vals_in[i] : 0;
+        digit[r] = (uint32_t)(key[r] >> shift) & 255u;
+        // lanes with the same digit; invalid lanes get a private pseudo-digit
+        unsigned m = __match_any_sync(0xffffffffu, valid[r] ? digit[r] : 256u + lane);
+        rank[r] = __popc(m & ((1u << lane) - 1));
+        if (valid[r] && rank[r] == 0) cnt[r][warp][digit[r]] = __popc(m);
+    }
+    __syncthreads();
+    {   // thread d: running offset of digit d over (round, warp) in order
+        const int d = threadIdx.x;
+        uint32_t run = ghist_scanned[(size_t)d * n_tiles + blockIdx.x];
+        for (int r = 0; r < 4; ++r)
+            for (int w = 0; w < 8; ++w) {
+                uint32_t c = cnt[r][w][d];
+                cnt[r][w][d] = run;
+                run += c;
+            }
+    }
+    __syncthreads();
+    for (int r = 0; r < 4; ++r) {
+        if (!valid[r]) continue;
+        uint32_t pos = cnt[r][warp][digit[r]] + rank[r];
+        keys_out[pos] = key[r];
+        vals_out[pos] = val[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// build kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_tri_bounds(const float* __restrict__ verts, uint32_t n, float4* __restrict__ tlo, float4* __restrict__ thi,
+                             float* __restrict__ scene_bounds /* lo[3], hi[3] */) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < n) {
+        const float* v = verts + 9 * (size_t)i;
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = fminf(fminf(v[a], v[3 + a]), v[6 + a]);
+            hi[a] = fmaxf(fmaxf(v[a], v[3 + a]), v[6 + a]);
+        }
+        tlo[i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        thi[i] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    }
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_down_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_down_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int a = 0; a < 3; ++a) {
+            atomic_min_float(scene_bounds + a, lo[a]);
+            atomic_max_float(scene_bounds + 3 + a, hi[a]);
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t expand21(uint64_t x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__device__ __forceinline__ uint64_t quant21(float c, float lo, float scale) {
+    float f = (c - lo) * scale;
+    int q = (int)f;
+    if (q > 0x1fffff) q = 0x1fffff;
+    if (q < 0) q = 0;
+    return (uint64_t)q;
+}
+
+__global__ void k_morton(const float4* __restrict__ tlo, const float4* __restrict__ thi, uint32_t n,
+                         const float* __restrict__ scene_bounds, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float slo[3] = {scene_bounds[0], scene_bounds[1], scene_bounds[2]};
+    float scale[3];
+    for (int a = 0; a < 3; ++a) {
+        float ext = scene_bounds[3 + a] - slo[a];
+        scale[a] = ext > 0.0f ? 2097152.0f / ext : 0.0f;
+    }
+    float4 lo = tlo[i], hi = thi[i];
+    float cx = (lo.x + hi.x) * 0.5f, cy = (lo.y + hi.y) * 0.5f, cz = (lo.z + hi.z) * 0.5f;
+    uint64_t qx = quant21(cx, slo[0], scale[0]), qy = quant21(cy, slo[1], scale[1]), qz = quant21(cz, slo[2], scale[2]);
+    keys[i] = (expand21(qx) << 2) | (expand21(qy) << 1) | expand21(qz);
+    vals[i] = i;
+}
+
+__device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ key, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = key[i], b = key[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+// Karras 2012, one thread per internal node i in [0, n-2]
+__global__ void k_radix_tree(const uint64_t* __restrict__ key, int n, int* __restrict__ left, int* __restrict__ right,
+                             int* __restrict__ first, int* __restrict__ last, int* __restrict__ parent_of_node,
+                             int* __restrict__ parent_of_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta_fn(key, n, i, i + 1) - delta_fn(key, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta_fn(key, n, i, i - d);
+    int lmax = 2;
+    while (delta_fn(key, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta_fn(key, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta_fn(key, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta_fn(key, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo_i = min(i, j), hi_i = max(i, j);
+    first[i] = lo_i;
+    last[i] = hi_i;
+    if (lo_i == gamma) { left[i] = ~gamma; parent_of_leaf[gamma] = i; }
+    else { left[i] = gamma; parent_of_node[gamma] = i; }
+    if (hi_i == gamma + 1) { right[i] = ~(gamma + 1); parent_of_leaf[gamma + 1] = i; }
+    else { right[i] = gamma + 1; parent_of_node[gamma + 1] = i; }
+    if (i == 0) parent_of_node[0] = -1;
+}
+
+// bottom-up refit: one thread per sorted slot; the second arrival at a node computes its box
+__global__ void k_refit(int n, const uint32_t* __restrict__ order, const float4* __restrict__ tlo, const float4* __restrict__ thi,
+                        const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent_of_node,
+                        const int* __restrict__ parent_of_leaf, float4* __restrict__ blo, float4* __restrict__ bhi,
+                        uint32_t* __restrict__ flags) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    int node = parent_of_leaf[slot];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[node], 1u) == 0) return;       // first arrival: the sibling finishes the job
+        __threadfence();
+        // child boxes were written by other threads of this launch: read and write them through
+        // L2 (ld.cg / st.cg) so that no stale L1 line is used
+        float4 llo, lhi, rlo, rhi;
+        int l = left[node], r = right[node];
+        if (l < 0) { uint32_t f = order[~l]; llo = tlo[f]; lhi = thi[f]; }
+        else { llo = __ldcg(blo + l); lhi = __ldcg(bhi + l); }
+        if (r < 0) { uint32_t f = order[~r]; rlo = tlo[f]; rhi = thi[f]; }
+        else { rlo = __ldcg(blo + r); rhi = __ldcg(bhi + r); }
+        __stcg(blo + node, make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f));
+        __stcg(bhi + node, make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f));
+        node = parent_of_node[node];
+    }
+}
+
+__global__ void k_keep_flags(int n_internal, const int* __restrict__ first, const int* __restrict__ last, uint32_t thresh,
+                             uint32_t* __restrict__ keep) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    keep[i] = (uint32_t)(last[i] - first[i] + 1) > thresh ? 1u : 0u;
+}
+
+__global__ void k_emit_nodes(int n_internal, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ rank,
+                             const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ first,
+                             const int* __restrict__ last, const uint32_t* __restrict__ order, const float4* __restrict__ tlo,
+                             const float4* __restrict__ thi, const float4* __restrict__ blo, const float4* __restrict__ bhi,
+                             float4* __restrict__ nodes, uint8_t* __restrict__ last_flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal || !keep[i]) return;
+    float4 lo[2], hi[2];
+    int ref[2], cnt[2];
+    for (int w = 0; w < 2; ++w) {
+        int c = w == 0 ? left[i] : right[i];
+        if (c < 0) {                       // single triangle
+            uint32_t f = order[~c];
+            lo[w] = tlo[f]; hi[w] = thi[f];
+            ref[w] = c; cnt[w] = 1;
+            last_flag[~c] = 1;
+        } else {
+            lo[w] = blo[c]; hi[w] = bhi[c];
+            cnt[w] = last[c] - first[c] + 1;
+            if (keep[c]) ref[w] = (int)rank[c];
+            else { ref[w] = ~first[c]; last_flag[last[c]] = 1; }
+        }
+    }
+    float4* o = nodes + 4 * (size_t)rank[i];
+    o[0] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
+    o[1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
+    o[2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
+    o[3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(cnt[0]), __int_as_float(cnt[1]));
+}
+
+// the whole scene is one leaf: one node, child 1 absent with an inverted box
+__global__ void k_emit_single_leaf(int n, const float* __restrict__ scene_bounds, float4* __restrict__ nodes,
+                                   uint8_t* __restrict__ last_flag) {
+    nodes[0] = make_float4(scene_bounds[0], scene_bounds[3], scene_bounds[1], scene_bounds[4]);
+    nodes[1] = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
+    nodes[2] = make_float4(scene_bounds[2], scene_bounds[5], FLT_MAX, -FLT_MAX);
+    nodes[3] = make_float4(__int_as_float(~0), __int_as_float(kEmptyChild), __int_as_float(n), __int_as_float(0));
+    last_flag[n - 1] = 1;
+}
+
+// per-slot triangle records (DeviceTriangle::DeviceTriangle, reference DeviceTriangle.cuh:22-33)
+__global__ void k_emit_tris(uint32_t n, const uint32_t* __restrict__ order, const uint8_t* __restrict__ last_flag,
+                            const float* __restrict__ verts, const float4* __restrict__ face_shade,
+                            float4* __restrict__ tri_geom, float4* __restrict__ tri_shade) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    uint32_t f = order[slot];
+    const float* v = verts + 9 * (size_t)f;
+    float4 sh = face_shade[f];
+    uint32_t fw = f | (last_flag[slot] ? kLastBit : 0u);
+    tri_geom[3 * (size_t)slot + 0] = make_float4(v[0], v[1], v[2], __uint_as_float(fw));
+    tri_geom[3 * (size_t)slot + 1] = make_float4(v[3] - v[0], v[4] - v[1], v[5] - v[2], sh.w);
+    tri_geom[3 * (size_t)slot + 2] = make_float4(v[6] - v[0], v[7] - v[1], v[8] - v[2], 0.0f);
+    tri_shade[slot] = sh;
+}
+
+// ------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------
+#define BUILD_CHECK(x)                                                                           \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess) { rc = cuda_fail(e_, #x); goto done; }                            \
+    } while (0)
+
+int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face_shade, uint32_t n, uint32_t thresh_n,
+                     cudaStream_t st, float* build_ms) {
+    int rc = CRT_OK;
+    if (thresh_n < 1) thresh_n = 1;
+    const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    const int nb = (int)((n + 255) / 256);
+    float4 *tlo = nullptr, *thi = nullptr, *blo = nullptr, *bhi = nullptr;
+    float* bounds = nullptr;
+    uint64_t *keys0 = nullptr, *keys1 = nullptr;
+    uint32_t *vals0 = nullptr, *vals1 = nullptr, *ghist = nullptr, *scratch = nullptr, *flags = nullptr, *keep = nullptr,
+             *rank = nullptr, *d_total = nullptr;
+    int *left = nullptr, *right = nullptr, *first = nullptr, *last = nullptr, *pnode = nullptr, *pleaf = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t n_kept = 0;
+    const float init_bounds[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+
+    ds.n_tris = n;
+    ds.n_nodes = 0;
+    if (n == 0) { if (build_ms) *build_ms = 0; return CRT_OK; }
+
+    BUILD_CHECK(cudaEventCreate(&ev0));
+    BUILD_CHECK(cudaEventCreate(&ev1));
+    BUILD_CHECK(cudaMalloc(&tlo, sizeof(float4) * n));
+    BUILD_CHECK(cudaMalloc(&thi, sizeof(float4) * n));
+    BUILD_CHECK(cudaMalloc(&bounds, sizeof(float) * 6));
+    BUILD_CHECK(cudaMalloc(&keys0, sizeof(uint64_t) * n));
+    BUILD_CHECK(cudaMalloc(&keys1, sizeof(uint64_t) * n));
+    BUILD_CHECK(cudaMalloc(&vals0, sizeof(uint32_t) * n));
+    BUILD_CHECK(cudaMalloc(&vals1, sizeof(uint32_t) * n));
+    BUILD_CHECK(cudaMalloc(&ghist, sizeof(uint32_t) * 256 * (size_t)n_tiles));
+    BUILD_CHECK(cudaMalloc(&scratch, sizeof(uint32_t) * (std::max((256 * (size_t)n_tiles + kScanTile - 1) / kScanTile,
+                                                             ((size_t)n + kScanTile - 1) / kScanTile) + 1)));
+    BUILD_CHECK(cudaMalloc(&d_total, sizeof(uint32_t)));
+    BUILD_CHECK(cudaMalloc(&ds.order, sizeof(uint32_t) * n));
+    BUILD_CHECK(cudaMalloc(&ds.last, n));
+    BUILD_CHECK(cudaMalloc(&ds.tri_geom, sizeof(float4) * 3 * (size_t)n));
+    BUILD_CHECK(cudaMalloc(&ds.tri_shade, sizeof(float4) * (size_t)n));
+    BUILD_CHECK(cudaMemsetAsync(ds.last, 0, n, st));
+    BUILD_CHECK(cudaMemcpyAsync(bounds, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, st));
+
+    BUILD_CHECK(cudaEventRecord(ev0, st));
+    k_tri_bounds<<<nb, 256, 0, st>>>(d_verts, n, tlo, thi, bounds);
+    k_morton<<<nb, 256, 0, st>>>(tlo, thi, n, bounds, keys0, vals0);
+    {
+        uint64_t *kin = keys0, *kout = keys1;
+        uint32_t *vin = vals0, *vout = vals1;
+        for (int pass = 0; pass < 8; ++pass) {
+            int shift = pass * 8;
+            k_sort_hist<<<n_tiles, 256, 0, st>>>(kin, n, shift, ghist, n_tiles);
+            BUILD_CHECK(exclusive_scan_u32(ghist, ghist, 256 * n_tiles, scratch, nullptr, st));
+            k_sort_scatter<<<n_tiles, 256, 0, st>>>(kin, vin, kout, vout, n, shift, ghist, n_tiles);
+            std::swap(kin, kout);
+            std::swap(vin, vout);
+        }
+        // 8 passes: result is back in keys0 / vals0
+        BUILD_CHECK(cudaMemcpyAsync(ds.order, vals0, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+    }
+    BUILD_CHECK(cudaGetLastError());
+
+    if (n <= thresh_n) {
+        n_kept = 1;
+        BUILD_CHECK(cudaMalloc(&ds.nodes, sizeof(float4) * 4));
+        k_emit_single_leaf<<<1, 1, 0, st>>>((int)n, bounds, ds.nodes, ds.last);
+    } else {
+        const uint32_t ni = n - 1;
+        const int nbi = (int)((ni + 255) / 256);
+        BUILD_CHECK(cudaMalloc(&left, sizeof(int) * ni));
+        BUILD_CHECK(cudaMalloc(&right, sizeof(int) * ni));
+        BUILD_CHECK(cudaMalloc(&first, sizeof(int) * ni));
+        BUILD_CHECK(cudaMalloc(&last, sizeof(int) * ni));
+        BUILD_CHECK(cudaMalloc(&pnode, sizeof(int) * ni));
+        BUILD_CHECK(cudaMalloc(&pleaf, sizeof(int) * n));
+        BUILD_CHECK(cudaMalloc(&blo, sizeof(float4) * ni));
+        BUILD_CHECK(cudaMalloc(&bhi, sizeof(float4) * ni));
+        BUILD_CHECK(cudaMalloc(&flags, sizeof(uint32_t) * ni));
+        BUILD_CHECK(cudaMalloc(&keep, sizeof(uint32_t) * ni));
+        BUILD_CHECK(cudaMalloc(&rank, sizeof(uint32_t) * ni));
+        BUILD_CHECK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * ni, st));
+        k_radix_tree<<<nbi, 256, 0, st>>>(keys0, (int)n, left, right, first, last, pnode, pleaf);
+        k_refit<<<nb, 256, 0, st>>>((int)n, ds.order, tlo, thi, left, right, pnode, pleaf, blo, bhi, flags);
+        k_keep_flags<<<nbi, 256, 0, st>>>((int)ni, first, last, thresh_n, keep);
+        BUILD_CHECK(exclusive_scan_u32(keep, rank, ni, scratch, d_total, st));
+        BUILD_CHECK(cudaMemcpyAsync(&n_kept, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        BUILD_CHECK(cudaStreamSynchronize(st));
+        BUILD_CHECK(cudaMalloc(&ds.nodes, sizeof(float4) * 4 * (size_t)n_kept));
+        k_emit_nodes<<<nbi, 256, 0, st>>>((int)ni, keep, rank, left, right, first, last, ds.order, tlo, thi, blo, bhi, ds.nodes,
+                                          ds.last);
+    }
+    k_emit_tris<<<nb, 256, 0, st>>>(n, ds.order, ds.last, d_verts, d_face_shade, ds.tri_geom, ds.tri_shade);
+    BUILD_CHECK(cudaGetLastError());
+    BUILD_CHECK(cudaEventRecord(ev1, st));
+    BUILD_CHECK(cudaStreamSynchronize(st));
+    BUILD_CHECK(cudaMemcpy(ds.bounds, bounds, sizeof(float) * 6, cudaMemcpyDeviceToHost));
+    ds.n_nodes = n_kept;
+    if (build_ms) BUILD_CHECK(cudaEventElapsedTime(build_ms, ev0, ev1));
+
+done:
+    cudaFree(tlo); cudaFree(thi); cudaFree(blo); cudaFree(bhi); cudaFree(bounds);
+    cudaFree(keys0); cudaFree(keys1); cudaFree(vals0); cudaFree(vals1); cudaFree(ghist); cudaFree(scratch);
+    cudaFree(flags); cudaFree(keep); cudaFree(rank); cudaFree(d_total);
+    cudaFree(left); cudaFree(right); cudaFree(first); cudaFree(last); cudaFree(pnode); cudaFree(pleaf);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    return rc;
+}
+
+}  // namespace crt

@@ -1,0 +1,233 @@
+// crt_device.cuh — device-side arithmetic, RNG and BVH traversal shared by all kernels.
+//
+// Arithmetic contract (DESIGN.md "Arithmetic"): this translation unit is compiled with
+// -fmad=false, so every float operation below is a single IEEE-754 round-to-nearest operation and
+// a fused multiply-add happens only where fmaf() is written. Division and sqrt are the IEEE ones
+// (nvcc defaults -prec-div=true -prec-sqrt=true, -ftz=false). sin/cos are the fixed polynomials
+// below. The CPU oracle states the same operations, so hit ids and the fixed-point accumulation
+// buffer can be compared for exact equality.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace crt {
+
+#define CRT_DEV __device__ __forceinline__
+
+static constexpr float kEps = 0.00001f;                 // EPSILON, reference Global.h:11
+static constexpr float kPi = 3.14159265358979323846f;
+static constexpr float kTwoPi = 6.2831853071795864769f; // get_cuda_sphere_sample_inv_pdf(), Global.h:96-99
+static constexpr int kEmptyChild = 0x7fffffff;
+static constexpr uint32_t kLastBit = 0x80000000u;
+static constexpr int kStackSize = 96;                   // 63 Morton bits + duplicate-key levels
+
+struct V3 { float x, y, z; };
+CRT_DEV V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+CRT_DEV V3 mk3(float4 v) { return mk3(v.x, v.y, v.z); }
+CRT_DEV V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+CRT_DEV V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+CRT_DEV V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+CRT_DEV V3 operator*(float s, V3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+CRT_DEV V3 operator/(V3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+CRT_DEV V3 cmul(V3 a, V3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+CRT_DEV float dot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+CRT_DEV V3 cross(V3 a, V3 b) {
+    return mk3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+// Eigen normalized(): v / sqrt(v.v) when v.v > 0 (reference include/Eigen/src/Core/Dot.h:121-131)
+CRT_DEV V3 normalize(V3 a) {
+    float n = dot(a, a);
+    if (n > 0.0f) return a / sqrtf(n);
+    return a;
+}
+CRT_DEV float length(V3 a) { return sqrtf(dot(a, a)); }
+
+// ---- Philox4x32-10 (Salmon et al., SC'11). Replaces curand XORWOW + clock() seed
+// (reference Global.h:52-55,106-109; Render.cuh:340-341).
+CRT_DEV uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+static constexpr uint32_t kPhiloxKey1 = 0x43525431u;    // "CRT1"
+static constexpr uint32_t kCameraBounce = 0xFFFFFFFFu;
+CRT_DEV uint4 draw(uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t dim, uint32_t seed) {
+    return philox4x32_10(make_uint4(pixel, sample, bounce, dim), seed, kPhiloxKey1);
+}
+// (0,1], like curand_uniform (reference Global.h:52-55)
+CRT_DEV float u01(uint32_t x) { return (float)((x >> 8) + 1u) * 5.9604644775390625e-08f; }
+
+// ---- deterministic sin/cos
+CRT_DEV void sincos_poly(float x, float* s, float* c) {
+    float x2 = x * x;
+    float ps = fmaf(x2, 2.7557319e-06f, -1.9841270e-04f);
+    ps = fmaf(ps, x2, 8.3333333e-03f);
+    ps = fmaf(ps, x2, -1.6666667e-01f);
+    *s = fmaf(x * x2, ps, x);
+    float pc = fmaf(x2, -2.7557319e-07f, 2.4801587e-05f);
+    pc = fmaf(pc, x2, -1.3888889e-03f);
+    pc = fmaf(pc, x2, 4.1666667e-02f);
+    pc = fmaf(pc, x2, -0.5f);
+    *c = fmaf(pc, x2, 1.0f);
+}
+CRT_DEV void quadrant(int q, float ss, float cc, float* s, float* c) {
+    switch (q & 3) {
+        case 0: *s = ss; *c = cc; break;
+        case 1: *s = cc; *c = -ss; break;
+        case 2: *s = -ss; *c = -cc; break;
+        default: *s = -cc; *c = ss; break;
+    }
+}
+CRT_DEV void sincos_2pi(float u, float* s, float* c) {
+    int q = (int)fmaf(u, 4.0f, 0.5f);
+    float r = u - (float)q * 0.25f;
+    float ss, cc;
+    sincos_poly(r * 6.2831855f, &ss, &cc);
+    quadrant(q, ss, cc, s, c);
+}
+CRT_DEV void sincos_rad(float x, float* s, float* c) {
+    if (!(fabsf(x) <= 1.0e6f)) x = 0.0f;
+    float n = rintf(x * 0.63661975f);
+    float r = fmaf(-n, 1.5707963705062866f, x);
+    r = fmaf(-n, -4.371138828673793e-08f, r);
+    float ss, cc;
+    sincos_poly(r, &ss, &cc);
+    quadrant((int)n, ss, cc, s, c);
+}
+
+// ---- scene view passed to kernels by value
+struct SceneView {
+    const float4* __restrict__ nodes;       // 4 x 16 B per node (crt_bvh_node)
+    const float4* __restrict__ tri_geom;    // 3 x 16 B per slot: (v1, face|last) (e1, mat) (e2, 0)
+    const float4* __restrict__ tri_shade;   // 1 x 16 B per slot: (normal, mat)
+    const float4* __restrict__ mats;        // 4 x 16 B per material, see MatRec
+    const float4* __restrict__ light_tris;  // 4 x 16 B per light triangle: (v1,ke.r) (v2,ke.g) (v3,ke.b) (n, 0)
+    const int4* __restrict__ lights;        // per light object: (first light tri, count, area bits, 0)
+    int n_nodes;
+    int n_lights;
+};
+
+// Canonical triangle test: Moeller-Trumbore of reference DeviceTriangle.cuh:39-65 (strict inside).
+CRT_DEV bool tri_test(V3 v1, V3 e1, V3 e2, V3 o, V3 d, float* t_out) {
+    V3 sv = o - v1;
+    V3 s1 = cross(d, e2);
+    V3 s2 = cross(sv, e1);
+    float rcp = 1.0f / dot(s1, e1);
+    float beta = dot(s1, sv) * rcp;
+    float gamma = dot(s2, d) * rcp;
+    float t = dot(s2, e2) * rcp;
+    float alpha = (1.0f - beta) - gamma;
+    *t_out = t;
+    return 0.0f < alpha && alpha < 1.0f && 0.0f < beta && beta < 1.0f && 0.0f < gamma && gamma < 1.0f;
+}
+
+// Conservative slab test (DESIGN.md "Traversal rule").
+CRT_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, V3 o, V3 inv, float limit,
+                  float* enter) {
+    float tx0 = (lox - o.x) * inv.x, tx1 = (hix - o.x) * inv.x;
+    float ty0 = (loy - o.y) * inv.y, ty1 = (hiy - o.y) * inv.y;
+    float tz0 = (loz - o.z) * inv.z, tz1 = (hiz - o.z) * inv.z;
+    float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+    float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), limit));
+    *enter = tmin;
+    return tmin <= tmax * 1.0000004f;
+}
+
+struct HitRec { float t; int slot; int face; };
+
+// MODE 0: closest hit, t > 1e-5, ties -> lower face id (reference DeviceBVH.cuh:128-170 semantics
+//         made BVH-independent). MODE 1: any hit with t > 1e-5 && tmax - t > 1e-5 (the decision of
+//         reference Render.cuh:19-27, with early exit).
+template <int MODE>
+CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
+    HitRec best;
+    best.t = FLT_MAX; best.slot = -1; best.face = -1;
+    if (sc.n_nodes == 0) return best;
+    const V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float tlimit = MODE == 0 ? FLT_MAX : tmax;
+    int stack[kStackSize];
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        if (cur >= 0) {
+            if (cur == kEmptyChild) { if (sp == 0) break; cur = stack[--sp]; continue; }
+            const float4 n0 = __ldg(sc.nodes + 4 * (size_t)cur + 0);
+            const float4 n1 = __ldg(sc.nodes + 4 * (size_t)cur + 1);
+            const float4 n2 = __ldg(sc.nodes + 4 * (size_t)cur + 2);
+            const float4 n3 = __ldg(sc.nodes + 4 * (size_t)cur + 3);
+            const float lim = tlimit * 1.0001f;
+            float e0, e1;
+            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);
+            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1);
+            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                int nearc = c0, farc = c1;
+                if (e1 < e0) { nearc = c1; farc = c0; }
+                stack[sp++] = farc;
+                cur = nearc;
+            } else if (h0) cur = c0;
+            else if (h1) cur = c1;
+            else { if (sp == 0) break; cur = stack[--sp]; }
+        } else {
+            int slot = ~cur;
+            for (;; ++slot) {
+                const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
+                const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
+                const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
+                const uint32_t fw = __float_as_uint(a.w);
+                const int face = (int)(fw & ~kLastBit);
+                float t;
+                if (tri_test(mk3(a), mk3(b), mk3(c), o, d, &t) && t > kEps) {
+                    if (MODE == 0) {
+                        if (t < best.t || (t == best.t && face < best.face)) {
+                            best.t = t; best.slot = slot; best.face = face;
+                            tlimit = t;
+                        }
+                    } else if (tmax - t > kEps) {
+                        best.t = t; best.slot = slot; best.face = face;
+                        return best;
+                    }
+                }
+                if (fw & kLastBit) break;
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return best;
+}
+
+// ---- fixed-point accumulation (DESIGN.md "Accumulation"): radiance * 2^32 summed in int64, which
+// makes the image independent of atomic ordering, wavefront scheduling and GPU count.
+CRT_DEV long long quantize(float c) {
+    if (!(fabsf(c) < 1073741824.0f)) return 0;
+    return __double2ll_rn((double)c * 4294967296.0);
+}
+CRT_DEV void accum_add(long long* accum, uint32_t pixel, V3 c) {
+    unsigned long long* p = (unsigned long long*)(accum + 3 * (size_t)pixel);
+    long long qx = quantize(c.x), qy = quantize(c.y), qz = quantize(c.z);
+    if (qx) atomicAdd(p + 0, (unsigned long long)qx);
+    if (qy) atomicAdd(p + 1, (unsigned long long)qy);
+    if (qz) atomicAdd(p + 2, (unsigned long long)qz);
+}
+
+// ---- warp-aggregated append: one atomicAdd per warp, returns this lane's slot (or -1)
+CRT_DEV int warp_append(uint32_t* counter, bool want) {
+    const unsigned mask = __ballot_sync(__activemask(), want);
+    if (!want) return -1;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return (int)(base + __popc(mask & ((1u << lane) - 1)));
+}
+
+}  // namespace crt

@@ -1,0 +1,77 @@
+// crt_gpu.h — device-side scene and the host entry points of the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "crt_device.cuh"
+#include "crt_host.h"
+
+namespace crt {
+
+// records cudaGetErrorString + context in the thread's error slot, returns CRT_ERR_CUDA
+int cuda_fail(cudaError_t e, const char* what);
+
+#define CRT_CUDA(x)                                          \
+    do {                                                     \
+        cudaError_t e__ = (x);                               \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #x);   \
+    } while (0)
+
+// Everything the kernels read, resident in HBM for the life of the scene handle
+// (replaces DeviceBVH / DeviceTriangle / DeviceLights / DeviceMaterial uploads,
+//  reference DeviceBVH.cuh:52-80, DeviceLights.cuh:12-31,63-87).
+struct DeviceScene {
+    int device = 0;
+    uint32_t n_tris = 0, n_nodes = 0, n_mats = 0, n_lights = 0, n_light_tris = 0;
+    float4* nodes = nullptr;        // n_nodes * 4
+    float4* tri_geom = nullptr;     // n_tris * 3, BVH slot order
+    float4* tri_shade = nullptr;    // n_tris, BVH slot order
+    uint32_t* order = nullptr;      // slot -> face id
+    uint8_t* last = nullptr;        // slot -> leaf terminator
+    float4* mats = nullptr;         // n_mats * 4
+    float4* light_tris = nullptr;   // n_light_tris * 4
+    int4* lights = nullptr;         // n_lights
+    float bounds[6] = {0, 0, 0, 0, 0, 0};
+    bool has_specular = false;
+    SceneView view() const {
+        SceneView v;
+        v.nodes = nodes; v.tri_geom = tri_geom; v.tri_shade = tri_shade; v.mats = mats;
+        v.light_tris = light_tris; v.lights = lights; v.n_nodes = (int)n_nodes; v.n_lights = (int)n_lights;
+        return v;
+    }
+    void release();
+};
+
+// GPU BVH build; d_verts: n*9 floats (face order), d_face_shade: n float4 (normal, mat bits).
+int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face_shade, uint32_t n, uint32_t thresh_n,
+                     cudaStream_t st, float* build_ms);
+
+// Uploads materials and lights, builds the BVH. Leaves the device selected.
+int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene& ds, float* build_ms);
+
+// Ray batches (device pointers). rays: n * 2 float4 {o,tmax}{d,0}.
+int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
+                      cudaStream_t st, float* kernel_ms);
+
+struct RenderSettings {
+    uint32_t width = 0, height = 0;
+    uint32_t spp = 16;               // Render.cuh:379 defaults
+    float p_rr = 0.8f;
+    uint32_t light_sample_n = 1;
+    uint32_t seed = 0;
+    int estimator = 0;
+    uint32_t s_begin = 0, s_end = 0; // 0,0 -> [0, spp)
+    bool range_set = false;
+    bool stage_timing = false;
+};
+
+struct Wavefront;   // opaque pipeline state (crt_render.cu)
+int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wavefront** out);
+void wavefront_destroy(Wavefront* w);
+int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
+                     float tan_half, cudaStream_t st, crt_render_stats* stats);
+long long* wavefront_accum(Wavefront* w);
+// fixed point -> linear float mean and tone-mapped RGB8 (reference Render.cuh:348,350), on the device
+int resolve_device(const long long* d_accum, uint32_t n_pixels, uint32_t spp, float* d_linear, uint8_t* d_rgb8, cudaStream_t st);
+
+}  // namespace crt

@@ -1,0 +1,105 @@
+// crt — headless command-line host (replaces the GLFW/ImGui shell of reference src/main.cu:119-426):
+//   main() -> config_task -> scene ingest -> set_BVH -> Render -> run_view -> save_frame_buffer,
+// all through the C-ABI of include/crt.h.
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/crt.h"
+
+static bool exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+static std::string dir_of(const std::string& p) { size_t k = p.find_last_of('/'); return k == std::string::npos ? "." : p.substr(0, k); }
+static std::string base_of(const std::string& p) {
+    std::string q = p;
+    while (!q.empty() && q.back() == '/') q.pop_back();
+    size_t k = q.find_last_of('/');
+    return k == std::string::npos ? q : q.substr(k + 1);
+}
+// The shipped configs name paths relative to build/Debug ("../../scenes/..."): try the path as
+// given, under --root, next to the config file, and by file name next to the config file.
+static std::string resolve(const std::string& p, const std::string& root, const std::string& cfg_dir, bool is_dir) {
+    std::vector<std::string> cand = {p, root + "/" + p, cfg_dir + "/" + p, is_dir ? cfg_dir : cfg_dir + "/" + base_of(p)};
+    for (auto& c : cand) if (exists(c)) return c;
+    return p;
+}
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+#define DIE_IF(rc, what) do { if ((rc) != CRT_OK) { fprintf(stderr, "crt: %s failed: %s\n", what, crt_last_error()); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    std::string config = "config.json", out = "out.png", root = ".";
+    long spp = -1, seed = -1, width = -1, height = -1;
+    int estimator = -1, device = 0;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--config") config = next();
+        else if (a == "--out") out = next();
+        else if (a == "--root") root = next();
+        else if (a == "--spp") spp = atol(next());
+        else if (a == "--seed") seed = atol(next());
+        else if (a == "--width") width = atol(next());
+        else if (a == "--height") height = atol(next());
+        else if (a == "--device") device = atoi(next());
+        else if (a == "--estimator") { std::string e = next(); estimator = e == "mis" ? CRT_ESTIMATOR_MIS : CRT_ESTIMATOR_COMPAT; }
+        else if (a == "--help" || a == "-h") {
+            printf("usage: crt --config config.json [--root DIR] [--out image.png] [--spp N] [--seed S]\n"
+                   "           [--width W --height H] [--estimator compat|mis] [--device D]\n");
+            return 0;
+        } else { fprintf(stderr, "crt: unknown argument %s\n", a.c_str()); return 2; }
+    }
+    crt_config cfg;
+    DIE_IF(crt_config_load(config.c_str(), &cfg), "config");
+    if (spp > 0) cfg.spp = (uint32_t)spp;
+    if (seed >= 0) cfg.seed = (uint32_t)seed;
+    if (width > 0) cfg.width = (uint32_t)width;
+    if (height > 0) cfg.height = (uint32_t)height;
+    if (estimator >= 0) cfg.estimator = (uint32_t)estimator;
+    const std::string cfg_dir = dir_of(config);
+
+    crt_scene* scene = nullptr;
+    DIE_IF(crt_scene_create(&scene), "scene_create");
+    double t0 = now_ms();
+    for (uint32_t k = 0; k < cfg.n_obj; ++k) {
+        std::string obj = resolve(cfg.obj_path[k], root, cfg_dir, false), mtl = resolve(cfg.mtl_dir[k], root, cfg_dir, true);
+        DIE_IF(crt_scene_add_obj(scene, obj.c_str(), mtl.c_str()), "add_obj");
+    }
+    double t1 = now_ms();
+    float build_ms = 0;
+    DIE_IF(crt_scene_build_bvh(scene, cfg.bvh_thresh_n, CRT_BUILDER_LBVH, device, &build_ms), "build_bvh");
+    double t2 = now_ms();
+    uint64_t n_tris = 0, n_nodes = 0; uint32_t n_mats = 0, n_lights = 0;
+    crt_scene_counts(scene, &n_tris, &n_mats, &n_lights, &n_nodes);
+
+    crt_render* render = nullptr;
+    DIE_IF(crt_render_create(scene, cfg.width, cfg.height, &render), "render_create");
+    crt_render_set_spp(render, cfg.spp);
+    crt_render_set_p_rr(render, cfg.p_rr);
+    crt_render_set_light_sample_n(render, cfg.light_sample_n);
+    crt_render_set_seed(render, cfg.seed);
+    DIE_IF(crt_render_set_estimator(render, (int)cfg.estimator), "set_estimator");
+    float M[9];
+    crt_inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up, M);
+    double t3 = now_ms();
+    DIE_IF(crt_render_run_view(render, cfg.eye_pos, M, cfg.fov_y * (float)M_PI / 180.0f), "run_view");   // main.cu:372
+    double t4 = now_ms();
+    DIE_IF(crt_render_save_png(render, out.c_str()), "save_png");
+    crt_render_stats st;
+    crt_render_get_stats(render, &st);
+    double msamples = (double)cfg.width * cfg.height * cfg.spp / (st.ms_total * 1e3);
+    printf("{\"triangles\": %llu, \"nodes\": %llu, \"materials\": %u, \"lights\": %u, \"load_ms\": %.2f, \"bvh_build_gpu_ms\": %.3f, "
+           "\"upload_and_build_ms\": %.2f, \"render_ms\": %.3f, \"render_wall_ms\": %.2f, \"msamples_per_s\": %.2f, "
+           "\"extend_rays\": %llu, \"shadow_rays\": %llu, \"probe_rays\": %llu, \"iterations\": %llu, \"out\": \"%s\"}\n",
+           (unsigned long long)n_tris, (unsigned long long)n_nodes, n_mats, n_lights, t1 - t0, build_ms, t2 - t1, st.ms_total, t4 - t3,
+           msamples, (unsigned long long)st.extend_rays, (unsigned long long)st.shadow_rays, (unsigned long long)st.probe_rays,
+           (unsigned long long)st.iterations, out.c_str());
+    crt_render_destroy(render);
+    crt_scene_destroy(scene);
+    return 0;
+}

@@ -1,0 +1,671 @@
+// crt_render.cu — ray-batch kernels and the wavefront path tracer.
+//
+// Replaces the reference's single per-pixel megakernel (include/Render.cuh:330-354 view_render_kernel
+// + cast_ray_v2 :199-328 + per-pixel global-memory stacks, DeviceStack.cuh) by a wavefront:
+//     prepare -> generate -> extend -> [probe] -> shade -> shadow        (one iteration)
+// over a fixed pool of in-flight paths that is refilled with new camera paths every iteration
+// (path regeneration), with double-buffered compacted queues (warp-aggregated atomics), persistent
+// warps that fetch 32 rays at a time, counter-based Philox draws keyed by (pixel, sample, bounce,
+// dimension), and an order-independent fixed-point accumulation buffer.
+// The estimator arithmetic mirrors oracle/orc_render.cpp operation by operation (-fmad=false).
+#include "crt_gpu.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace crt {
+
+// =============================================================================================
+// scene upload
+// =============================================================================================
+void DeviceScene::release() {
+    cudaFree(nodes); cudaFree(tri_geom); cudaFree(tri_shade); cudaFree(order); cudaFree(last);
+    cudaFree(mats); cudaFree(light_tris); cudaFree(lights);
+    nodes = tri_geom = tri_shade = mats = light_tris = nullptr;
+    order = nullptr; last = nullptr; lights = nullptr;
+    n_tris = n_nodes = n_mats = n_lights = n_light_tris = 0;
+}
+
+static inline float bits_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene& ds, float* build_ms) {
+    CRT_CUDA(cudaSetDevice(device));
+    ds.release();
+    ds.device = device;
+    const size_t n = hs.n_tris();
+    if (n > 0x7fffffffu / 4) { set_error("scene too large (more than 2^29 triangles)"); return CRT_ERR_INVALID; }
+    // materials: (kd, ns) (ke, flags) (probe_dtheta, probe_dphi, probe_shin, 0) (ks, 0)
+    std::vector<float4> mats(hs.mats.size() * 4);
+    ds.has_specular = false;
+    for (size_t m = 0; m < hs.mats.size(); ++m) {
+        const HostMaterial& hm = hs.mats[m];
+        uint32_t flags = (hm.has_emit ? 1u : 0u) | (hm.mode == 1 ? 2u : 0u);
+        if (hm.mode == 1 && !hm.has_emit) ds.has_specular = true;
+        mats[4 * m + 0] = make_float4(hm.kd[0], hm.kd[1], hm.kd[2], hm.ns);
+        mats[4 * m + 1] = make_float4(hm.ke[0], hm.ke[1], hm.ke[2], bits_f(flags));
+        mats[4 * m + 2] = make_float4(hm.probe_dtheta, hm.probe_dphi, hm.probe_shin, 0.0f);
+        mats[4 * m + 3] = make_float4(hm.ks[0], hm.ks[1], hm.ks[2], 0.0f);
+    }
+    // lights (DeviceLights.cuh:63-87): object table + flat triangle table
+    std::vector<int4> lights;
+    std::vector<float4> ltris;
+    for (const HostLight& L : hs.lights) {
+        int4 rec;
+        rec.x = (int)(ltris.size() / 4);
+        rec.y = (int)L.faces.size();
+        uint32_t ab; memcpy(&ab, &L.area, 4);
+        rec.z = (int)ab;
+        rec.w = 0;
+        lights.push_back(rec);
+        for (int32_t f : L.faces) {
+            const float* v = &hs.verts[9 * (size_t)f];
+            const float* nn = &hs.normal[3 * (size_t)f];
+            const HostMaterial& hm = hs.mats[hs.mat[f]];
+            ltris.push_back(make_float4(v[0], v[1], v[2], hm.ke[0]));
+            ltris.push_back(make_float4(v[3], v[4], v[5], hm.ke[1]));
+            ltris.push_back(make_float4(v[6], v[7], v[8], hm.ke[2]));
+            ltris.push_back(make_float4(nn[0], nn[1], nn[2], 0.0f));
+        }
+    }
+    ds.n_mats = (uint32_t)hs.mats.size();
+    ds.n_lights = (uint32_t)lights.size();
+    ds.n_light_tris = (uint32_t)(ltris.size() / 4);
+    if (!mats.empty()) {
+        CRT_CUDA(cudaMalloc(&ds.mats, sizeof(float4) * mats.size()));
+        CRT_CUDA(cudaMemcpy(ds.mats, mats.data(), sizeof(float4) * mats.size(), cudaMemcpyHostToDevice));
+    }
+    if (!lights.empty()) {
+        CRT_CUDA(cudaMalloc(&ds.lights, sizeof(int4) * lights.size()));
+        CRT_CUDA(cudaMemcpy(ds.lights, lights.data(), sizeof(int4) * lights.size(), cudaMemcpyHostToDevice));
+        CRT_CUDA(cudaMalloc(&ds.light_tris, sizeof(float4) * ltris.size()));
+        CRT_CUDA(cudaMemcpy(ds.light_tris, ltris.data(), sizeof(float4) * ltris.size(), cudaMemcpyHostToDevice));
+    }
+    // geometry in face order for the builder
+    float* d_verts = nullptr;
+    float4* d_shade = nullptr;
+    int rc = CRT_OK;
+    if (n > 0) {
+        std::vector<float4> shade(n);
+        for (size_t t = 0; t < n; ++t)
+            shade[t] = make_float4(hs.normal[3 * t], hs.normal[3 * t + 1], hs.normal[3 * t + 2], bits_f((uint32_t)hs.mat[t]));
+        CRT_CUDA(cudaMalloc(&d_verts, sizeof(float) * 9 * n));
+        cudaError_t e = cudaMalloc(&d_shade, sizeof(float4) * n);
+        if (e != cudaSuccess) { cudaFree(d_verts); return cuda_fail(e, "cudaMalloc face_shade"); }
+        cudaMemcpy(d_verts, hs.verts.data(), sizeof(float) * 9 * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_shade, shade.data(), sizeof(float4) * n, cudaMemcpyHostToDevice);
+    }
+    rc = build_bvh_device(ds, d_verts, d_shade, (uint32_t)n, thresh_n, 0, build_ms);
+    cudaFree(d_verts);
+    cudaFree(d_shade);
+    return rc;
+}
+
+// =============================================================================================
+// ray batches
+// =============================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(128) k_trace_batch(SceneView sc, const float4* __restrict__ rays, unsigned long long n,
+                                                     float* __restrict__ t_out, int* __restrict__ face_out,
+                                                     unsigned long long* __restrict__ fetch) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(fetch, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned long long i = base + lane;
+        if (i < n) {
+            float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+            HitRec h = traverse<MODE>(sc, mk3(ro), mk3(rd), ro.w);
+            if (t_out) t_out[i] = h.t;
+            if (face_out) face_out[i] = h.face;
+        }
+    }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
+                      cudaStream_t st, float* kernel_ms) {
+    unsigned long long* fetch = nullptr;
+    CRT_CUDA(cudaMalloc(&fetch, sizeof(unsigned long long)));
+    cudaMemsetAsync(fetch, 0, sizeof(unsigned long long), st);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    int blocks = num_sms() * 16;
+    cudaEventRecord(a, st);
+    if (mode == CRT_RAY_CLOSEST) k_trace_batch<0><<<blocks, 128, 0, st>>>(ds.view(), d_rays, n, d_t, d_face, fetch);
+    else k_trace_batch<1><<<blocks, 128, 0, st>>>(ds.view(), d_rays, n, d_t, d_face, fetch);
+    cudaEventRecord(b, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    float ms = 0;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(fetch);
+    if (e != cudaSuccess) return cuda_fail(e, "k_trace_batch");
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_trace_batch launch");
+    if (kernel_ms) *kernel_ms = ms;
+    return CRT_OK;
+}
+
+// =============================================================================================
+// wavefront state
+// =============================================================================================
+struct Counters {
+    unsigned long long work_next, work_end, gen_work0;
+    unsigned long long stat_extend, stat_shadow, stat_probe;
+    uint32_t n_cur, n_next, n_shadow, n_probe_cur, n_probe_next;
+    uint32_t gen_base, gen_count;
+    uint32_t fetch_extend, fetch_shadow, fetch_probe;
+    uint32_t iterations;
+};
+struct HostStatus { volatile uint32_t done; volatile uint32_t n_cur; volatile unsigned long long work_next; };
+
+struct RenderParamsDev {
+    float eye[3];
+    float M[9];
+    float tan_half;
+    uint32_t width, height;
+    unsigned long long n_pixels;
+    uint32_t s_begin;
+    float p_rr;
+    int light_sample_n;
+    uint32_t seed;
+    int max_vertices;
+};
+
+static constexpr uint32_t kFlagProbe = 0x100u;
+
+struct Wavefront {
+    uint32_t width = 0, height = 0;
+    uint32_t pool = 0;             // path slots per queue
+    uint32_t shadow_cap = 0;
+    bool has_probe = false;
+    float4 *q_o[2] = {nullptr, nullptr}, *q_d[2] = {nullptr, nullptr}, *q_T[2] = {nullptr, nullptr};
+    float* hit_t = nullptr;
+    int* hit_slot = nullptr;
+    float4 *pr_o[2] = {nullptr, nullptr}, *pr_d[2] = {nullptr, nullptr}, *pr_w[2] = {nullptr, nullptr};
+    uint32_t* pr_list[2] = {nullptr, nullptr};
+    int* pr_hit = nullptr;
+    float4 *sh_o = nullptr, *sh_d = nullptr, *sh_c = nullptr;
+    long long* accum = nullptr;
+    Counters* counters = nullptr;
+    HostStatus* status_host = nullptr;
+    HostStatus* status_dev = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    int grid_trace = 0, grid_shade = 0;
+};
+
+// =============================================================================================
+// kernels
+// =============================================================================================
+__global__ void k_prepare(Counters* c, uint32_t pool, HostStatus* status) {
+    c->stat_shadow += c->n_shadow;
+    uint32_t n_cur = c->n_next;
+    c->n_probe_cur = c->n_probe_next;
+    c->n_next = 0;
+    c->n_probe_next = 0;
+    c->n_shadow = 0;
+    unsigned long long remaining = c->work_end - c->work_next;
+    uint32_t room = pool - n_cur;
+    uint32_t n_new = remaining < (unsigned long long)room ? (uint32_t)remaining : room;
+    c->gen_base = n_cur;
+    c->gen_count = n_new;
+    c->gen_work0 = c->work_next;
+    n_cur += n_new;
+    c->work_next += n_new;
+    c->n_cur = n_cur;
+    c->fetch_extend = c->fetch_shadow = c->fetch_probe = 0;
+    c->stat_extend += n_cur;
+    c->iterations += n_cur ? 1u : 0u;
+    status->n_cur = n_cur;
+    status->work_next = c->work_next;
+    if (n_cur == 0) status->done = 1;
+    __threadfence_system();
+}
+
+// Primary rays: reference Render.cuh:338-347 + Ray.cuh:12-15. Work item w -> (sample, pixel) with
+// consecutive items on consecutive pixels of one sample index (coherent warps, distinct pixels).
+__global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c, RenderParamsDev p, float4* __restrict__ q_o,
+                                                  float4* __restrict__ q_d, float4* __restrict__ q_T) {
+    const uint32_t count = c->gen_count, base = c->gen_base;
+    const unsigned long long w0 = c->gen_work0;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        unsigned long long w = w0 + k;
+        uint32_t pixel = (uint32_t)(w % p.n_pixels);
+        uint32_t sample = p.s_begin + (uint32_t)(w / p.n_pixels);
+        uint32_t i = pixel % p.width, j = pixel / p.width;
+        uint4 r = draw(pixel, sample, kCameraBounce, 0, p.seed);
+        float u1 = u01(r.x), u2 = u01(r.y);
+        float ar = (float)p.width / (float)p.height;
+        float x = (2.0f * ((float)i + u1) / (float)p.width - 1.0f) * p.tan_half * ar;
+        float y = (1.0f - 2.0f * ((float)j + u2) / (float)p.height) * p.tan_half;
+        V3 dc = normalize(mk3(-x, y, 1.0f));
+        V3 d = mk3(dot(mk3(p.M[0], p.M[1], p.M[2]), dc), dot(mk3(p.M[3], p.M[4], p.M[5]), dc), dot(mk3(p.M[6], p.M[7], p.M[8]), dc));
+        d = normalize(d);
+        q_o[base + k] = make_float4(p.eye[0], p.eye[1], p.eye[2], __uint_as_float(pixel));
+        q_d[base + k] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
+        q_T[base + k] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+    }
+}
+
+__global__ void __launch_bounds__(128) k_extend(SceneView sc, Counters* c, const float4* __restrict__ q_o,
+                                                const float4* __restrict__ q_d, float* __restrict__ hit_t,
+                                                int* __restrict__ hit_slot) {
+    const uint32_t n = c->n_cur;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&c->fetch_extend, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            float4 o = q_o[i], d = q_d[i];
+            HitRec h = traverse<0>(sc, mk3(o), mk3(d), FLT_MAX);
+            hit_t[i] = h.t;
+            hit_slot[i] = h.slot;
+        }
+    }
+}
+
+// SPECULAR probe rays (reference Render.cuh:303): traced only when the continuation ray hit.
+__global__ void __launch_bounds__(128) k_probe(SceneView sc, Counters* c, const uint32_t* __restrict__ list,
+                                               const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
+                                               const int* __restrict__ hit_slot, int* __restrict__ pr_hit) {
+    const uint32_t n = c->n_probe_cur;
+    const int lane = threadIdx.x & 31;
+    unsigned long long traced = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&c->fetch_probe, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t k = base + lane;
+        if (k < n) {
+            uint32_t i = list[k];
+            int res = -1;
+            if (hit_slot[i] >= 0) {
+                float4 o = pr_o[i], d = pr_d[i];
+                HitRec h = traverse<0>(sc, mk3(o), mk3(d), FLT_MAX);
+                res = h.slot;
+                traced++;
+            }
+            pr_hit[i] = res;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
+    if (lane == 0 && traced) atomicAdd(&c->stat_probe, traced);
+}
+
+// Global.h:35-50
+CRT_DEV V3 to_world(V3 a, V3 N) {
+    V3 C;
+    if (fabsf(N.x) > fabsf(N.y)) {
+        float inv = 1.0f / sqrtf(fmaf(N.z, N.z, N.x * N.x));
+        C = mk3(N.z * inv, 0.0f, -N.x * inv);
+    } else {
+        float inv = 1.0f / sqrtf(fmaf(N.z, N.z, N.y * N.y));
+        C = mk3(0.0f, N.z * inv, -N.y * inv);
+    }
+    V3 B = cross(C, N);
+    return (a.x * B + a.y * C) + a.z * N;
+}
+// Global.h:57-66
+CRT_DEV V3 sample_hemisphere(V3 N, float u1, float u2) {
+    float z = fabsf(1.0f - 2.0f * u1);
+    float r = sqrtf(1.0f - z * z);
+    float sn, cs;
+    sincos_2pi(u2, &sn, &cs);
+    return to_world(mk3(r * cs, r * sn, z), N);
+}
+// Global.h:68-94 by angle addition
+CRT_DEV V3 sample_probe_lobe(V3 out, float dtheta, float dphi, float u1, float u2) {
+    float eta1 = 2.0f * u1 - 1.0f, eta2 = 2.0f * u2 - 1.0f;
+    float r = length(out);
+    float ct0 = out.z / r;
+    ct0 = fminf(1.0f, fmaxf(-1.0f, ct0));
+    float st0 = sqrtf(fmaxf(0.0f, 1.0f - ct0 * ct0));
+    float cp0, sp0;
+    if (fabsf(out.x) < 1e-5f) {
+        cp0 = 0.0f;
+        sp0 = out.y > 0.0f ? 1.0f : -1.0f;
+    } else {
+        float rho = sqrtf(fmaf(out.y, out.y, out.x * out.x));
+        cp0 = out.x / rho;
+        sp0 = out.y / rho;
+    }
+    float sa, ca, sb, cb;
+    sincos_rad(eta1 * dtheta, &sa, &ca);
+    sincos_rad(eta2 * dphi, &sb, &cb);
+    float st = fmaf(st0, ca, ct0 * sa), ct = fmaf(ct0, ca, -(st0 * sa));
+    float sp = fmaf(sp0, cb, cp0 * sb), cp = fmaf(cp0, cb, -(sp0 * sb));
+    return mk3(st * cp, st * sp, ct);
+}
+
+// compat estimator, one path vertex per thread: the forward form of cast_ray_v2
+// (reference Render.cuh:199-328); statement shared with oracle/orc_render.cpp path_compat.
+__global__ void __launch_bounds__(128) k_shade_compat(SceneView sc, Counters* c, RenderParamsDev p,
+                                                      const float4* __restrict__ q_o, const float4* __restrict__ q_d,
+                                                      const float4* __restrict__ q_T, const float* __restrict__ hit_t,
+                                                      const int* __restrict__ hit_slot, const float4* __restrict__ pr_w_cur,
+                                                      const int* __restrict__ pr_hit, float4* __restrict__ n_o,
+                                                      float4* __restrict__ n_d, float4* __restrict__ n_T,
+                                                      float4* __restrict__ pr_o_next, float4* __restrict__ pr_d_next,
+                                                      float4* __restrict__ pr_w_next, uint32_t* __restrict__ pr_list_next,
+                                                      float4* __restrict__ sh_o, float4* __restrict__ sh_d,
+                                                      float4* __restrict__ sh_c, long long* __restrict__ accum) {
+    const uint32_t n = c->n_cur;
+    const float lsn_f = (float)p.light_sample_n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 qo = q_o[i], qd = q_d[i], qT = q_T[i];
+        const uint32_t pixel = __float_as_uint(qo.w), sample = __float_as_uint(qd.w), meta = __float_as_uint(qT.w);
+        const uint32_t bounce = meta & 0xffu;
+        const int slot = hit_slot[i];
+        if (meta & kFlagProbe) {                                   // Render.cuh:294-314
+            if (slot >= 0) {
+                int ps = pr_hit[i];
+                if (ps >= 0) {
+                    uint32_t pm = __float_as_uint(__ldg(sc.tri_shade + ps).w);
+                    float4 m1 = __ldg(sc.mats + 4 * pm + 1);
+                    if (__float_as_uint(m1.w) & 1u) accum_add(accum, pixel, cmul(mk3(pr_w_cur[i]), mk3(m1)));
+                }
+            }
+        }
+        if (slot < 0) continue;                                     // miss, :210
+        const float4 sh = __ldg(sc.tri_shade + slot);
+        const uint32_t mat = __float_as_uint(sh.w);
+        const float4 m0 = __ldg(sc.mats + 4 * mat + 0), m1 = __ldg(sc.mats + 4 * mat + 1);
+        const uint32_t mflags = __float_as_uint(m1.w);
+        if (mflags & 1u) {                                          // emissive vertex, :210,249-255
+            if (bounce == 0) accum_add(accum, pixel, mk3(m1));
+            continue;
+        }
+        const V3 o = mk3(qo), d = mk3(qd), T = mk3(qT);
+        const V3 pos = o + hit_t[i] * d;                            // DeviceTriangle.cuh:50
+        const V3 nrm = mk3(sh);
+        const V3 f_r = mk3(m0) / kPi;                               // :259
+        const V3 Tf = cmul(T, f_r);
+        // next-event estimation, :262-286
+        for (int li = 0; li < sc.n_lights; ++li) {
+            const int4 L = __ldg(sc.lights + li);
+            const float area = __int_as_float(L.z);
+            for (int sj = 0; sj < p.light_sample_n; ++sj) {
+                uint4 q = draw(pixel, sample, bounce, 2u + (uint32_t)(li * p.light_sample_n + sj), p.seed);
+                const float4* lt = sc.light_tris + 4 * (size_t)(L.x + (int)(q.x % (uint32_t)L.y));   // DeviceLights.cuh:35
+                const float4 a = __ldg(lt), b = __ldg(lt + 1), cc = __ldg(lt + 2), ln = __ldg(lt + 3);
+                float alpha = u01(q.y);                             // DeviceTriangle.cuh:69-72
+                float beta = u01(q.z) * (1.0f - alpha);
+                float gamma = (1.0f - alpha) - beta;
+                V3 lp = (alpha * mk3(a) + beta * mk3(b)) + gamma * mk3(cc);
+                V3 dist = lp - pos;
+                V3 dir = normalize(dist);
+                float d1 = length(dist);
+                float d2 = d1 * d1;
+                float cos1 = fmaxf(0.0f, dot(dir, nrm));
+                float cos2 = fmaxf(0.0f, -dot(dir, mk3(ln)));
+                V3 contrib = cmul(mk3(a.w, b.w, cc.w), Tf) * cos1 * cos2 * area / d2 / lsn_f;     // :274-283
+                bool live = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);
+                float t_to_light = dist.x / dir.x;                  // :272
+                bool needs_trace = live && (t_to_light == t_to_light);
+                if (live && !needs_trace) accum_add(accum, pixel, contrib);   // NaN: never blocked, :19-27
+                int k = warp_append(&c->n_shadow, needs_trace);
+                if (k >= 0) {
+                    V3 rd = normalize(dir);                          // Ray ctor normalises again
+                    sh_o[k] = make_float4(pos.x, pos.y, pos.z, t_to_light);
+                    sh_d[k] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(pixel));
+                    sh_c[k] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+                }
+            }
+        }
+        bool alive = bounce != (uint32_t)(p.max_vertices - 1);      // bounce stack full, :210
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (alive) {
+            q = draw(pixel, sample, bounce, 0, p.seed);
+            alive = !(u01(q.x) > p.p_rr);                            // :216-221
+        }
+        int k = warp_append(&c->n_next, alive);
+        if (k < 0) continue;
+        V3 wdir = normalize(normalize(sample_hemisphere(nrm, u01(q.y), u01(q.z))));   // :225-227 + Ray ctor
+        uint32_t nmeta = bounce + 1u;
+        if (mflags & 2u) {                                          // SPECULAR probe, :294-303
+            const float4 m2 = __ldg(sc.mats + 4 * mat + 2);
+            V3 in = normalize(d);
+            V3 out = in - (2.0f * dot(in, nrm)) * nrm;
+            uint4 e = draw(pixel, sample, bounce, 1, p.seed);
+            V3 pd = normalize(normalize(sample_probe_lobe(out, m2.x, m2.y, u01(e.x), u01(e.y))));
+            float pc = fmaxf(0.0f, dot(pd, nrm));
+            V3 pw = cmul(T, mk3(m0)) * m2.z * pc * (kTwoPi / 8.0f);  // :306-312
+            pr_o_next[k] = make_float4(pos.x, pos.y, pos.z, 0.0f);
+            pr_d_next[k] = make_float4(pd.x, pd.y, pd.z, 0.0f);
+            pr_w_next[k] = make_float4(pw.x, pw.y, pw.z, 0.0f);
+            int pk = warp_append(&c->n_probe_next, true);
+            pr_list_next[pk] = (uint32_t)k;
+            nmeta |= kFlagProbe;
+        }
+        float cosn = fmaxf(0.0f, dot(wdir, nrm));
+        V3 Tn = Tf * cosn * kTwoPi / p.p_rr;                        // :288-293
+        n_o[k] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel));
+        n_d[k] = make_float4(wdir.x, wdir.y, wdir.z, __uint_as_float(sample));
+        n_T[k] = make_float4(Tn.x, Tn.y, Tn.z, __uint_as_float(nmeta));
+    }
+}
+
+// Shadow rays: the decision of blocked() (reference Render.cuh:19-27) with an any-hit traversal.
+__global__ void __launch_bounds__(128) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
+                                                const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
+                                                long long* __restrict__ accum) {
+    const uint32_t n = c->n_shadow;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&c->fetch_shadow, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        if (i < n) {
+            float4 o = sh_o[i], d = sh_d[i];
+            HitRec h = traverse<1>(sc, mk3(o), mk3(d), o.w);
+            if (h.slot < 0) accum_add(accum, __float_as_uint(d.w), mk3(sh_c[i]));
+        }
+    }
+}
+
+// E11 (reference Render.cuh:348,350): mean over spp, clamp, pow 0.6, *255, truncate.
+__global__ void k_resolve(const long long* __restrict__ accum, uint32_t n_values, uint32_t spp, float* __restrict__ linear,
+                          uint8_t* __restrict__ rgb8) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_values) return;
+    float v = (float)((double)accum[k] / 4294967296.0 / (double)spp);
+    if (linear) linear[k] = v;
+    if (rgb8) {
+        float cl = fmaxf(0.0f, fminf(1.0f, v));
+        rgb8[k] = (uint8_t)(255.0f * powf(cl, 0.6f));
+    }
+}
+
+int resolve_device(const long long* d_accum, uint32_t n_pixels, uint32_t spp, float* d_linear, uint8_t* d_rgb8, cudaStream_t st) {
+    uint32_t nv = n_pixels * 3;
+    k_resolve<<<(nv + 255) / 256, 256, 0, st>>>(d_accum, nv, spp ? spp : 1, d_linear, d_rgb8);
+    CRT_CUDA(cudaGetLastError());
+    return CRT_OK;
+}
+
+// =============================================================================================
+// host driver
+// =============================================================================================
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (uint32_t)strtoul(v, nullptr, 0);
+}
+
+int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wavefront** out) {
+    Wavefront* w = new Wavefront();
+    w->width = width; w->height = height;
+    w->has_probe = ds.has_specular;
+    const size_t npix = (size_t)width * height;
+    CRT_CUDA(cudaMalloc(&w->accum, sizeof(long long) * 3 * npix));
+    CRT_CUDA(cudaMalloc(&w->counters, sizeof(Counters)));
+    CRT_CUDA(cudaHostAlloc((void**)&w->status_host, sizeof(HostStatus), cudaHostAllocMapped));
+    CRT_CUDA(cudaHostGetDevicePointer((void**)&w->status_dev, (void*)w->status_host, 0));
+    for (int k = 0; k < 4; ++k) CRT_CUDA(cudaEventCreateWithFlags(&w->ev[k], cudaEventDisableTiming));
+    CRT_CUDA(cudaEventCreate(&w->ev_begin));
+    CRT_CUDA(cudaEventCreate(&w->ev_end));
+    int occ = 0;
+    CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, 128, 0));
+    w->grid_trace = num_sms() * std::max(occ, 1);
+    w->grid_shade = num_sms() * 8;
+    *out = w;
+    return CRT_OK;
+}
+
+static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs) {
+    uint32_t pool = env_u32("CRT_POOL", 1u << 20);
+    uint64_t per_vertex = (uint64_t)std::max<uint32_t>(ds.n_lights, 1) * std::max<uint32_t>(rs.light_sample_n, 1);
+    const uint64_t shadow_budget = 1ull << 25;        // 32 Mi shadow rays in flight at most (1.5 GiB)
+    while (pool > 4096 && (uint64_t)pool * per_vertex > shadow_budget) pool >>= 1;
+    uint64_t shadow_cap = (uint64_t)pool * per_vertex;
+    if (shadow_cap > 0xffffffffull) { set_error("light_sample_n x lights too large"); return CRT_ERR_INVALID; }
+    if (w->pool == pool && w->shadow_cap >= shadow_cap) return CRT_OK;
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(w->q_o[b]); cudaFree(w->q_d[b]); cudaFree(w->q_T[b]);
+        cudaFree(w->pr_o[b]); cudaFree(w->pr_d[b]); cudaFree(w->pr_w[b]); cudaFree(w->pr_list[b]);
+        w->q_o[b] = w->q_d[b] = w->q_T[b] = w->pr_o[b] = w->pr_d[b] = w->pr_w[b] = nullptr;
+        w->pr_list[b] = nullptr;
+    }
+    cudaFree(w->hit_t); cudaFree(w->hit_slot); cudaFree(w->pr_hit); cudaFree(w->sh_o); cudaFree(w->sh_d); cudaFree(w->sh_c);
+    w->hit_t = nullptr; w->hit_slot = nullptr; w->pr_hit = nullptr; w->sh_o = w->sh_d = w->sh_c = nullptr;
+    for (int b = 0; b < 2; ++b) {
+        CRT_CUDA(cudaMalloc(&w->q_o[b], sizeof(float4) * pool));
+        CRT_CUDA(cudaMalloc(&w->q_d[b], sizeof(float4) * pool));
+        CRT_CUDA(cudaMalloc(&w->q_T[b], sizeof(float4) * pool));
+        if (w->has_probe) {
+            CRT_CUDA(cudaMalloc(&w->pr_o[b], sizeof(float4) * pool));
+            CRT_CUDA(cudaMalloc(&w->pr_d[b], sizeof(float4) * pool));
+            CRT_CUDA(cudaMalloc(&w->pr_w[b], sizeof(float4) * pool));
+            CRT_CUDA(cudaMalloc(&w->pr_list[b], sizeof(uint32_t) * pool));
+        }
+    }
+    CRT_CUDA(cudaMalloc(&w->hit_t, sizeof(float) * pool));
+    CRT_CUDA(cudaMalloc(&w->hit_slot, sizeof(int) * pool));
+    if (w->has_probe) CRT_CUDA(cudaMalloc(&w->pr_hit, sizeof(int) * pool));
+    CRT_CUDA(cudaMalloc(&w->sh_o, sizeof(float4) * shadow_cap));
+    CRT_CUDA(cudaMalloc(&w->sh_d, sizeof(float4) * shadow_cap));
+    CRT_CUDA(cudaMalloc(&w->sh_c, sizeof(float4) * shadow_cap));
+    w->pool = pool;
+    w->shadow_cap = (uint32_t)shadow_cap;
+    return CRT_OK;
+}
+
+void wavefront_destroy(Wavefront* w) {
+    if (!w) return;
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(w->q_o[b]); cudaFree(w->q_d[b]); cudaFree(w->q_T[b]);
+        cudaFree(w->pr_o[b]); cudaFree(w->pr_d[b]); cudaFree(w->pr_w[b]); cudaFree(w->pr_list[b]);
+    }
+    cudaFree(w->hit_t); cudaFree(w->hit_slot); cudaFree(w->pr_hit);
+    cudaFree(w->sh_o); cudaFree(w->sh_d); cudaFree(w->sh_c);
+    cudaFree(w->accum); cudaFree(w->counters);
+    if (w->status_host) cudaFreeHost((void*)w->status_host);
+    for (int k = 0; k < 4; ++k) if (w->ev[k]) cudaEventDestroy(w->ev[k]);
+    if (w->ev_begin) cudaEventDestroy(w->ev_begin);
+    if (w->ev_end) cudaEventDestroy(w->ev_end);
+    delete w;
+}
+
+long long* wavefront_accum(Wavefront* w) { return w->accum; }
+
+int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
+                     float tan_half, cudaStream_t st, crt_render_stats* stats) {
+    if (rs.estimator != CRT_ESTIMATOR_COMPAT) { set_error("estimator not implemented"); return CRT_ERR_INVALID; }
+    int rc = ensure_pool(w, ds, rs);
+    if (rc != CRT_OK) return rc;
+    const uint32_t s_begin = rs.range_set ? rs.s_begin : 0, s_end = rs.range_set ? rs.s_end : rs.spp;
+    const size_t npix = (size_t)w->width * w->height;
+    RenderParamsDev p;
+    memcpy(p.eye, eye, sizeof(p.eye));
+    memcpy(p.M, M, sizeof(p.M));
+    p.tan_half = tan_half;
+    p.width = w->width; p.height = w->height; p.n_pixels = npix;
+    p.s_begin = s_begin; p.p_rr = rs.p_rr; p.light_sample_n = (int)rs.light_sample_n; p.seed = rs.seed;
+    p.max_vertices = 64;                                           // BOUNCE_STACK_SIZE, Global.h:18
+    Counters h;
+    memset(&h, 0, sizeof(h));
+    h.work_end = (unsigned long long)npix * (s_end > s_begin ? (s_end - s_begin) : 0);
+    w->status_host->done = 0;
+    w->status_host->n_cur = 0;
+    CRT_CUDA(cudaEventRecord(w->ev_begin, st));
+    CRT_CUDA(cudaMemsetAsync(w->accum, 0, sizeof(long long) * 3 * npix, st));
+    CRT_CUDA(cudaMemcpyAsync(w->counters, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    const SceneView sv = ds.view();
+    uint64_t launches = 0;
+    float ms_stage[4] = {0, 0, 0, 0};
+    cudaEvent_t se[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (rs.stage_timing) for (auto& e : se) cudaEventCreate(&e);
+    uint32_t it = 0;
+    for (;; ++it) {
+        if (it >= 2) {
+            CRT_CUDA(cudaEventSynchronize(w->ev[(it - 2) & 3]));
+            if (w->status_host->done) break;
+        }
+        const int cur = it & 1, nxt = cur ^ 1;
+        k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, w->status_dev);
+        if (rs.stage_timing) cudaEventRecord(se[0], st);
+        k_generate<<<w->grid_shade, 256, 0, st>>>(w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur]);
+        if (rs.stage_timing) cudaEventRecord(se[1], st);
+        k_extend<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->q_o[cur], w->q_d[cur], w->hit_t, w->hit_slot);
+        launches += 3;
+        if (w->has_probe) {
+            k_probe<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->pr_list[cur], w->pr_o[cur], w->pr_d[cur], w->hit_slot, w->pr_hit);
+            launches++;
+        }
+        if (rs.stage_timing) cudaEventRecord(se[2], st);
+        k_shade_compat<<<w->grid_shade, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->hit_t,
+                                                       w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt], w->q_d[nxt],
+                                                       w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
+                                                       w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum);
+        if (rs.stage_timing) cudaEventRecord(se[3], st);
+        k_shadow<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum);
+        launches += 2;
+        if (rs.stage_timing) {
+            cudaEventRecord(se[4], st);
+            cudaEventSynchronize(se[4]);
+            for (int k = 0; k < 4; ++k) { float ms = 0; cudaEventElapsedTime(&ms, se[k], se[k + 1]); ms_stage[k] += ms; }
+        }
+        CRT_CUDA(cudaEventRecord(w->ev[it & 3], st));
+        CRT_CUDA(cudaGetLastError());
+    }
+    CRT_CUDA(cudaEventRecord(w->ev_end, st));
+    CRT_CUDA(cudaStreamSynchronize(st));
+    if (rs.stage_timing) for (auto& e : se) cudaEventDestroy(e);
+    if (stats) {
+        CRT_CUDA(cudaMemcpy(&h, w->counters, sizeof(h), cudaMemcpyDeviceToHost));
+        memset(stats, 0, sizeof(*stats));
+        stats->samples = h.work_end;
+        stats->extend_rays = h.stat_extend;
+        stats->shadow_rays = h.stat_shadow + h.n_shadow;
+        stats->probe_rays = h.stat_probe;
+        stats->iterations = h.iterations;
+        stats->kernel_launches = launches;
+        CRT_CUDA(cudaEventElapsedTime(&stats->ms_total, w->ev_begin, w->ev_end));
+        stats->ms_generate = ms_stage[0]; stats->ms_extend = ms_stage[1]; stats->ms_shade = ms_stage[2]; stats->ms_shadow = ms_stage[3];
+    }
+    return CRT_OK;
+}
+
+}  // namespace crt

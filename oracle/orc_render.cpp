@@ -153,21 +153,21 @@ static void path_compat(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sam
                 V3 lp = (alpha * lt.v1 + beta * lt.v2) + gamma * lt.v3;
                 V3 dist = lp - pos;
                 V3 dir = normalize(dist);
-                float t_to_light = dist.x / dir.x;                        // :272
-                bool blocked = false;
-                if (t_to_light == t_to_light) {                           // NaN => never "blocked" (:19-27)
-                    Ray sh{pos, normalize(dir), t_to_light};
-                    Hit bh = new_intersect(s, c.b, sh, 1, &st->any);
-                    st->shadow_rays++;
-                    blocked = bh.face >= 0;
-                }
-                if (blocked) continue;
                 float d1 = length(dist);
                 float d2 = d1 * d1;
                 float cos1 = fmaxf(0.0f, dot(dir, n));
                 float cos2 = fmaxf(0.0f, -dot(dir, lt.normal));
                 const Material& lm = s.mats[lt.mat];
-                V3 contrib = cmul(lm.ke, Tf) * cos1 * cos2 * L.area / d2 / lsn_f;   // :283
+                V3 contrib = cmul(lm.ke, Tf) * cos1 * cos2 * L.area / d2 / lsn_f;   // :274-283
+                // a sample that cannot contribute needs no visibility test (the reference traces it anyway)
+                if (contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f) continue;
+                float t_to_light = dist.x / dir.x;                        // :272
+                if (t_to_light == t_to_light) {                           // NaN => never "blocked" (:19-27)
+                    Ray sh{pos, normalize(dir), t_to_light};
+                    Hit bh = new_intersect(s, c.b, sh, 1, &st->any);
+                    st->shadow_rays++;
+                    if (bh.face >= 0) continue;
+                }
                 add_contrib(px, contrib);
             }
         }
