@@ -90,6 +90,8 @@ def load_library():
         "crt_render_set_seed": [vp, u32],
         "crt_render_set_estimator": [vp, i32],
         "crt_render_set_sample_range": [vp, u32, u32],
+        "crt_render_set_work_range": [vp, u64, u64],
+        "crt_render_clear_range": [vp],
         "crt_render_set_stream": [vp, vp],
         "crt_render_set_stage_timing": [vp, i32],
         "crt_render_run_view": [vp, vp, vp, f32],
@@ -301,6 +303,12 @@ class Render:
 
     def set_sample_range(self, begin, end):
         _check(self.L.crt_render_set_sample_range(self.h, begin, end))
+
+    def set_work_range(self, begin, end):
+        _check(self.L.crt_render_set_work_range(self.h, begin, end))
+
+    def clear_range(self):
+        _check(self.L.crt_render_clear_range(self.h))
 
     def set_stream(self, cuda_stream):
         _check(self.L.crt_render_set_stream(self.h, cuda_stream))

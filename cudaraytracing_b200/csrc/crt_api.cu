@@ -269,7 +269,18 @@ int crt_render_set_estimator(crt_render* r, int estimator) {
 }
 int crt_render_set_sample_range(crt_render* r, uint32_t begin, uint32_t end) {
     CHECK_ARG(r && begin <= end, "crt_render_set_sample_range: invalid range");
-    r->rs.s_begin = begin; r->rs.s_end = end; r->rs.range_set = true;
+    const unsigned long long npix = (unsigned long long)r->rs.width * r->rs.height;
+    r->rs.work_begin = npix * begin; r->rs.work_end = npix * end; r->rs.range_set = true;
+    return CRT_OK;
+}
+int crt_render_set_work_range(crt_render* r, uint64_t begin, uint64_t end) {
+    CHECK_ARG(r && begin <= end, "crt_render_set_work_range: invalid range");
+    r->rs.work_begin = begin; r->rs.work_end = end; r->rs.range_set = true;
+    return CRT_OK;
+}
+int crt_render_clear_range(crt_render* r) {
+    CHECK_ARG(r, "crt_render_clear_range: null handle");
+    r->rs.range_set = false;
     return CRT_OK;
 }
 int crt_render_set_stream(crt_render* r, void* cuda_stream) {
@@ -287,7 +298,6 @@ int crt_render_set_stage_timing(crt_render* r, int on) {
 
 int crt_render_run_view(crt_render* r, const float eye[3], const float inv_view[9], float fovy_rad) {
     CHECK_ARG(r && eye && inv_view, "crt_render_run_view: null argument");
-    if (r->rs.range_set) CHECK_ARG(r->rs.s_end <= r->rs.spp, "crt_render_run_view: sample range exceeds spp");
     CRT_CUDA(cudaSetDevice(r->scene->dev.device));
     float tan_half = tanf(fovy_rad / 2);                          // Render.cuh:338, evaluated on the host
     int rc = wavefront_render(r->wf, r->scene->dev, r->rs, eye, inv_view, tan_half, r->stream, &r->stats);

@@ -60,7 +60,9 @@ struct RenderSettings {
     uint32_t light_sample_n = 1;
     uint32_t seed = 0;
     int estimator = 0;
-    uint32_t s_begin = 0, s_end = 0; // 0,0 -> [0, spp)
+    // work items [work_begin, work_end) of the width*height*spp (sample-major) index space;
+    // range_set == false -> everything
+    unsigned long long work_begin = 0, work_end = 0;
     bool range_set = false;
     bool stage_timing = false;
 };

@@ -595,18 +595,21 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     if (rs.estimator != CRT_ESTIMATOR_COMPAT) { set_error("estimator not implemented"); return CRT_ERR_INVALID; }
     int rc = ensure_pool(w, ds, rs);
     if (rc != CRT_OK) return rc;
-    const uint32_t s_begin = rs.range_set ? rs.s_begin : 0, s_end = rs.range_set ? rs.s_end : rs.spp;
     const size_t npix = (size_t)w->width * w->height;
+    const unsigned long long work_all = (unsigned long long)npix * rs.spp;
+    const unsigned long long w_begin = rs.range_set ? std::min(rs.work_begin, work_all) : 0;
+    const unsigned long long w_end = rs.range_set ? std::min(rs.work_end, work_all) : work_all;
     RenderParamsDev p;
     memcpy(p.eye, eye, sizeof(p.eye));
     memcpy(p.M, M, sizeof(p.M));
     p.tan_half = tan_half;
     p.width = w->width; p.height = w->height; p.n_pixels = npix;
-    p.s_begin = s_begin; p.p_rr = rs.p_rr; p.light_sample_n = (int)rs.light_sample_n; p.seed = rs.seed;
+    p.s_begin = 0; p.p_rr = rs.p_rr; p.light_sample_n = (int)rs.light_sample_n; p.seed = rs.seed;
     p.max_vertices = 64;                                           // BOUNCE_STACK_SIZE, Global.h:18
     Counters h;
     memset(&h, 0, sizeof(h));
-    h.work_end = (unsigned long long)npix * (s_end > s_begin ? (s_end - s_begin) : 0);
+    h.work_next = w_begin;
+    h.work_end = std::max(w_end, w_begin);
     w->status_host->done = 0;
     w->status_host->n_cur = 0;
     CRT_CUDA(cudaEventRecord(w->ev_begin, st));
@@ -656,7 +659,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     if (stats) {
         CRT_CUDA(cudaMemcpy(&h, w->counters, sizeof(h), cudaMemcpyDeviceToHost));
         memset(stats, 0, sizeof(*stats));
-        stats->samples = h.work_end;
+        stats->samples = h.work_end - w_begin;
         stats->extend_rays = h.stat_extend;
         stats->shadow_rays = h.stat_shadow + h.n_shadow;
         stats->probe_rays = h.stat_probe;

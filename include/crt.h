@@ -148,6 +148,11 @@ int crt_render_set_estimator(crt_render* r, int estimator);
 /* Multi-GPU sharding: this handle renders sample indices [begin, end) of the spp set above
  * (default [0, spp)). The accumulation buffer of every shard sums to the full image exactly. */
 int crt_render_set_sample_range(crt_render* r, uint32_t begin, uint32_t end);
+/* Finer sharding for spp < number of GPUs: work items [begin, end) of the sample-major index space
+ * w = sample * (width*height) + pixel, 0 <= w < width*height*spp. Ranges past the end are clipped. */
+int crt_render_set_work_range(crt_render* r, uint64_t begin, uint64_t end);
+/* Back to the default (all samples). */
+int crt_render_clear_range(crt_render* r);
 /* Optional: run on this CUDA stream (cudaStream_t) instead of the handle's own. */
 int crt_render_set_stream(crt_render* r, void* cuda_stream);
 /* Render::run_view, include/Render.cuh:435-475 (without the GL PBO). Blocking. Clears the

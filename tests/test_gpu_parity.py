@@ -1,0 +1,272 @@
+"""GPU parity tests (run on the B200 box with -m gpu). Everything goes through the C-ABI (libcrt.so) and is
+compared with the CPU oracle: BVH bytes, hit ids / t bits, the fixed-point accumulation buffer."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import BOX_CAMERA, box_scene, random_rays, soup
+
+pytestmark = pytest.mark.gpu
+
+FLT_MAX = np.finfo(np.float32).max
+
+
+@pytest.fixture(scope="module")
+def gpu(crt):
+    if crt.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU fallback and these tests need the B200")
+    return crt
+
+
+def _pair(gpu, orc, files, name, thresh=None):
+    cfg = gpu.load_config(files[name]["cfg_path"])
+    th = thresh if thresh is not None else cfg.bvh_thresh_n
+    a = gpu.Scene().add_obj(files[name]["obj"], files[name]["dir"])
+    a.set_BVH(th)
+    b = orc.Scene().add_obj(files[name]["obj"], files[name]["dir"])
+    b.build_new_bvh(th)
+    return cfg, a, b
+
+
+def _same_bvh(a, b_built):
+    nodes, order, last, bounds = a.export_bvh()
+    onodes, oorder, olast, obounds = b_built
+    assert len(nodes) == len(onodes)
+    assert nodes.tobytes() == onodes.tobytes(), "node bytes differ"
+    assert np.array_equal(order, oorder) and np.array_equal(last, olast) and np.array_equal(bounds, obounds)
+
+
+@pytest.mark.parametrize("name,thresh", [("veach-mis", 2), ("veach-mis", 1), ("veach-mis", 6), ("cornell-box", 2), ("cornell-box", 4)])
+def test_gpu_bvh_build_is_bit_exact(gpu, orc, scene_files, name, thresh):
+    a = gpu.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    a.set_BVH(thresh)
+    b = orc.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    _same_bvh(a, b.build_new_bvh(thresh))
+
+
+@pytest.mark.parametrize("n,thresh", [(1, 1), (1, 4), (2, 1), (2, 2), (3, 1), (5, 8), (1024, 2), (1025, 2), (4097, 3), (50000, 2), (300000, 4)])
+def test_gpu_bvh_build_random_soups(gpu, orc, n, thresh):
+    rng = np.random.default_rng(n * 31 + thresh)
+    verts = soup(rng, n, extent=20.0, size=0.7)
+    if n > 100:
+        verts[10:40] = verts[10]                       # duplicate triangles -> duplicate Morton keys
+        verts[50:60, [1, 4, 7]] = 3.0                  # flat, axis-aligned boxes
+    mats = [[.5, .5, .5, 0, 0, 0, 1]]
+    a = gpu.Scene().add_triangles(verts, np.zeros(n, np.uint32), np.zeros(n, np.uint32), mats)
+    a.set_BVH(thresh)
+    b = orc.Scene().add_arrays(verts, np.zeros(n, np.int32), np.zeros(n, np.int32), mats)
+    _same_bvh(a, b.build_new_bvh(thresh))
+    rays = random_rays(rng, [-22] * 3, [22] * 3, 20000)
+    t, f, _ = a.trace_rays(rays, gpu.RAY_CLOSEST)
+    ot, of = b.trace(rays, which=0, mode=0)
+    assert np.array_equal(f, of) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+
+
+def test_gpu_bvh_flat_and_degenerate_extent(gpu, orc):
+    """All triangles in one plane (zero extent on an axis) and all-identical triangles."""
+    rng = np.random.default_rng(11)
+    verts = soup(rng, 3000, extent=5.0, size=0.5)
+    verts[:, [2, 5, 8]] = 1.25
+    same = np.repeat(soup(rng, 1), 257, axis=0)
+    for v in (verts, same):
+        n = len(v)
+        a = gpu.Scene().add_triangles(v, np.zeros(n, np.uint32), np.zeros(n, np.uint32), [[.5, .5, .5, 0, 0, 0, 1]])
+        a.set_BVH(2)
+        b = orc.Scene().add_arrays(v, np.zeros(n, np.int32), np.zeros(n, np.int32), [[.5, .5, .5, 0, 0, 0, 1]])
+        _same_bvh(a, b.build_new_bvh(2))
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
+def test_primary_hit_ids_bit_exact_vs_reference_rule(gpu, orc, scene_files, name):
+    """North-star check 1: primary-ray hit triangle ids from the GPU (new BVH, new traversal) equal the
+    reference's host BVH + traversal rule (oracle transcription, canonical ties), at the shipped 800x600."""
+    cfg, a, b = _pair(gpu, orc, scene_files, name)
+    b.build_ref_bvh(cfg.bvh_thresh_n)
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    rays = orc.primary_rays(cfg.eye_pos, M, float(cfg.fovy_rad), cfg.width, cfg.height)
+    t, f, _ = a.trace_rays(rays, gpu.RAY_CLOSEST)
+    t_ref, f_ref = b.trace(rays, which=1)
+    assert np.array_equal(f, f_ref)
+    assert np.array_equal(t.view(np.uint32), t_ref.view(np.uint32))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", name + "_hits_200x150.npz"))
+    rays_s = orc.primary_rays(cfg.eye_pos, M, float(cfg.fovy_rad), 200, 150)
+    t_s, f_s, _ = a.trace_rays(rays_s, gpu.RAY_CLOSEST)
+    assert np.array_equal(f_s, gold["face"]) and np.array_equal(t_s.view(np.uint32), gold["t_bits"])
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
+def test_incoherent_rays_closest_and_any(gpu, orc, scene_files, name):
+    cfg, a, b = _pair(gpu, orc, scene_files, name)
+    _, _, _, bounds = a.export_bvh()
+    rng = np.random.default_rng(2)
+    for mode in (gpu.RAY_CLOSEST, gpu.RAY_ANY):
+        rays = random_rays(rng, bounds[:3], bounds[3:], 300000, tmax_any=(mode == gpu.RAY_ANY))
+        t, f, _ = a.trace_rays(rays, mode)
+        ot, of = b.trace(rays, which=0, mode=mode)
+        assert np.array_equal(f, of) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    # brute force on a sample: the traversal never loses the closest triangle
+    rays = random_rays(rng, bounds[:3], bounds[3:], 300 if name == "cornell-box" else 5000)
+    t, f, _ = a.trace_rays(rays, gpu.RAY_CLOSEST)
+    bt, bf = b.trace(rays, which=3, mode=0)
+    assert np.array_equal(f, bf) and np.array_equal(t.view(np.uint32), bt.view(np.uint32))
+
+
+def test_ray_edge_cases(gpu, orc):
+    verts, mat, obj, mats = box_scene(np.random.default_rng(0), 100)
+    a = gpu.Scene().add_triangles(verts, mat.astype(np.uint32), obj.astype(np.uint32), mats)
+    a.set_BVH(2)
+    b = orc.Scene().add_arrays(verts, mat, obj, mats)
+    b.build_new_bvh(2)
+    rays = np.array([
+        [5, 5, 5, FLT_MAX, 1, 0, 0, 0], [5, 5, 5, FLT_MAX, 0, -1, 0, 0], [5, 5, 5, FLT_MAX, 0, 0, 1, 0],      # axis-aligned (inf inv_dir)
+        [5, 5, 5, FLT_MAX, -1, 0, 0, 0], [5, 0, 5, FLT_MAX, 1, 0, 0, 0],                                       # in the floor plane
+        [0, 0, 0, FLT_MAX, 0.57735026, 0.57735026, 0.57735026, 0],                                               # through a corner
+        [5, 5, -30, FLT_MAX, 0, 0, -1, 0],                                                                       # away from everything
+        [5, 5, 5, 1e-3, 0, 1, 0, 0], [5, 5, 5, 0.0, 0, 1, 0, 0],                                                 # tiny / zero tmax
+    ], np.float32)
+    for mode in (0, 1):
+        t, f, _ = a.trace_rays(rays, mode)
+        ot, of = b.trace(rays, which=0, mode=mode)
+        assert np.array_equal(f, of) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    t, f, ms = a.trace_rays(np.zeros((0, 8), np.float32), 0)                                                     # empty batch
+    assert len(t) == 0 and len(f) == 0
+
+
+def _render_pair(gpu, orc, a, b, cam_eye, M, fovy, W, H, spp, p_rr, lsn, seed=0):
+    R = gpu.Render(a, W, H, spp, p_rr, lsn)
+    R.set_seed(seed)
+    R.run_view(cam_eye, M, fovy)
+    acc = R.get_accum_i64()
+    oacc, ost = b.render(cam_eye, M, float(fovy), W, H, 0, spp, p_rr, lsn, seed=seed)
+    return R, acc, oacc, ost
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
+def test_matched_seed_radiance_shipped_configs(gpu, orc, scene_files, name):
+    """North-star check 2 at BASELINE configs C1 / C2 (full 800x600, shipped spp): radiance under matched
+    seeds. Stated tolerance 1e-4 relative per pixel; the fixed-point buffers are in fact identical."""
+    cfg, a, b = _pair(gpu, orc, scene_files, name)
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    R, acc, oacc, ost = _render_pair(gpu, orc, a, b, cfg.eye_pos, M, cfg.fovy_rad, cfg.width, cfg.height, cfg.spp, cfg.P_RR, cfg.light_sample_n)
+    st = R.stats()
+    assert (st["extend_rays"], st["shadow_rays"], st["probe_rays"]) == (ost["extend_rays"], ost["shadow_rays"], ost["probe_rays"])
+    lin = R.get_accum().reshape(-1)
+    olin, orgb = orc.resolve(oacc, cfg.width * cfg.height, cfg.spp)
+    rel = np.abs(lin - olin) / np.maximum(np.abs(olin), 1e-6)
+    assert rel.max() <= 1e-4                                  # the north star's tolerance
+    assert np.array_equal(acc, oacc)                          # and what actually holds: exact equality
+    rgb = R.get_frame_buffer().reshape(-1)
+    assert np.abs(rgb.astype(int) - orgb.astype(int)).max() <= 1     # powf on device vs host: at most one code value
+    assert (rgb != orgb).mean() < 1e-3
+
+
+def test_matched_seed_radiance_synthetic_specular_and_options(gpu, orc):
+    verts, mat, obj, mats = box_scene(np.random.default_rng(1), 400)
+    a = gpu.Scene().add_triangles(verts, mat.astype(np.uint32), obj.astype(np.uint32), mats)
+    a.set_BVH(2)
+    b = orc.Scene().add_arrays(verts, mat, obj, mats)
+    b.build_new_bvh(2)
+    M = gpu.inverse_view_matrix(BOX_CAMERA["eye"], BOX_CAMERA["lookat"], BOX_CAMERA["up"])
+    for (W, H, spp, p_rr, lsn, seed) in [(96, 64, 8, 0.6, 2, 0), (33, 17, 3, 0.9, 1, 5), (64, 64, 2, 1.0, 3, 9), (50, 40, 4, 0.0, 1, 2)]:
+        R, acc, oacc, ost = _render_pair(gpu, orc, a, b, BOX_CAMERA["eye"], M, BOX_CAMERA["fovy"], W, H, spp, p_rr, lsn, seed)
+        assert np.array_equal(acc, oacc), (W, H, spp, p_rr, lsn, seed)
+        assert R.stats()["probe_rays"] == ost["probe_rays"]
+        if p_rr > 0.5:
+            assert ost["probe_rays"] > 0                      # the SPECULAR plate is exercised
+    # P_RR = 1: paths stop at 64 vertices (BOUNCE_STACK_SIZE)
+    assert R.stats()["iterations"] <= 66
+
+
+def test_render_is_deterministic_and_shards_add_up(gpu, orc, scene_files):
+    """Multi-GPU invariance on one GPU: any split of the work index space sums to the full buffer exactly,
+    and repeated runs are identical (atomics are integer, so ordering cannot matter)."""
+    cfg, a, b = _pair(gpu, orc, scene_files, "veach-mis")
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    W, H, spp = 320, 240, 6
+    R = gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n)
+    R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+    full = R.get_accum_i64()
+    R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+    assert np.array_equal(full, R.get_accum_i64())
+    from cudaraytracing_b200.distributed import shard_work
+    for world in (2, 4, 8):
+        total = np.zeros_like(full)
+        for r in range(world):
+            w0, w1 = shard_work(W * H, spp, r, world)
+            R.set_work_range(w0, w1)
+            R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+            total += R.get_accum_i64()
+        assert np.array_equal(total, full), world
+    R.set_sample_range(2, 5)
+    R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+    oacc, _ = b.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 2, 5, cfg.P_RR, cfg.light_sample_n)
+    assert np.array_equal(R.get_accum_i64(), oacc)
+    R.clear_range()
+    R.set_spp(1)
+    R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+    oacc, _ = b.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 0, 1, cfg.P_RR, cfg.light_sample_n)
+    assert np.array_equal(R.get_accum_i64(), oacc)
+
+
+def test_pool_smaller_than_frame(gpu, orc, scene_files, monkeypatch):
+    """Path regeneration: a pool far smaller than the number of samples gives the same image."""
+    monkeypatch.setenv("CRT_POOL", "8192")
+    cfg, a, b = _pair(gpu, orc, scene_files, "veach-mis")
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    R, acc, oacc, _ = _render_pair(gpu, orc, a, b, cfg.eye_pos, M, cfg.fovy_rad, 200, 150, 3, cfg.P_RR, cfg.light_sample_n)
+    assert np.array_equal(acc, oacc)
+    assert R.stats()["iterations"] > 12
+
+
+def test_save_png_and_cli(gpu, scene_files, tmp_path):
+    import subprocess
+    import struct
+    import zlib
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "cudaraytracing_b200", "crt")
+    out = str(tmp_path / "v.png")
+    r = subprocess.run([exe, "--config", scene_files["veach-mis"]["cfg_path"], "--out", out, "--width", "160", "--height", "120"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import json
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["triangles"] == 3092 and info["lights"] == 4
+    data = open(out, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n" and struct.unpack(">II", data[16:24]) == (160, 120)
+    # same image through the API
+    cfg = gpu.load_config(scene_files["veach-mis"]["cfg_path"])
+    a = gpu.Scene().add_obj(scene_files["veach-mis"]["obj"], scene_files["veach-mis"]["dir"])
+    a.set_BVH(cfg.bvh_thresh_n)
+    R = gpu.Render(a, 160, 120, cfg.spp, cfg.P_RR, cfg.light_sample_n)
+    R.run_view(cfg.eye_pos, gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up), cfg.fovy_rad)
+    p2 = str(tmp_path / "api.png")
+    R.save_frame_buffer(p2)
+    assert open(p2, "rb").read() == data
+
+
+def test_error_paths_on_gpu(gpu):
+    s = gpu.Scene().add_triangles([[0, 0, 0, 1, 0, 0, 0, 1, 0]], [0], [0], [[.5, .5, .5, 0, 0, 0, 1]])
+    with pytest.raises(gpu.CrtError) as e:
+        gpu.Render(s, 8, 8)
+    assert e.value.code == -5
+    with pytest.raises(gpu.CrtError):
+        s.set_BVH(2, device=99)
+    s.set_BVH(2)
+    with pytest.raises(gpu.CrtError) as e:
+        s.add_triangles([[0, 0, 0, 1, 0, 0, 0, 1, 0]], [0], [0], [[.5, .5, .5, 0, 0, 0, 1]])
+    assert e.value.code == -5
+    R = gpu.Render(s, 8, 8)
+    with pytest.raises(gpu.CrtError):
+        R.set_P_RR(1.5)
+    with pytest.raises(gpu.CrtError):
+        R.set_estimator(7)
+    # a scene with no lights and an empty scene still render (to black)
+    R.run_view([0.2, 0.2, -1], np.eye(3, dtype=np.float32).reshape(9), 0.5)
+    assert not R.get_accum_i64().any()
+    e0 = gpu.Scene()
+    e0.set_BVH(2)
+    R0 = gpu.Render(e0, 4, 4)
+    R0.run_view([0, 0, 0], np.eye(3, dtype=np.float32).reshape(9), 0.5)
+    assert not R0.get_accum_i64().any()

@@ -1,0 +1,190 @@
+"""CPU tests of the product's host side and of the C-ABI surface (no GPU compute calls)."""
+import ctypes as C
+import json
+import os
+import re
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, box_scene
+
+
+def test_cabi_exports_every_declared_symbol(crt):
+    hdr = open(os.path.join(ROOT, "include", "crt.h")).read()
+    names = sorted(set(re.findall(r"\b(crt_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 35
+    L = C.CDLL(crt.lib_path())
+    for n in names:
+        assert hasattr(L, n), "libcrt.so does not export " + n
+    assert L.crt_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback(crt):
+    if crt.device_count() > 0:
+        pytest.skip("a GPU is present")
+    s = crt.Scene().add_triangles([[0, 0, 0, 1, 0, 0, 0, 1, 0]], [0], [0], [[.5, .5, .5, 0, 0, 0, 1]])
+    with pytest.raises(crt.CrtError) as e:
+        s.set_BVH(2)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+    with pytest.raises(crt.CrtError) as e:
+        crt.Render(s, 8, 8)
+    assert e.value.code == -5                      # render before build_bvh: state error
+    with pytest.raises(crt.CrtError):
+        s.trace_rays(np.zeros((1, 8), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no include, import, link or dlopen of it from the product."""
+    pkg = os.path.join(ROOT, "cudaraytracing_b200")
+    bad = re.compile(r'#\s*include\s*[<"][^>"]*(orc_|oracle)|^\s*(from|import)\s+oracle|liborc|-lorc|CDLL\([^)]*oracle', re.M)
+    n = 0
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert not bad.search(txt), f
+                n += 1
+    assert n >= 10
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
+def test_obj_ingest_matches_oracle_restatement(crt, orc, scene_files, name):
+    f = scene_files[name]
+    a = crt.Scene().add_obj(f["obj"], f["dir"])
+    b = orc.Scene().add_obj(f["obj"], f["dir"])
+    ta, tb = a.tris(), b.tris()
+    for k in ("verts", "normal", "area", "area_of_obj", "mat", "obj"):
+        assert np.array_equal(ta[k].view(np.uint32), tb[k].view(np.uint32)), k
+    assert np.array_equal(a.mats(), b.mats())
+    la, lb = a.lights(), b.lights()
+    assert len(la) == len(lb)
+    for (fa, aa), (fb, ab) in zip(la, lb):
+        assert np.array_equal(fa, fb) and np.float32(aa) == np.float32(ab)
+
+
+def test_obj_loader_quirks(crt, orc, tmp_path):
+    """Reference loader behaviour: faces before the first usemtl are dropped, polygons keep their first
+    three corners, v/vt/vn and v//vn and bare indices parse, unknown materials stay black, Ks is ignored by
+    compat, Ns>1 switches the mode, CRLF line ends are fine (OBJLoader.h:61-203, Loader.h:40-124)."""
+    obj = ("mtllib m.mtl\r\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvn 0 0 1\nvt 0 0\n"
+           "f 1 2 3\n"                      # dropped: no usemtl yet
+           "usemtl a\nf 1/1/1 2/1/1 3/1/1 4/1/1\nf 1//1 2//1 4//1\n"
+           "usemtl glow\nf 2 3 4\n"
+           "usemtl missing\nf 1 3 4\n"
+           "usemtl a\nf 3 2 1\n")
+    mtl = "newmtl a\nKd 0.25 0.5 0.75\nKs 1 1 1\nNs 50\nnewmtl glow\nKe 2 0 0\nKd 0 0 0\nNs 1\n"
+    (tmp_path / "s.obj").write_text(obj)
+    (tmp_path / "m.mtl").write_text(mtl)
+    a = crt.Scene().add_obj(str(tmp_path / "s.obj"), str(tmp_path))
+    b = orc.Scene().add_obj(str(tmp_path / "s.obj"), str(tmp_path))
+    assert a.counts()["n_tris"] == 5 and b.n_tris == 5
+    ta, tb = a.tris(), b.tris()
+    for k in ("verts", "normal", "area", "area_of_obj", "mat", "obj"):
+        assert np.array_equal(ta[k].view(np.uint32), tb[k].view(np.uint32)), k
+    m = a.mats()
+    assert np.array_equal(m, b.mats())
+    assert m[0][8] == 1 and m[0][6] == 50 and list(m[0][:3]) == [0.25, 0.5, 0.75]       # SPECULAR from Ns
+    assert m[1][7] == 1 and m[2][7] == 0 and list(m[2][:6]) == [0] * 6                  # emissive; unknown = black
+    assert ta["obj"].tolist() == [0, 0, 1, 2, 3]
+    assert [len(f) for f, _ in a.lights()] == [1]
+    assert np.array_equal(ta["verts"][0], np.array([0, 0, 0, 1, 0, 0, 0, 1, 0], np.float32))   # first 3 corners of the quad
+
+
+def test_ingest_errors(crt, tmp_path):
+    with pytest.raises(crt.CrtError) as e:
+        crt.Scene().add_obj(str(tmp_path / "nope.obj"), str(tmp_path))
+    assert e.value.code == -2 and "Unable to open OBJ file" in str(e.value)
+    (tmp_path / "a.obj").write_text("mtllib gone.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nusemtl x\nf 1 2 3\n")
+    with pytest.raises(crt.CrtError) as e:
+        crt.Scene().add_obj(str(tmp_path / "a.obj"), str(tmp_path))
+    assert "Unable to open MTL file" in str(e.value)
+    (tmp_path / "b.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nusemtl x\nf 1 2 9\n")
+    (tmp_path / "m.mtl").write_text("newmtl x\nKd 1 1 1\n")
+    with pytest.raises(crt.CrtError) as e:
+        crt.Scene().add_obj(str(tmp_path / "b.obj"), str(tmp_path))
+    assert "malformed face" in str(e.value)
+    with pytest.raises(crt.CrtError):
+        crt.Scene().add_triangles([[0, 0, 0, 1, 0, 0, 0, float("nan"), 0]], [0], [0], [[.5, .5, .5, 0, 0, 0, 1]])
+    with pytest.raises(crt.CrtError):
+        crt.Scene().add_triangles([[0, 0, 0, 1, 0, 0, 0, 1, 0]], [3], [0], [[.5, .5, .5, 0, 0, 0, 1]])
+
+
+def test_add_triangles_matches_oracle(crt, orc):
+    verts, mat, obj, mats = box_scene(np.random.default_rng(0), 50)
+    a = crt.Scene().add_triangles(verts, mat, obj, mats)
+    b = orc.Scene().add_arrays(verts, mat, obj, mats)
+    ta, tb = a.tris(), b.tris()
+    for k in ("verts", "normal", "area", "area_of_obj", "mat", "obj"):
+        assert np.array_equal(ta[k].view(np.uint32), tb[k].view(np.uint32)), k
+    assert np.array_equal(a.mats(), b.mats())
+    assert len(a.lights()) == len(b.lights()) == 1
+
+
+def test_config_loader(crt, scene_files, tmp_path):
+    cfg = crt.load_config(scene_files["cornell-box"]["cfg_path"])
+    assert (cfg.width, cfg.height, cfg.spp, cfg.light_sample_n, cfg.bvh_thresh_n) == (800, 600, 2, 2, 2)
+    assert cfg.P_RR == np.float32(0.6) and cfg.fov_y == np.float32(39.3077)
+    assert list(cfg.eye_pos) == [278.0, 273.0, -800.0] and cfg.seed == 0 and cfg.estimator == 0
+    v = crt.load_config(scene_files["veach-mis"]["cfg_path"])
+    assert v.eye_pos[2] == np.float32(1.23612e-06) and v.spp == 4
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"OBJ_paths": [], "width": 8}')
+    with pytest.raises(crt.CrtError) as e:
+        crt.load_config(str(bad))
+    assert "missing" in str(e.value)
+    bad.write_text("{ not json")
+    with pytest.raises(crt.CrtError):
+        crt.load_config(str(bad))
+    ext = json.load(open(scene_files["veach-mis"]["cfg_path"]))
+    ext.update(seed=7, estimator="mis")
+    (tmp_path / "ext.json").write_text(json.dumps(ext))
+    c2 = crt.load_config(str(tmp_path / "ext.json"))
+    assert c2.seed == 7 and c2.estimator == 1
+
+
+def test_camera_matrix_matches_oracle(crt, orc):
+    for eye, look, up in ([[278, 273, -800], [278, 273, -799], [0, 1, 0]], [[28.2792, 5.2, 1.23612e-06], [0, 2.8, 0], [0, 1, 0]],
+                          [[1, 2, 3], [-4, 0.5, 9], [0.1, 1, 0.2]]):
+        assert np.array_equal(crt.inverse_view_matrix(eye, look, up), orc.inverse_view_matrix(eye, look, up))
+
+
+def test_png_writer_round_trip(crt, tmp_path):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    p = str(tmp_path / "x.png")
+    crt.write_png(p, img)
+    data = open(p, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, ihdr = 8, b"", None
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == (zlib.crc32(typ + body) & 0xffffffff)
+        if typ == b"IHDR": ihdr = struct.unpack(">IIBBBBB", body)
+        if typ == b"IDAT": idat += body
+        pos += 12 + n
+    assert ihdr == (53, 37, 8, 2, 0, 0, 0)
+    raw = zlib.decompress(idat)
+    rows = np.frombuffer(raw, np.uint8).reshape(37, 1 + 53 * 3)
+    assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(37, 53, 3), img)
+
+
+def test_cli_reports_errors(crt, tmp_path):
+    import subprocess
+    exe = os.path.join(ROOT, "cudaraytracing_b200", "crt")
+    r = subprocess.run([exe, "--config", str(tmp_path / "missing.json")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+
+
+def test_shard_work_partitions_exactly(crt):
+    from cudaraytracing_b200.distributed import shard_work
+    for npix, spp in ((800 * 600, 2), (800 * 600, 4), (3840 * 2160, 1024), (7, 3), (5, 1)):
+        for world in (1, 2, 3, 4, 8):
+            parts = [shard_work(npix, spp, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == npix * spp
+            assert all(parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+            if spp >= world:
+                assert all(b % npix == 0 and e % npix == 0 for b, e in parts)

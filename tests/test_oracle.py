@@ -1,0 +1,207 @@
+"""CPU tests of the oracle itself: known-answer vectors, golden fixtures, internal consistency."""
+import hashlib
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, BOX_CAMERA, box_scene, random_rays, soup
+
+
+def test_philox_known_answers(orc):
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert list(orc.philox(ctr, key)) == want
+
+
+def test_u01_is_curand_like(orc):
+    L = orc.lib()
+    assert L.orc_u01(0) == np.float32(2.0 ** -24)          # never 0
+    assert L.orc_u01(0xffffffff) == 1.0                    # 1 is included, like curand_uniform
+    assert L.orc_u01(0x80000000) == np.float32(0.5) + np.float32(2.0 ** -24)
+
+
+def test_sincos_accuracy(orc):
+    worst = 0.0
+    for u in np.linspace(2.0 ** -24, 1.0, 4001, dtype=np.float32):
+        s, c = orc.sincos_2pi(float(u))
+        worst = max(worst, abs(s - math.sin(2 * math.pi * float(u))), abs(c - math.cos(2 * math.pi * float(u))))
+    assert worst < 1.5e-7
+    worst = 0.0
+    for x in np.linspace(-40, 40, 4001, dtype=np.float32):
+        s, c = orc.sincos_rad(float(x))
+        worst = max(worst, abs(s - math.sin(float(x))), abs(c - math.cos(float(x))))
+    assert worst < 2e-7
+    assert orc.sincos_rad(float("nan")) == (0.0, 1.0) and orc.sincos_rad(1e30) == (0.0, 1.0)
+
+
+def _load_scene(orc, files, name):
+    return orc.Scene().add_obj(files[name]["obj"], files[name]["dir"])
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
+def test_reference_host_path_golden(orc, scene_files, name):
+    """Scene statistics and the reference BVH (BVH.h) against golden values produced by the REAL reference
+    host code (oracle/_ref, tools/make_golden.py) in the survey container."""
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        g = json.load(f)[name]
+    S = _load_scene(orc, scene_files, name)
+    assert S.n_tris == g["n_tris"] and S.n_lights == g["n_lights"]
+    tr = S.tris()
+    assert hashlib.sha256(tr["verts"].tobytes()).hexdigest() == g["ref_verts_sha256"]
+    assert hashlib.sha256(tr["normal"].tobytes()).hexdigest() == g["ref_normal_sha256"]
+    assert hashlib.sha256(tr["area"].tobytes()).hexdigest() == g["ref_area_sha256"]
+    assert [float(np.float32(a)) for _, a in S.lights()] == g["light_areas"]
+    assert [len(f) for f, _ in S.lights()] == g["light_sizes"]
+    nodes, order, root = S.build_ref_bvh(g["thresh_n"])
+    assert len(nodes) == g["ref_n_nodes"] and root == g["ref_root"]
+    assert hashlib.sha256(nodes.tobytes()).hexdigest() == g["ref_nodes_sha256"]
+    assert hashlib.sha256(tr["verts"][order].tobytes()).hexdigest() == g["ref_sorted_verts_sha256"]
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
+def test_hit_ids_new_rule_equals_reference_rule(orc, scene_files, name):
+    """Primary-ray hit ids: reference BVH + reference traversal rule == new BVH + new rule == golden vector."""
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        g = json.load(f)[name]
+    S = _load_scene(orc, scene_files, name)
+    S.build_ref_bvh(g["thresh_n"])
+    S.build_new_bvh(g["thresh_n"])
+    cam = g["camera"]
+    M = orc.inverse_view_matrix(cam["eye"], cam["lookat"], cam["up"])
+    rays = orc.primary_rays(cam["eye"], M, float(np.float32(np.float32(cam["fov_y"]) * np.float32(math.pi) / np.float32(180))), 200, 150)
+    t_ref, f_ref, st_ref = S.trace(rays, which=1, want_stats=True)
+    t_lit, f_lit = S.trace(rays, which=2)
+    t_new, f_new, st_new = S.trace(rays, which=0, want_stats=True)
+    assert np.array_equal(f_ref, f_new) and np.array_equal(t_ref.view(np.uint32), t_new.view(np.uint32))
+    # The literal "first found, strict <" rule (DeviceBVH.cuh:37,144) may only differ where two triangles
+    # tie in t exactly — cornell-box's light quad is coplanar with the ceiling — and there the winner depends
+    # on the BVH's visiting order (implementation-defined in the reference); the canonical rule picks the
+    # lower face id (the light, as in the reference's published image).
+    diff = f_ref != f_lit
+    assert np.array_equal(t_ref.view(np.uint32), t_lit.view(np.uint32)) and diff.mean() < 0.005
+    if name == "cornell-box":
+        assert set(f_ref[diff].tolist()) <= {0, 1} and set(f_lit[diff].tolist()) <= {4, 5}
+    else:
+        assert not diff.any()
+    gold = np.load(os.path.join(GOLDEN, name + "_hits_200x150.npz"))
+    assert np.array_equal(f_new, gold["face"]) and np.array_equal(t_new.view(np.uint32), gold["t_bits"])
+    assert abs((f_new >= 0).mean() - g["hit_fraction_200x150"]) < 1e-9
+    # traversal work per primary ray of the reference rule and of the new rule
+    assert abs(st_ref["inner"] / st_ref["rays"] - g["ref_pops_per_ray_200x150"]) < 1e-6
+    assert st_new["inner"] / st_new["rays"] < 0.5 * st_ref["inner"] / st_ref["rays"]
+
+
+def test_new_traversal_equals_brute_force(orc):
+    rng = np.random.default_rng(7)
+    verts = soup(rng, 3000)
+    S = orc.Scene().add_arrays(verts, np.zeros(3000, np.int32), np.zeros(3000, np.int32), [[.5, .5, .5, 0, 0, 0, 1]])
+    for thresh in (1, 2, 4, 7):
+        S.build_new_bvh(thresh)
+        for any_mode in (0, 1):
+            rays = random_rays(rng, [-12] * 3, [12] * 3, 4000, tmax_any=bool(any_mode))
+            t0, f0 = S.trace(rays, which=0, mode=any_mode)
+            t3, f3 = S.trace(rays, which=3, mode=any_mode)
+            if any_mode == 0:
+                assert np.array_equal(f0, f3) and np.array_equal(t0.view(np.uint32), t3.view(np.uint32))
+            else:
+                assert np.array_equal(f0 >= 0, f3 >= 0)       # the blocker found may differ, the decision may not
+
+
+def test_new_bvh_structure(orc):
+    rng = np.random.default_rng(3)
+    n = 2000
+    verts = soup(rng, n)
+    verts[100:140] = verts[100]                   # duplicate triangles -> duplicate Morton keys
+    S = orc.Scene().add_arrays(verts, np.zeros(n, np.int32), np.zeros(n, np.int32), [[.5, .5, .5, 0, 0, 0, 1]])
+    for thresh in (1, 2, 3, 8, 64):
+        nodes, order, last, bounds = S.build_new_bvh(thresh)
+        assert sorted(order.tolist()) == list(range(n))
+        # every slot belongs to exactly one leaf; leaves hold <= thresh triangles unless they are duplicates
+        seen = np.zeros(n, np.int32)
+        total = 0
+        for nd in nodes:
+            for c, cnt in ((nd["c0"], nd["n0"]), (nd["c1"], nd["n1"])):
+                if c < 0:
+                    first = ~int(c)
+                    seen[first:first + cnt] += 1
+                    assert last[first + cnt - 1] == 1 and not last[first:first + cnt - 1].any()
+                    assert cnt <= thresh
+                    total += cnt
+        assert total == n and (seen == 1).all()
+        assert nodes[0]["n0"] + nodes[0]["n1"] == n
+        lo = verts.reshape(n, 3, 3).min(axis=(0, 1)); hi = verts.reshape(n, 3, 3).max(axis=(0, 1))
+        assert np.array_equal(bounds, np.concatenate([lo, hi]))
+
+
+def test_new_bvh_degenerate_inputs(orc):
+    one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    for n in (1, 2, 3):
+        verts = np.repeat(one, n, axis=0) + np.arange(n, dtype=np.float32)[:, None]
+        S = orc.Scene().add_arrays(verts, np.zeros(n, np.int32), np.zeros(n, np.int32), [[.5, .5, .5, 0, 0, 0, 1]])
+        for thresh in (1, 2, 5):
+            nodes, order, last, _ = S.build_new_bvh(thresh)
+            assert len(nodes) >= 1 and last[-1] == 1
+            rays = np.array([[0.2 + (n - 1), 0.2 + (n - 1), -1 + (n - 1), 3e38, 0, 0, 1, 0]], np.float32)
+            t, f = S.trace(rays, which=0)
+            tb, fb = S.trace(rays, which=3)
+            assert f[0] == fb[0] == n - 1 and t[0] == tb[0]
+    S = orc.Scene()
+    nodes, order, last, _ = S.build_new_bvh(2)          # empty scene
+    assert len(nodes) == 0
+    t, f = S.trace(np.array([[0, 0, 0, 3e38, 0, 0, 1, 0]], np.float32), which=0)
+    assert f[0] == -1
+
+
+def test_render_oracle_golden_and_sharding(orc, scene_files):
+    """Matched-seed accumulation buffer of the oracle against the committed golden vector, and exact
+    additivity of sample shards (what the multi-GPU reduce relies on)."""
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        g = json.load(f)
+    for name in ("cornell-box", "veach-mis"):
+        S = _load_scene(orc, scene_files, name)
+        S.build_new_bvh(g[name]["thresh_n"])
+        cam = g[name]["camera"]
+        M = orc.inverse_view_matrix(cam["eye"], cam["lookat"], cam["up"])
+        fov = float(np.float32(np.float32(cam["fov_y"]) * np.float32(math.pi) / np.float32(180)))
+        W, H, spp = 64, 48, 4
+        acc, st = S.render(cam["eye"], M, fov, W, H, 0, spp, cam["P_RR"], cam["light_sample_n"], seed=0)
+        assert hashlib.sha256(acc.tobytes()).hexdigest() == g[name]["oracle_accum_64x48_spp4_sha256"]
+        a0, _ = S.render(cam["eye"], M, fov, W, H, 0, 1, cam["P_RR"], cam["light_sample_n"], seed=0)
+        a1, _ = S.render(cam["eye"], M, fov, W, H, 1, 4, cam["P_RR"], cam["light_sample_n"], seed=0)
+        assert np.array_equal(a0 + a1, acc)
+        acc2, _ = S.render(cam["eye"], M, fov, W, H, 0, spp, cam["P_RR"], cam["light_sample_n"], seed=1)
+        assert not np.array_equal(acc, acc2)
+        lin, rgb = orc.resolve(acc, W * H, spp)
+        assert rgb.max() > 0 and np.isfinite(lin).all()
+
+
+def test_compat_estimator_converges_to_analytic_value(orc):
+    """Furnace-like check of the compat estimator's direct lighting: one diffuse floor quad under one
+    downward light quad, no occluders; the mean radiance at the floor centre has a closed form for the
+    reference's (non-uniform) light sampling only numerically, so compare two independent seeds and
+    the energy bound instead."""
+    floor = [[-50, 0, -50, -50, 0, 50, 50, 0, 50], [-50, 0, -50, 50, 0, 50, 50, 0, -50]]
+    light = [[-1, 5, -1, 1, 5, -1, 1, 5, 1], [-1, 5, -1, 1, 5, 1, -1, 5, 1]]
+    verts = np.array(floor + light, np.float32)
+    mats = [[0.5, 0.5, 0.5, 0, 0, 0, 1], [0, 0, 0, 10, 10, 10, 1]]
+    S = orc.Scene().add_arrays(verts, np.array([0, 0, 1, 1], np.int32), np.array([0, 0, 1, 1], np.int32), mats)
+    S.build_new_bvh(2)
+    tr = S.tris()
+    assert tr["normal"][0][1] == 1.0 and tr["normal"][2][1] == -1.0
+    eye, look = [0, 3, -6], [0, 0, 0]
+    M = orc.inverse_view_matrix(eye, look, [0, 1, 0])
+    W, H = 16, 12
+    means = []
+    for seed in (0, 1):
+        acc, _ = S.render(eye, M, math.radians(30), W, H, 0, 256, 0.5, 2, seed=seed)
+        lin, _ = orc.resolve(acc, W * H, 256)
+        means.append(lin.reshape(H, W, 3)[H // 2, W // 2])
+    assert np.allclose(means[0], means[1], rtol=0.1)
+    # direct light at the floor centre from a 2x2 light of radiance 10 at height 5: E ~ L*A*cos*cos/d^2 = 10*4/25
+    assert 0.05 < means[0][0] < 10 * 4 / 25 * 0.5 / math.pi * 3

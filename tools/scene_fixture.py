@@ -69,7 +69,7 @@ def unpack(fixture_path, out_dir):
     # every vertex gets a vn and a vt so that "a/a/a" corners stay valid for the reference's parser
     # (include/OBJLoader.h:98-118 reads all three indices; Loader.h:70-72 indexes normals by vertex)
     for x, y, z in verts:
-        lines.append("v %s %s %s\nvn 0 1 0\nvt 0 0\n" % (repr(float(np.float32(x))) if False else "%.9g" % x, "%.9g" % y, "%.9g" % z))
+        lines.append("v %s %s %s\nvn 0 1 0\nvt 0 0\n" % ("%.9g" % x, "%.9g" % y, "%.9g" % z))
     bounds = [s for s, _ in meta["groups"]] + [len(faces)]
     for gi, (start, mat) in enumerate(meta["groups"]):
         lines.append("g\nusemtl %s\n" % mat)
