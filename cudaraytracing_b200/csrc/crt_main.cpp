@@ -21,12 +21,23 @@ static std::string base_of(const std::string& p) {
     size_t k = q.find_last_of('/');
     return k == std::string::npos ? q : q.substr(k + 1);
 }
-// The shipped configs name paths relative to build/Debug ("../../scenes/..."): try the path as
-// given, under --root, next to the config file, and by file name next to the config file.
-static std::string resolve(const std::string& p, const std::string& root, const std::string& cfg_dir, bool is_dir) {
-    std::vector<std::string> cand = {p, root + "/" + p, cfg_dir + "/" + p, is_dir ? cfg_dir : cfg_dir + "/" + base_of(p)};
-    for (auto& c : cand) if (exists(c)) return c;
-    return p;
+// The shipped configs name paths relative to build/Debug ("../../scenes/..."). The OBJ is looked up as
+// given (cwd), under --root, next to the config file, and by file name next to the config file; MTL_dir
+// is then taken relative to the same base (or is the config's directory).
+static void resolve(const std::string& obj, const std::string& mtl, const std::string& root, const std::string& cfg_dir,
+                    std::string* obj_out, std::string* mtl_out) {
+    const bool absolute = !obj.empty() && obj[0] == '/';
+    std::vector<std::string> bases = absolute ? std::vector<std::string>{""} : std::vector<std::string>{cfg_dir + "/", root + "/", ""};
+    for (auto& b : bases) {
+        if (!exists(b + obj)) continue;
+        *obj_out = b + obj;
+        std::string m = (!mtl.empty() && mtl[0] == '/') ? mtl : b + mtl;
+        *mtl_out = exists(m) ? m : dir_of(*obj_out);
+        return;
+    }
+    if (exists(cfg_dir + "/" + base_of(obj))) { *obj_out = cfg_dir + "/" + base_of(obj); *mtl_out = cfg_dir; return; }
+    *obj_out = obj;
+    *mtl_out = mtl;
 }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -67,7 +78,8 @@ int main(int argc, char** argv) {
     DIE_IF(crt_scene_create(&scene), "scene_create");
     double t0 = now_ms();
     for (uint32_t k = 0; k < cfg.n_obj; ++k) {
-        std::string obj = resolve(cfg.obj_path[k], root, cfg_dir, false), mtl = resolve(cfg.mtl_dir[k], root, cfg_dir, true);
+        std::string obj, mtl;
+        resolve(cfg.obj_path[k], cfg.mtl_dir[k], root, cfg_dir, &obj, &mtl);
         DIE_IF(crt_scene_add_obj(scene, obj.c_str(), mtl.c_str()), "add_obj");
     }
     double t1 = now_ms();
