@@ -51,7 +51,8 @@ BVH_NODE = np.dtype([("c0lox", "<f4"), ("c0hix", "<f4"), ("c0loy", "<f4"), ("c0h
 
 
 def lib_path():
-    return os.path.join(_HERE, "libcrt.so")
+    # CRT_LIB: development override used by tools/variant_bench.py to compare kernel variants
+    return os.environ.get("CRT_LIB") or os.path.join(_HERE, "libcrt.so")
 
 
 def load_library():

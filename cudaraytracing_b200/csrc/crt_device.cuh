@@ -204,6 +204,128 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
     return best;
 }
 
+// ---- persistent-lane traversal -------------------------------------------------------------
+// The per-ray rule is exactly traverse<MODE> above (same visits in the same order, so the oracle's
+// node/triangle counts apply); what changes is how a warp's lanes are kept busy:
+//   * every lane owns one ray at a time and, when it finishes, takes the next ray of the queue
+//     (warp-aggregated atomicAdd on `fetch`) as soon as at least kRefillLanes lanes are idle, instead of
+//     waiting for the slowest ray of a fixed group of 32;
+//   * "while-while" phases (Aila & Laine 2009): all lanes walk inner nodes until each holds a leaf, then
+//     all lanes intersect their leaf, which keeps lanes on the same instructions.
+// load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result.
+static constexpr int kDone = 0x7ffffffe;
+#ifndef CRT_REFILL_LANES
+#define CRT_REFILL_LANES 8
+#endif
+static constexpr int kRefillLanes = CRT_REFILL_LANES;
+#ifndef CRT_NODE_BREAK
+#define CRT_NODE_BREAK 0
+#endif
+static constexpr int kNodeBreak = CRT_NODE_BREAK;
+
+template <int MODE, int STRAT, typename Load, typename Done>
+CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int stack[kStackSize];
+    int sp = 0, cur = kDone;
+    uint32_t idx = 0;
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0);
+    float tmax = 0.0f, tlimit = 0.0f;
+    HitRec best;
+    best.t = FLT_MAX; best.slot = -1; best.face = -1;
+    bool have = false, exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (idle) {
+            const int n_idle = __popc(idle);
+            if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!have) {
+                    const uint32_t i = base + __popc(idle & lt_mask);
+                    if (i < n) {
+                        idx = i;
+                        const bool live = load(i, o, d, tmax);
+                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        tlimit = MODE == 0 ? FLT_MAX : tmax;
+                        best.t = FLT_MAX; best.slot = -1; best.face = -1;
+                        sp = 0;
+                        cur = (live && sc.n_nodes) ? 0 : kDone;
+                        have = true;
+                    }
+                }
+                if (base + (uint32_t)n_idle >= n) exhausted = true;
+            }
+            if (!__any_sync(0xffffffffu, have)) {
+                if (exhausted) break;
+                continue;
+            }
+        }
+        if (have) {
+            // inner nodes until this lane holds a leaf (or is finished)
+            // STRAT 0: while-while (walk nodes until a leaf); STRAT 1: if-if (one node step per turn)
+            bool first = true;
+            while (cur >= 0 && cur != kDone && (STRAT == 0 || first)) {
+                first = false;
+                if (cur == kEmptyChild) { cur = sp ? stack[--sp] : kDone; continue; }   // absent child of a one-leaf scene
+                const float4 n0 = __ldg(sc.nodes + 4 * (size_t)cur + 0);
+                const float4 n1 = __ldg(sc.nodes + 4 * (size_t)cur + 1);
+                const float4 n2 = __ldg(sc.nodes + 4 * (size_t)cur + 2);
+                const float4 n3 = __ldg(sc.nodes + 4 * (size_t)cur + 3);
+                const float lim = tlimit * 1.0001f;
+                float e0, e1;
+                const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);
+                const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1);
+                const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                if (h0 && h1) {
+                    int nearc = c0, farc = c1;
+                    if (e1 < e0) { nearc = c1; farc = c0; }
+                    stack[sp++] = farc;
+                    cur = nearc;
+                } else if (h0) cur = c0;
+                else if (h1) cur = c1;
+                else cur = sp ? stack[--sp] : kDone;
+                // leave the node phase once fewer than kNodeBreak lanes are still walking nodes: the
+                // others are waiting with a leaf in hand (fresh rays have long first descents)
+                if (kNodeBreak > 0 && __popc(__activemask()) < kNodeBreak) break;
+            }
+            if (cur < 0 && (STRAT == 0 || first)) {   // one leaf
+                int slot = ~cur;
+                bool stop = false;
+                for (;; ++slot) {
+                    const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
+                    const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
+                    const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
+                    const uint32_t fw = __float_as_uint(a.w);
+                    const int face = (int)(fw & ~kLastBit);
+                    float t;
+                    if (tri_test(mk3(a), mk3(b), mk3(c), o, d, &t) && t > kEps) {
+                        if (MODE == 0) {
+                            if (t < best.t || (t == best.t && face < best.face)) {
+                                best.t = t; best.slot = slot; best.face = face;
+                                tlimit = t;
+                            }
+                        } else if (tmax - t > kEps) {
+                            best.t = t; best.slot = slot; best.face = face;
+                            stop = true;
+                            break;
+                        }
+                    }
+                    if (fw & kLastBit) break;
+                }
+                cur = (stop || sp == 0) ? kDone : stack[--sp];
+            }
+            if (cur == kDone) {
+                done(idx, best);
+                have = false;
+            }
+        }
+    }
+}
+
 // ---- fixed-point accumulation (DESIGN.md "Accumulation"): radiance * 2^32 summed in int64, which
 // makes the image independent of atomic ordering, wavefront scheduling and GPU count.
 CRT_DEV long long quantize(float c) {

@@ -10,6 +10,10 @@
 // The estimator arithmetic mirrors oracle/orc_render.cpp operation by operation (-fmad=false).
 #include "crt_gpu.h"
 
+#ifndef CRT_STRAT
+#define CRT_STRAT 0
+#endif
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -107,23 +111,20 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene
 // ray batches
 // =============================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(128) k_trace_batch(SceneView sc, const float4* __restrict__ rays, unsigned long long n,
+__global__ void __launch_bounds__(128) k_trace_batch(SceneView sc, const float4* __restrict__ rays, uint32_t n,
                                                      float* __restrict__ t_out, int* __restrict__ face_out,
-                                                     unsigned long long* __restrict__ fetch) {
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(fetch, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned long long i = base + lane;
-        if (i < n) {
-            float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
-            HitRec h = traverse<MODE>(sc, mk3(ro), mk3(rd), ro.w);
+                                                     uint32_t* __restrict__ fetch) {
+    trace_persistent<MODE, CRT_STRAT>(
+        sc, n, fetch,
+        [&](uint32_t i, V3& o, V3& d, float& tmax) {
+            const float4 ro = __ldg(rays + 2 * (size_t)i), rd = __ldg(rays + 2 * (size_t)i + 1);
+            o = mk3(ro); d = mk3(rd); tmax = ro.w;
+            return true;
+        },
+        [&](uint32_t i, const HitRec& h) {
             if (t_out) t_out[i] = h.t;
             if (face_out) face_out[i] = h.face;
-        }
-    }
+        });
 }
 
 static int g_num_sms = 0;
@@ -139,25 +140,35 @@ static int num_sms() {
 
 int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
                       cudaStream_t st, float* kernel_ms) {
-    unsigned long long* fetch = nullptr;
-    CRT_CUDA(cudaMalloc(&fetch, sizeof(unsigned long long)));
-    cudaMemsetAsync(fetch, 0, sizeof(unsigned long long), st);
+    uint32_t* fetch = nullptr;
+    CRT_CUDA(cudaMalloc(&fetch, sizeof(uint32_t)));
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    int blocks = num_sms() * 16;
-    cudaEventRecord(a, st);
-    if (mode == CRT_RAY_CLOSEST) k_trace_batch<0><<<blocks, 128, 0, st>>>(ds.view(), d_rays, n, d_t, d_face, fetch);
-    else k_trace_batch<1><<<blocks, 128, 0, st>>>(ds.view(), d_rays, n, d_t, d_face, fetch);
-    cudaEventRecord(b, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    float ms = 0;
-    if (e == cudaSuccess) cudaEventElapsedTime(&ms, a, b);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0>, 128, 0);
+    const int blocks = num_sms() * std::max(occ, 1);
+    const uint64_t chunk = 1ull << 30;                   // queue indices are 32-bit
+    float ms_total = 0;
+    cudaError_t e = cudaSuccess;
+    for (uint64_t off = 0; off < n && e == cudaSuccess; off += chunk) {
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, n - off);
+        cudaMemsetAsync(fetch, 0, sizeof(uint32_t), st);
+        cudaEventRecord(a, st);
+        if (mode == CRT_RAY_CLOSEST)
+            k_trace_batch<0><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, d_t ? d_t + off : nullptr, d_face ? d_face + off : nullptr, fetch);
+        else
+            k_trace_batch<1><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, d_t ? d_t + off : nullptr, d_face ? d_face + off : nullptr, fetch);
+        cudaEventRecord(b, st);
+        e = cudaStreamSynchronize(st);
+        float ms = 0;
+        if (e == cudaSuccess) { cudaEventElapsedTime(&ms, a, b); ms_total += ms; }
+    }
     cudaEventDestroy(a); cudaEventDestroy(b);
     cudaFree(fetch);
     if (e != cudaSuccess) return cuda_fail(e, "k_trace_batch");
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_trace_batch launch");
-    if (kernel_ms) *kernel_ms = ms;
+    if (kernel_ms) *kernel_ms = ms_total;
     return CRT_OK;
 }
 
@@ -266,48 +277,27 @@ __global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c
 __global__ void __launch_bounds__(128) k_extend(SceneView sc, Counters* c, const float4* __restrict__ q_o,
                                                 const float4* __restrict__ q_d, float* __restrict__ hit_t,
                                                 int* __restrict__ hit_slot) {
-    const uint32_t n = c->n_cur;
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&c->fetch_extend, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            float4 o = q_o[i], d = q_d[i];
-            HitRec h = traverse<0>(sc, mk3(o), mk3(d), FLT_MAX);
-            hit_t[i] = h.t;
-            hit_slot[i] = h.slot;
-        }
-    }
+    trace_persistent<0, CRT_STRAT>(
+        sc, c->n_cur, &c->fetch_extend,
+        [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
+        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });
 }
 
 // SPECULAR probe rays (reference Render.cuh:303): traced only when the continuation ray hit.
 __global__ void __launch_bounds__(128) k_probe(SceneView sc, Counters* c, const uint32_t* __restrict__ list,
                                                const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
                                                const int* __restrict__ hit_slot, int* __restrict__ pr_hit) {
-    const uint32_t n = c->n_probe_cur;
-    const int lane = threadIdx.x & 31;
     unsigned long long traced = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&c->fetch_probe, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t k = base + lane;
-        if (k < n) {
-            uint32_t i = list[k];
-            int res = -1;
-            if (hit_slot[i] >= 0) {
-                float4 o = pr_o[i], d = pr_d[i];
-                HitRec h = traverse<0>(sc, mk3(o), mk3(d), FLT_MAX);
-                res = h.slot;
-                traced++;
-            }
-            pr_hit[i] = res;
-        }
-    }
+    trace_persistent<0, CRT_STRAT>(
+        sc, c->n_probe_cur, &c->fetch_probe,
+        [&](uint32_t k, V3& o, V3& d, float& tmax) {
+            const uint32_t i = list[k];
+            if (hit_slot[i] < 0) return false;            // continuation missed: the probe is not traced
+            o = mk3(pr_o[i]); d = mk3(pr_d[i]); tmax = FLT_MAX; traced++;
+            return true;
+        },
+        [&](uint32_t k, const HitRec& h) { pr_hit[list[k]] = h.slot; });
+    const int lane = threadIdx.x & 31;
     for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
     if (lane == 0 && traced) atomicAdd(&c->stat_probe, traced);
 }
@@ -469,20 +459,12 @@ __global__ void __launch_bounds__(128) k_shade_compat(SceneView sc, Counters* c,
 __global__ void __launch_bounds__(128) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
                                                 const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
                                                 long long* __restrict__ accum) {
-    const uint32_t n = c->n_shadow;
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&c->fetch_shadow, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            float4 o = sh_o[i], d = sh_d[i];
-            HitRec h = traverse<1>(sc, mk3(o), mk3(d), o.w);
-            if (h.slot < 0) accum_add(accum, __float_as_uint(d.w), mk3(sh_c[i]));
-        }
-    }
+    trace_persistent<1, CRT_STRAT>(
+        sc, c->n_shadow, &c->fetch_shadow,
+        [&](uint32_t i, V3& o, V3& d, float& tmax) { const float4 a = sh_o[i]; o = mk3(a); tmax = a.w; d = mk3(sh_d[i]); return true; },
+        [&](uint32_t i, const HitRec& h) {
+            if (h.slot < 0) accum_add(accum, __float_as_uint(sh_d[i].w), mk3(sh_c[i]));
+        });
 }
 
 // E11 (reference Render.cuh:348,350): mean over spp, clamp, pow 0.6, *255, truncate.
