@@ -24,10 +24,72 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (fixture, width, height, spp, light_sample_n, description)   None -> value from the shipped config
-    "c1": ("cornell-box", None, None, None, None, "C1 cornell-box 800x600 spp=2 light_sample_n=2 bvh_thresh_n=2 P_RR=0.6 (shipped config.json)"),
-    "c2": ("veach-mis", None, None, None, None, "C2 veach-mis 800x600 spp=4 light_sample_n=1 (shipped config.json)"),
-    "c3": ("cornell-box", 3840, 2160, 1024, None, "C3 cornell-box 3840x2160 spp=1024, samples sharded across the GPUs"),
+    # name: (source, width, height, spp, description)   None -> value from the shipped config
+    "c1": ("cornell-box", None, None, None, "C1 cornell-box 800x600 spp=2 light_sample_n=2 bvh_thresh_n=2 P_RR=0.6 (shipped config.json)"),
+    "c2": ("veach-mis", None, None, None, "C2 veach-mis 800x600 spp=4 light_sample_n=1 (shipped config.json)"),
+    "c3": ("cornell-box", 3840, 2160, 1024, "C3 cornell-box 3840x2160 spp=1024, samples sharded across the GPUs"),
+    "c4": ("synthetic", 1920, 1080, 64, "C4 synthetic 10M-triangle heightfield scene 1920x1080 spp=64 (GPU BVH build + deep traversal)"),
+    "c5": ("synthetic", 0, 0, 0, "C5 incoherent rays: 100M random rays vs the 10M-triangle BVH, closest-hit and any-hit"),
+}
+
+
+class Workload:
+    """Camera + render settings + how to build the scene (product and oracle side)."""
+
+    def __init__(self, name, small=False):
+        import numpy as np
+        import cudaraytracing_b200 as crt
+        self.name = name
+        source, W, H, spp, self.desc = WORKLOADS[name]
+        self.source = source
+        self.tmp = tempfile.mkdtemp(prefix="crt_bench_")
+        if source == "synthetic":
+            from tools import synthetic as sy
+            c = sy.C4_CAMERA
+            self.eye, self.lookat, self.up = (np.asarray(c[k], np.float32) for k in ("eye", "lookat", "up"))
+            self.fov_y = c["fov_y"]
+            self.width, self.height, self.spp = W or c["width"], H or c["height"], spp or c["spp"]
+            self.light_sample_n, self.P_RR, self.bvh_thresh_n = c["light_sample_n"], c["P_RR"], c["bvh_thresh_n"]
+            self.grid_n = int(os.environ.get("CRT_C4_GRID", "257" if small else str(sy.C4_FULL_N)))
+            self.obj = None
+        else:
+            from tools import scene_fixture as sf
+            cfg = crt.load_config(sf.unpack(sf.fixture(source), self.tmp))
+            self.eye, self.lookat, self.up, self.fov_y = cfg.eye, cfg.lookat, cfg.up, cfg.fov_y
+            self.width, self.height, self.spp = W or cfg.width, H or cfg.height, spp or cfg.spp
+            self.light_sample_n, self.P_RR, self.bvh_thresh_n = cfg.light_sample_n, cfg.P_RR, cfg.bvh_thresh_n
+            self.obj = os.path.join(self.tmp, cfg.OBJ_paths[0][0])
+        self.fovy_rad = np.float32(np.float32(self.fov_y) * np.float32(math.pi) / np.float32(180.0))
+        self._arrays = None
+
+    def arrays(self):
+        if self._arrays is None:
+            from tools import synthetic as sy
+            self._arrays = sy.c4_scene(self.grid_n)
+        return self._arrays
+
+    def build_scene(self, crt, device):
+        if self.obj:
+            scene = crt.Scene().add_obj(self.obj, self.tmp)
+        else:
+            scene = crt.Scene().add_triangles(*self.arrays())
+        return scene, scene.set_BVH(self.bvh_thresh_n, device=device)
+
+    def build_oracle(self, orc):
+        import numpy as np
+        if self.obj:
+            S = orc.Scene().add_obj(self.obj, self.tmp)
+        else:
+            v, m, o, mats = self.arrays()
+            S = orc.Scene().add_arrays(v, m.astype(np.int32), o.astype(np.int32), mats)
+        S.build_new_bvh(self.bvh_thresh_n)
+        return S
+
+
+DATA_NOTE = {
+    "fixture": "synthetic camera paths (Philox seed 0) over the reference's cornell-box / veach-mis geometry "
+               "(tests/golden/scenes fixtures, regenerated to OBJ/MTL at run time)",
+    "synthetic": "procedural scene generated from a seed at run time (tools/synthetic.py), Philox seed 0",
 }
 
 S_NODE, S_TRI, S_RAY_IO_CLOSEST, S_RAY_IO_ANY = 64, 48, 32 + 8, 48 + 0   # bytes, DESIGN.md "Algorithmic bytes"
@@ -97,39 +159,24 @@ def dist_env():
     return rank, world, local
 
 
-def prepare_scene_files(workload):
-    from tools import scene_fixture as sf
-    import cudaraytracing_b200 as crt
-    fixture, W, H, spp, lsn, desc = WORKLOADS[workload]
-    tmp = tempfile.mkdtemp(prefix="crt_bench_")
-    cfg_path = sf.unpack(sf.fixture(fixture), tmp)
-    cfg = crt.load_config(cfg_path)
-    if W: cfg.width, cfg.height = W, H
-    if spp: cfg.spp = spp
-    if lsn: cfg.light_sample_n = lsn
-    obj = os.path.join(tmp, cfg.OBJ_paths[0][0])
-    return cfg, obj, tmp, desc
-
-
 # ------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port) — bounded sample of the same workload; also yields the per-ray
 # node / triangle visit counts the roofline uses (counted by the oracle on the same BVH and rule).
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline_leg(cfg, obj, mtl_dir, budget_samples=2.0e6):
+def cpu_baseline_leg(cfg, budget_samples=2.0e6):
     from oracle import orc
     import numpy as np
-    S = orc.Scene().add_obj(obj, mtl_dir)
-    S.build_new_bvh(cfg.bvh_thresh_n)
-    M = orc.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    S = cfg.build_oracle(orc)
+    M = orc.inverse_view_matrix(cfg.eye, cfg.lookat, cfg.up)
     # bounded sample: the full frame at reduced resolution (same camera, same per-ray statistics), 1..spp samples
     scale = 1
     while (cfg.width // scale) * (cfg.height // scale) > budget_samples:
         scale *= 2
     w, h = cfg.width // scale, cfg.height // scale
     spp = max(1, min(cfg.spp, int(budget_samples // (w * h))))
-    threads = orc.max_threads()
+    threads = os.cpu_count() or orc.max_threads()          # torchrun exports OMP_NUM_THREADS=1; use every host core
     t0 = time.time()
-    _, st = S.render(cfg.eye_pos, M, float(cfg.fovy_rad), w, h, 0, spp, cfg.P_RR, cfg.light_sample_n, threads=threads)
+    _, st = S.render(cfg.eye, M, float(cfg.fovy_rad), w, h, 0, spp, cfg.P_RR, cfg.light_sample_n, threads=threads)
     dt = time.time() - t0
     per_ray = {
         "closest_inner": st["closest_inner"] / max(st["closest_rays"], 1), "closest_tris": st["closest_tris"] / max(st["closest_rays"], 1),
@@ -156,11 +203,11 @@ def ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    cfg, obj, tmp, desc = prepare_scene_files(args.workload)
+    cfg = Workload(args.workload)
+    desc = cfg.desc
     npix = cfg.width * cfg.height
-    scene = crt.Scene().add_obj(obj, tmp)
-    build_ms = scene.set_BVH(cfg.bvh_thresh_n, device=local)
-    M = crt.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    scene, build_ms = cfg.build_scene(crt, local)
+    M = crt.inverse_view_matrix(cfg.eye, cfg.lookat, cfg.up)
     render = crt.Render(scene, cfg.width, cfg.height, cfg.spp, cfg.P_RR, cfg.light_sample_n)
     render.set_seed(0)
     stream = torch.cuda.current_stream()
@@ -180,13 +227,13 @@ def ours(args):
     launches = [0]
 
     def step_device():
-        render.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+        render.run_view(cfg.eye, M, cfg.fovy_rad)
         launches[0] += render.stats()["kernel_launches"]
         cd.reduce_accum(accum_t, 0)
 
     def step_e2e():
         # host buffers in, host buffer out: camera (13 floats) goes in with the call, the RGB8 frame comes back
-        render.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+        render.run_view(cfg.eye, M, cfg.fovy_rad)
         cd.reduce_accum(accum_t, 0)
         if rank == 0:
             render.get_frame_buffer(frame_np)
@@ -228,12 +275,12 @@ def ours(args):
     roof, cpu_base, extra = None, None, {}
     if rank == 0:
         peaks, peak_kind = load_peaks()
-        cpu_base, per_ray = cpu_baseline_leg(cfg, obj, tmp)
+        cpu_base, per_ray = cpu_baseline_leg(cfg)
         render.clear_range()
         spp_probe = min(cfg.spp, 16)
         render.set_spp(spp_probe)
         render.set_stage_timing(True)
-        render.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+        render.run_view(cfg.eye, M, cfg.fovy_rad)
         st = render.stats()
         render.set_stage_timing(False)
         render.set_spp(cfg.spp)
@@ -268,8 +315,7 @@ def ours(args):
         out = {
             "metric": "Msamples/s", "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic camera paths over the reference's cornell-box / veach-mis "
-            "geometry (tests/golden/scenes fixtures, regenerated to OBJ/MTL at run time), seed 0",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE[cfg.source if cfg.source == "synthetic" else "fixture"],
             "config": {"workload": desc, "width": cfg.width, "height": cfg.height, "spp": cfg.spp, "light_sample_n": cfg.light_sample_n,
                        "P_RR": round(float(cfg.P_RR), 4), "bvh_thresh_n": cfg.bvh_thresh_n, "estimator": "compat",
                        "parallelism": "samples sharded over %d GPU(s), one int64 NCCL reduce" % world,
@@ -295,7 +341,12 @@ def reference(args):
     if rank != 0:
         return
     so = os.path.join(ROOT, "oracle", "_ref", "libref.so")
-    cfg, obj, tmp, desc = prepare_scene_files(args.workload)
+    cfg = Workload(args.workload)
+    obj, tmp, desc = cfg.obj, cfg.tmp, cfg.desc
+    if obj is None:
+        print(json.dumps({"impl": "reference", "unavailable": "C4/C5: the reference's host BVH build (std::sort of 152-byte triangles at every "
+                          "level, BVH.h:64-76) over 10M triangles and its 140-byte device triangles are not run in this round"}))
+        return
     if not os.path.exists(so):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref.so not built (needs /root/reference at build time)"}))
         return
@@ -322,7 +373,7 @@ def reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "reference device init failed rc=%d (per-pixel stacks need %.1f GB)" %
                           (rc, 8712.0 * cfg.width * cfg.height / 1e9)}))
         return
-    eye = np.asarray(cfg.eye_pos, np.float32)
+    eye = np.asarray(cfg.eye, np.float32)
     M = np.zeros(9, np.float32)
     R.ref_inverse_view(eye.ctypes.data_as(C.c_void_p), np.asarray(cfg.lookat, np.float32).ctypes.data_as(C.c_void_p),
                        np.asarray(cfg.up, np.float32).ctypes.data_as(C.c_void_p), M.ctypes.data_as(C.c_void_p))
@@ -367,6 +418,92 @@ def reference(args):
         "clocks": clocks}), flush=True)
 
 
+def ours_c5(args):
+    """C5: 100M incoherent rays against the 10M-triangle BVH; value = closest-hit Mrays/s (any-hit reported beside it)."""
+    import numpy as np
+    import torch
+    import cudaraytracing_b200 as crt
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    cfg = Workload("c5")
+    scene, build_ms = cfg.build_scene(crt, local)
+    n_total = int(os.environ.get("CRT_C5_RAYS", "100000000"))
+    n0, n1 = rank * n_total // world, (rank + 1) * n_total // world      # independent rays: shard, no collective
+    n = n1 - n0
+    stream = torch.cuda.current_stream()
+    rays = torch.empty((n, 8), dtype=torch.float32, device=dev)
+    t_out = torch.empty(n, dtype=torch.float32, device=dev)
+    f_out = torch.empty(n, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    res = {}
+    for mode, name in ((crt.RAY_CLOSEST, "closest"), (crt.RAY_ANY, "any")):
+        scene.random_rays_device(rays.data_ptr(), n, start=n0, key=0xC5, any_hit=(mode == crt.RAY_ANY), stream=stream.cuda_stream)
+        for _ in range(args.warmup):
+            scene.trace_rays_device(rays.data_ptr(), n, mode, t_out.data_ptr(), f_out.data_ptr(), stream.cuda_stream)
+        flush.zero_()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0 and mode == crt.RAY_CLOSEST:
+            sampler.start()
+        kms = 0.0
+        for _ in range(args.steps):
+            kms += scene.trace_rays_device(rays.data_ptr(), n, mode, t_out.data_ptr(), f_out.data_ptr(), stream.cuda_stream)
+        barrier()
+        if rank == 0 and mode == crt.RAY_CLOSEST:
+            res["clocks"] = sampler.stop()
+        t = torch.tensor([kms], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        res[name] = dict(ms=float(t[0]) / args.steps, mrays=n_total * args.steps / (float(t[0]) * 1e3), hit_frac=float((f_out >= 0).float().mean()))
+    # e2e through the host-buffer entry point on a bounded batch (rays H2D, results D2H inside the timed call)
+    nb = min(n, 10_000_000)
+    host_rays = rays[:nb].cpu().numpy()
+    t0 = time.time()
+    scene.trace_rays(host_rays, crt.RAY_CLOSEST)
+    e2e_s = time.time() - t0
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        # algorithmic bytes from an oracle count on a bounded sample of the same rays / same BVH
+        from oracle import orc
+        O = cfg.build_oracle(orc)
+        sample = rays[:200000].cpu().numpy()
+        _, _, st = O.trace(sample, which=0, mode=0, want_stats=True, threads=os.cpu_count())
+        t0 = time.time()
+        O.trace(sample, which=0, mode=0, threads=os.cpu_count())
+        cpu_dt = time.time() - t0
+        bpr = st["inner"] / st["rays"] * S_NODE + st["tris"] / st["rays"] * S_TRI + S_RAY_IO_CLOSEST
+        ach = res["closest"]["mrays"] * 1e6 * bpr / 1e9
+        print(json.dumps({
+            "metric": "Mrays/s (closest-hit)", "value": round(res["closest"]["mrays"], 1), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(res["closest"]["ms"], 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": DATA_NOTE["synthetic"],
+            "config": {"workload": cfg.desc, "rays": n_total, "triangles": scene.counts()["n_tris"], "nodes": scene.counts()["n_nodes"],
+                       "l2": "BVH + triangles (%.0f MB) and the ray buffers exceed L2; 256 MiB flush before the timed region" %
+                             ((scene.counts()["n_nodes"] * 64 + scene.counts()["n_tris"] * 64) / 1e6)},
+            "any_hit": {"mrays_s": round(res["any"]["mrays"], 1), "ms_per_step": round(res["any"]["ms"], 3), "blocked_frac": round(res["any"]["hit_frac"], 4)},
+            "closest_hit_frac": round(res["closest"]["hit_frac"], 4),
+            "e2e": {"value": round(nb / e2e_s / 1e6, 1), "unit": "Mrays/s", "h2d_bytes_per_step": nb * 32, "d2h_bytes_per_step": nb * 8,
+                    "note": "crt_trace_rays with host buffers on a %d-ray batch" % nb},
+            "gpu_launches": 2 * args.steps, "clocks": res.get("clocks"),
+            "roofline": {"bound": "hbm", "kernel": "k_trace_batch<closest>", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_kind": peak_kind,
+                         "per_ray": {"inner": round(st["inner"] / st["rays"], 2), "tris": round(st["tris"] / st["rays"], 2), "bytes": round(bpr, 1)}},
+            "cpu_baseline": {"value": round(len(sample) / cpu_dt / 1e6, 3), "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d of the same rays, oracle traversal, %.1f s" % (len(sample), cpu_dt)},
+            "bvh_build_gpu_ms": round(build_ms, 3)}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def cpu_model():
     try:
         with open("/proc/cpuinfo") as f:
@@ -389,6 +526,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         reference(args)
+    elif args.workload == "c5":
+        ours_c5(args)
     else:
         ours(args)
 

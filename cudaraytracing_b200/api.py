@@ -84,6 +84,7 @@ def load_library():
         "crt_scene_destroy": [vp],
         "crt_trace_rays": [vp, vp, u64, i32, vp, vp, C.POINTER(f32)],
         "crt_trace_rays_device": [vp, vp, u64, i32, vp, vp, vp, C.POINTER(f32)],
+        "crt_random_rays_device": [vp, vp, u64, u64, u32, i32, vp],
         "crt_render_create": [vp, u32, u32, pp],
         "crt_render_set_spp": [vp, u32],
         "crt_render_set_p_rr": [vp, f32],
@@ -263,6 +264,10 @@ class Scene:
         ms = C.c_float()
         _check(self.L.crt_trace_rays_device(self.h, d_rays_ptr, n, mode, d_t_ptr, d_face_ptr, stream, C.byref(ms)))
         return ms.value
+
+
+    def random_rays_device(self, d_rays_ptr, n, start=0, key=0xC5, any_hit=False, stream=None):
+        _check(self.L.crt_random_rays_device(self.h, d_rays_ptr, n, start, key, 1 if any_hit else 0, stream))
 
 
 class Render:

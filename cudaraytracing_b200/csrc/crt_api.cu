@@ -219,6 +219,13 @@ int crt_trace_rays(crt_scene* s, const float* rays, uint64_t n, int mode, float*
     return rc;
 }
 
+int crt_random_rays_device(crt_scene* s, void* d_rays, uint64_t n, uint64_t start, uint32_t key, int any_hit, void* stream) {
+    CHECK_ARG(s && (n == 0 || d_rays), "crt_random_rays_device: null argument");
+    if (!s->built) { set_error("crt_random_rays_device: BVH not built"); return CRT_ERR_STATE; }
+    CRT_CUDA(cudaSetDevice(s->dev.device));
+    return random_rays_device(s->dev, (float4*)d_rays, n, start, key, any_hit, (cudaStream_t)stream);
+}
+
 // ---- render ----------------------------------------------------------------------------------
 int crt_render_create(crt_scene* s, uint32_t width, uint32_t height, crt_render** out) {
     CHECK_ARG(s && out, "crt_render_create: null argument");

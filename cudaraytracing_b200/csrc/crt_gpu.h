@@ -53,6 +53,8 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene
 int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
                       cudaStream_t st, float* kernel_ms);
 
+int random_rays_device(const DeviceScene& ds, float4* d_rays, uint64_t n, uint64_t start, uint32_t key, int any_hit, cudaStream_t st);
+
 struct RenderSettings {
     uint32_t width = 0, height = 0;
     uint32_t spp = 16;               // Render.cuh:379 defaults

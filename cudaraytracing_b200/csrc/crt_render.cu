@@ -15,6 +15,7 @@
 #endif
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -169,6 +170,34 @@ int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, i
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_trace_batch launch");
     if (kernel_ms) *kernel_ms = ms_total;
+    return CRT_OK;
+}
+
+// C5 input: see crt_random_rays_device in include/crt.h (numpy statement: tools/synthetic.py:random_rays)
+__global__ void k_random_rays(float4* __restrict__ rays, unsigned long long n, unsigned long long start, float lox, float loy,
+                              float loz, float hix, float hiy, float hiz, float diag, uint32_t key, int any_hit) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long idx = start + i;
+        const uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32);
+        const uint4 a = philox4x32_10(make_uint4(c0, c1, 0u, 0u), key, 0u);
+        const uint4 b = philox4x32_10(make_uint4(c0, c1, 1u, 0u), key, 0u);
+        const float ox = lox + (hix - lox) * u01(a.x), oy = loy + (hiy - loy) * u01(a.y), oz = loz + (hiz - loz) * u01(a.z);
+        const float z = 1.0f - 2.0f * u01(a.w);
+        const float rad = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+        float sn, cs;
+        sincos_2pi(u01(b.x), &sn, &cs);
+        rays[2 * i] = make_float4(ox, oy, oz, any_hit ? u01(b.y) * diag : FLT_MAX);
+        rays[2 * i + 1] = make_float4(rad * cs, rad * sn, z, 0.0f);
+    }
+}
+
+int random_rays_device(const DeviceScene& ds, float4* d_rays, uint64_t n, uint64_t start, uint32_t key, int any_hit, cudaStream_t st) {
+    if (n == 0) return CRT_OK;
+    const float* b = ds.bounds;
+    double d2 = 0;
+    for (int k = 0; k < 3; ++k) { double e = (double)(b[3 + k] - b[k]); d2 += e * e; }
+    k_random_rays<<<num_sms() * 8, 256, 0, st>>>(d_rays, n, start, b[0], b[1], b[2], b[3], b[4], b[5], (float)sqrt(d2), key, any_hit);
+    CRT_CUDA(cudaGetLastError());
     return CRT_OK;
 }
 

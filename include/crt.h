@@ -136,6 +136,12 @@ int crt_trace_rays(crt_scene* s, const float* rays, uint64_t n, int mode, float*
 int crt_trace_rays_device(crt_scene* s, const void* d_rays, uint64_t n, int mode, void* d_t_out, void* d_face_out,
                           void* stream, float* kernel_ms);
 
+/* Incoherent-ray microbenchmark input (BASELINE config C5), generated on the device: ray i (i = start .. start+n-1)
+ * has its origin uniform in the scene's bounding box and its direction uniform on the sphere, from
+ * Philox4x32-10 with key (key, 0) and counters (i, 0) / (i, 1); any_hit != 0 draws tmax uniform in
+ * (0, box diagonal], else tmax = FLT_MAX. d_rays: n * 8 floats of device memory. */
+int crt_random_rays_device(crt_scene* s, void* d_rays, uint64_t n, uint64_t start, uint32_t key, int any_hit, void* stream);
+
 /* ---- render ---------------------------------------------------------------------------- */
 /* Render::Render, include/Render.cuh:379-433. The scene must outlive the render handle. */
 int crt_render_create(crt_scene* s, uint32_t width, uint32_t height, crt_render** out);
