@@ -55,7 +55,7 @@ class Workload:
         else:
             from tools import scene_fixture as sf
             cfg = crt.load_config(sf.unpack(sf.fixture(source), self.tmp))
-            self.eye, self.lookat, self.up, self.fov_y = cfg.eye, cfg.lookat, cfg.up, cfg.fov_y
+            self.eye, self.lookat, self.up, self.fov_y = cfg.eye_pos, cfg.lookat, cfg.up, cfg.fov_y
             self.width, self.height, self.spp = W or cfg.width, H or cfg.height, spp or cfg.spp
             self.light_sample_n, self.P_RR, self.bvh_thresh_n = cfg.light_sample_n, cfg.P_RR, cfg.bvh_thresh_n
             self.obj = os.path.join(self.tmp, cfg.OBJ_paths[0][0])
@@ -163,7 +163,7 @@ def dist_env():
 # CPU baseline (oracle port) — bounded sample of the same workload; also yields the per-ray
 # node / triangle visit counts the roofline uses (counted by the oracle on the same BVH and rule).
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline_leg(cfg, budget_samples=2.0e6):
+def cpu_baseline_leg(cfg, budget_samples=float(os.environ.get("CRT_CPU_BUDGET", "4.0e7"))):
     from oracle import orc
     import numpy as np
     S = cfg.build_oracle(orc)
