@@ -41,7 +41,7 @@ class _Config(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("probe_rays", C.c_uint64),
                 ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_total", C.c_float), ("ms_extend", C.c_float),
-                ("ms_shade", C.c_float), ("ms_shadow", C.c_float), ("ms_generate", C.c_float)]
+                ("ms_shade", C.c_float), ("ms_shadow", C.c_float), ("ms_generate", C.c_float), ("ms_tail", C.c_float)]
 
 
 BVH_NODE = np.dtype([("c0lox", "<f4"), ("c0hix", "<f4"), ("c0loy", "<f4"), ("c0hiy", "<f4"),

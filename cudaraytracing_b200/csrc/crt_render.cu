@@ -211,6 +211,7 @@ struct Counters {
     uint32_t gen_base, gen_count;
     uint32_t fetch_extend, fetch_shadow, fetch_probe;
     uint32_t iterations;
+    uint32_t tail_n, fetch_tail;       // paths handed to k_tail by the last k_prepare (0: none)
 };
 struct HostStatus { volatile uint32_t done; volatile uint32_t n_cur; volatile unsigned long long work_next; };
 
@@ -228,6 +229,7 @@ struct RenderParamsDev {
 };
 
 static constexpr uint32_t kFlagProbe = 0x100u;
+static constexpr uint32_t kTailDefault = 1u << 17;   // paths alive when k_tail takes over (CRT_TAIL overrides, 0 = never)
 
 struct Wavefront {
     uint32_t width = 0, height = 0;
@@ -247,16 +249,16 @@ struct Wavefront {
     HostStatus* status_dev = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    int grid_trace = 0, grid_shade = 0;
+    int grid_trace = 0, grid_shade = 0, grid_tail = 0;
 };
 
 // =============================================================================================
 // kernels
 // =============================================================================================
-__global__ void k_prepare(Counters* c, uint32_t pool, HostStatus* status) {
+__global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostStatus* status) {
     c->stat_shadow += c->n_shadow;
     uint32_t n_cur = c->n_next;
-    c->n_probe_cur = c->n_probe_next;
+    uint32_t n_probe = c->n_probe_next;
     c->n_next = 0;
     c->n_probe_next = 0;
     c->n_shadow = 0;
@@ -268,13 +270,18 @@ __global__ void k_prepare(Counters* c, uint32_t pool, HostStatus* status) {
     c->gen_work0 = c->work_next;
     n_cur += n_new;
     c->work_next += n_new;
-    c->n_cur = n_cur;
-    c->fetch_extend = c->fetch_shadow = c->fetch_probe = 0;
-    c->stat_extend += n_cur;
+    c->fetch_extend = c->fetch_shadow = c->fetch_probe = c->fetch_tail = 0;
     c->iterations += n_cur ? 1u : 0u;
+    // tail: every camera path has been started and few paths are alive -> k_tail finishes them
+    const bool tail = remaining == 0 && n_cur > 0 && n_cur <= tail_max;
+    c->tail_n = tail ? n_cur : 0u;
+    if (tail) n_cur = 0, n_probe = 0;
+    c->n_cur = n_cur;
+    c->n_probe_cur = n_probe;
+    c->stat_extend += n_cur;
     status->n_cur = n_cur;
     status->work_next = c->work_next;
-    if (n_cur == 0) status->done = 1;
+    if (n_cur == 0) status->done = 1;          // read by the host after this iteration's kernels have finished
     __threadfence_system();
 }
 
@@ -376,8 +383,93 @@ CRT_DEV V3 sample_probe_lobe(V3 out, float dtheta, float dphi, float u1, float u
     return mk3(st * cp, st * sp, ct);
 }
 
-// compat estimator, one path vertex per thread: the forward form of cast_ray_v2
-// (reference Render.cuh:199-328); statement shared with oracle/orc_render.cpp path_compat.
+// compat estimator, one path vertex: the forward form of cast_ray_v2 (reference Render.cuh:199-328);
+// statement shared with oracle/orc_render.cpp path_compat. Used by the wavefront shade kernel (shadow
+// rays and the continuation go to queues) and by the tail kernel (traced in place).
+//   shadow(needs_trace, pos, t_to_light, dir, contrib): called for every light sample by every lane that
+//   reached this vertex; when needs_trace it must trace the any-hit ray and add contrib if unblocked.
+// Returns true when the path continues; then nx / npr hold the next path state (npr only if
+// nx.meta has kFlagProbe).
+struct PathState { V3 o, d, T; uint32_t pixel, sample, meta; };
+struct ProbeState { V3 o, d, w; };
+
+template <typename ShadowFn>
+CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, const PathState& ps, float t, int slot,
+                                 long long* __restrict__ accum, ShadowFn&& shadow, PathState& nx, ProbeState& npr) {
+    const uint32_t pixel = ps.pixel, sample = ps.sample, bounce = ps.meta & 0xffu;
+    const float lsn_f = (float)p.light_sample_n;
+    const float4 sh = __ldg(sc.tri_shade + slot);
+    const uint32_t mat = __float_as_uint(sh.w);
+    const float4 m0 = __ldg(sc.mats + 4 * mat + 0), m1 = __ldg(sc.mats + 4 * mat + 1);
+    const uint32_t mflags = __float_as_uint(m1.w);
+    if (mflags & 1u) {                                          // emissive vertex, :210,249-255
+        if (bounce == 0) accum_add(accum, pixel, mk3(m1));
+        return false;
+    }
+    const V3 o = ps.o, d = ps.d, T = ps.T;
+    const V3 pos = o + t * d;                                   // DeviceTriangle.cuh:50
+    const V3 nrm = mk3(sh);
+    const V3 f_r = mk3(m0) / kPi;                               // :259
+    const V3 Tf = cmul(T, f_r);
+    // next-event estimation, :262-286
+    for (int li = 0; li < sc.n_lights; ++li) {
+        const int4 L = __ldg(sc.lights + li);
+        const float area = __int_as_float(L.z);
+        for (int sj = 0; sj < p.light_sample_n; ++sj) {
+            uint4 q = draw(pixel, sample, bounce, 2u + (uint32_t)(li * p.light_sample_n + sj), p.seed);
+            const float4* lt = sc.light_tris + 4 * (size_t)(L.x + (int)(q.x % (uint32_t)L.y));   // DeviceLights.cuh:35
+            const float4 a = __ldg(lt), b = __ldg(lt + 1), cc = __ldg(lt + 2), ln = __ldg(lt + 3);
+            float alpha = u01(q.y);                             // DeviceTriangle.cuh:69-72
+            float beta = u01(q.z) * (1.0f - alpha);
+            float gamma = (1.0f - alpha) - beta;
+            V3 lp = (alpha * mk3(a) + beta * mk3(b)) + gamma * mk3(cc);
+            V3 dist = lp - pos;
+            V3 dir = normalize(dist);
+            float d1 = length(dist);
+            float d2 = d1 * d1;
+            float cos1 = fmaxf(0.0f, dot(dir, nrm));
+            float cos2 = fmaxf(0.0f, -dot(dir, mk3(ln)));
+            V3 contrib = cmul(mk3(a.w, b.w, cc.w), Tf) * cos1 * cos2 * area / d2 / lsn_f;     // :274-283
+            bool live = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);
+            float t_to_light = dist.x / dir.x;                  // :272
+            bool needs_trace = live && (t_to_light == t_to_light);
+            if (live && !needs_trace) accum_add(accum, pixel, contrib);   // NaN: never blocked, :19-27
+            shadow(needs_trace, pos, t_to_light, dir, contrib);
+        }
+    }
+    if (bounce == (uint32_t)(p.max_vertices - 1)) return false;  // bounce stack full, :210
+    const uint4 q = draw(pixel, sample, bounce, 0, p.seed);
+    if (u01(q.x) > p.p_rr) return false;                         // :216-221
+    V3 wdir = normalize(normalize(sample_hemisphere(nrm, u01(q.y), u01(q.z))));   // :225-227 + Ray ctor
+    uint32_t nmeta = bounce + 1u;
+    if (mflags & 2u) {                                          // SPECULAR probe, :294-303
+        const float4 m2 = __ldg(sc.mats + 4 * mat + 2);
+        V3 in = normalize(d);
+        V3 out = in - (2.0f * dot(in, nrm)) * nrm;
+        uint4 e = draw(pixel, sample, bounce, 1, p.seed);
+        V3 pd = normalize(normalize(sample_probe_lobe(out, m2.x, m2.y, u01(e.x), u01(e.y))));
+        float pc = fmaxf(0.0f, dot(pd, nrm));
+        npr.o = pos;
+        npr.d = pd;
+        npr.w = cmul(T, mk3(m0)) * m2.z * pc * (kTwoPi / 8.0f);  // :306-312
+        nmeta |= kFlagProbe;
+    }
+    float cosn = fmaxf(0.0f, dot(wdir, nrm));
+    nx.o = pos;
+    nx.d = wdir;
+    nx.T = Tf * cosn * kTwoPi / p.p_rr;                         // :288-293
+    nx.pixel = pixel; nx.sample = sample; nx.meta = nmeta;
+    return true;
+}
+
+// SPECULAR probe of the previous vertex (reference Render.cuh:304-313): the probe hit an emitter.
+CRT_DEV void probe_resolve(const SceneView& sc, int probe_slot, V3 w, uint32_t pixel, long long* __restrict__ accum) {
+    if (probe_slot < 0) return;
+    const uint32_t pm = __float_as_uint(__ldg(sc.tri_shade + probe_slot).w);
+    const float4 m1 = __ldg(sc.mats + 4 * pm + 1);
+    if (__float_as_uint(m1.w) & 1u) accum_add(accum, pixel, cmul(w, mk3(m1)));
+}
+
 __global__ void __launch_bounds__(128) k_shade_compat(SceneView sc, Counters* c, RenderParamsDev p,
                                                       const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                       const float4* __restrict__ q_T, const float* __restrict__ hit_t,
@@ -389,59 +481,20 @@ __global__ void __launch_bounds__(128) k_shade_compat(SceneView sc, Counters* c,
                                                       float4* __restrict__ sh_o, float4* __restrict__ sh_d,
                                                       float4* __restrict__ sh_c, long long* __restrict__ accum) {
     const uint32_t n = c->n_cur;
-    const float lsn_f = (float)p.light_sample_n;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 qo = q_o[i], qd = q_d[i], qT = q_T[i];
-        const uint32_t pixel = __float_as_uint(qo.w), sample = __float_as_uint(qd.w), meta = __float_as_uint(qT.w);
-        const uint32_t bounce = meta & 0xffu;
+        PathState ps;
+        ps.o = mk3(qo); ps.d = mk3(qd); ps.T = mk3(qT);
+        ps.pixel = __float_as_uint(qo.w); ps.sample = __float_as_uint(qd.w); ps.meta = __float_as_uint(qT.w);
         const int slot = hit_slot[i];
-        if (meta & kFlagProbe) {                                   // Render.cuh:294-314
-            if (slot >= 0) {
-                int ps = pr_hit[i];
-                if (ps >= 0) {
-                    uint32_t pm = __float_as_uint(__ldg(sc.tri_shade + ps).w);
-                    float4 m1 = __ldg(sc.mats + 4 * pm + 1);
-                    if (__float_as_uint(m1.w) & 1u) accum_add(accum, pixel, cmul(mk3(pr_w_cur[i]), mk3(m1)));
-                }
-            }
-        }
-        if (slot < 0) continue;                                     // miss, :210
-        const float4 sh = __ldg(sc.tri_shade + slot);
-        const uint32_t mat = __float_as_uint(sh.w);
-        const float4 m0 = __ldg(sc.mats + 4 * mat + 0), m1 = __ldg(sc.mats + 4 * mat + 1);
-        const uint32_t mflags = __float_as_uint(m1.w);
-        if (mflags & 1u) {                                          // emissive vertex, :210,249-255
-            if (bounce == 0) accum_add(accum, pixel, mk3(m1));
-            continue;
-        }
-        const V3 o = mk3(qo), d = mk3(qd), T = mk3(qT);
-        const V3 pos = o + hit_t[i] * d;                            // DeviceTriangle.cuh:50
-        const V3 nrm = mk3(sh);
-        const V3 f_r = mk3(m0) / kPi;                               // :259
-        const V3 Tf = cmul(T, f_r);
-        // next-event estimation, :262-286
-        for (int li = 0; li < sc.n_lights; ++li) {
-            const int4 L = __ldg(sc.lights + li);
-            const float area = __int_as_float(L.z);
-            for (int sj = 0; sj < p.light_sample_n; ++sj) {
-                uint4 q = draw(pixel, sample, bounce, 2u + (uint32_t)(li * p.light_sample_n + sj), p.seed);
-                const float4* lt = sc.light_tris + 4 * (size_t)(L.x + (int)(q.x % (uint32_t)L.y));   // DeviceLights.cuh:35
-                const float4 a = __ldg(lt), b = __ldg(lt + 1), cc = __ldg(lt + 2), ln = __ldg(lt + 3);
-                float alpha = u01(q.y);                             // DeviceTriangle.cuh:69-72
-                float beta = u01(q.z) * (1.0f - alpha);
-                float gamma = (1.0f - alpha) - beta;
-                V3 lp = (alpha * mk3(a) + beta * mk3(b)) + gamma * mk3(cc);
-                V3 dist = lp - pos;
-                V3 dir = normalize(dist);
-                float d1 = length(dist);
-                float d2 = d1 * d1;
-                float cos1 = fmaxf(0.0f, dot(dir, nrm));
-                float cos2 = fmaxf(0.0f, -dot(dir, mk3(ln)));
-                V3 contrib = cmul(mk3(a.w, b.w, cc.w), Tf) * cos1 * cos2 * area / d2 / lsn_f;     // :274-283
-                bool live = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);
-                float t_to_light = dist.x / dir.x;                  // :272
-                bool needs_trace = live && (t_to_light == t_to_light);
-                if (live && !needs_trace) accum_add(accum, pixel, contrib);   // NaN: never blocked, :19-27
+        if (slot < 0) continue;                                     // miss, :210 (a pending probe is dropped, :294)
+        if (ps.meta & kFlagProbe) probe_resolve(sc, pr_hit[i], mk3(pr_w_cur[i]), ps.pixel, accum);
+        PathState nx;
+        ProbeState npr;
+        const uint32_t pixel = ps.pixel;
+        const bool alive = shade_vertex_compat(
+            sc, p, ps, hit_t[i], slot, accum,
+            [&](bool needs_trace, V3 pos, float t_to_light, V3 dir, V3 contrib) {
                 int k = warp_append(&c->n_shadow, needs_trace);
                 if (k >= 0) {
                     V3 rd = normalize(dir);                          // Ray ctor normalises again
@@ -449,38 +502,80 @@ __global__ void __launch_bounds__(128) k_shade_compat(SceneView sc, Counters* c,
                     sh_d[k] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(pixel));
                     sh_c[k] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
                 }
-            }
-        }
-        bool alive = bounce != (uint32_t)(p.max_vertices - 1);      // bounce stack full, :210
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (alive) {
-            q = draw(pixel, sample, bounce, 0, p.seed);
-            alive = !(u01(q.x) > p.p_rr);                            // :216-221
-        }
+            },
+            nx, npr);
         int k = warp_append(&c->n_next, alive);
         if (k < 0) continue;
-        V3 wdir = normalize(normalize(sample_hemisphere(nrm, u01(q.y), u01(q.z))));   // :225-227 + Ray ctor
-        uint32_t nmeta = bounce + 1u;
-        if (mflags & 2u) {                                          // SPECULAR probe, :294-303
-            const float4 m2 = __ldg(sc.mats + 4 * mat + 2);
-            V3 in = normalize(d);
-            V3 out = in - (2.0f * dot(in, nrm)) * nrm;
-            uint4 e = draw(pixel, sample, bounce, 1, p.seed);
-            V3 pd = normalize(normalize(sample_probe_lobe(out, m2.x, m2.y, u01(e.x), u01(e.y))));
-            float pc = fmaxf(0.0f, dot(pd, nrm));
-            V3 pw = cmul(T, mk3(m0)) * m2.z * pc * (kTwoPi / 8.0f);  // :306-312
-            pr_o_next[k] = make_float4(pos.x, pos.y, pos.z, 0.0f);
-            pr_d_next[k] = make_float4(pd.x, pd.y, pd.z, 0.0f);
-            pr_w_next[k] = make_float4(pw.x, pw.y, pw.z, 0.0f);
+        if (nx.meta & kFlagProbe) {
+            pr_o_next[k] = make_float4(npr.o.x, npr.o.y, npr.o.z, 0.0f);
+            pr_d_next[k] = make_float4(npr.d.x, npr.d.y, npr.d.z, 0.0f);
+            pr_w_next[k] = make_float4(npr.w.x, npr.w.y, npr.w.z, 0.0f);
             int pk = warp_append(&c->n_probe_next, true);
             pr_list_next[pk] = (uint32_t)k;
-            nmeta |= kFlagProbe;
         }
-        float cosn = fmaxf(0.0f, dot(wdir, nrm));
-        V3 Tn = Tf * cosn * kTwoPi / p.p_rr;                        // :288-293
-        n_o[k] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(pixel));
-        n_d[k] = make_float4(wdir.x, wdir.y, wdir.z, __uint_as_float(sample));
-        n_T[k] = make_float4(Tn.x, Tn.y, Tn.z, __uint_as_float(nmeta));
+        n_o[k] = make_float4(nx.o.x, nx.o.y, nx.o.z, __uint_as_float(nx.pixel));
+        n_d[k] = make_float4(nx.d.x, nx.d.y, nx.d.z, __uint_as_float(nx.sample));
+        n_T[k] = make_float4(nx.T.x, nx.T.y, nx.T.z, __uint_as_float(nx.meta));
+    }
+}
+
+// Tail of a frame: once no new camera paths remain and few paths are still alive, every remaining
+// path is run to its end by one lane (extend -> shade -> shadow in place), instead of paying five
+// launches per bounce for ever smaller wavefronts. Same per-vertex statement as above, same Philox
+// keys and the same order-independent accumulation, so the image does not depend on where the
+// switch happens.
+__global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderParamsDev p, const float4* __restrict__ q_o,
+                                              const float4* __restrict__ q_d, const float4* __restrict__ q_T,
+                                              const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
+                                              const float4* __restrict__ pr_w, long long* __restrict__ accum) {
+    const uint32_t n = c->tail_n;
+    if (n == 0) return;
+    unsigned long long n_ext = 0, n_sh = 0, n_pr = 0;
+    for (;;) {
+        const uint32_t i = atomicAdd(&c->fetch_tail, 1u);
+        if (i >= n) break;
+        const float4 qo = q_o[i], qd = q_d[i], qT = q_T[i];
+        PathState ps;
+        ps.o = mk3(qo); ps.d = mk3(qd); ps.T = mk3(qT);
+        ps.pixel = __float_as_uint(qo.w); ps.sample = __float_as_uint(qd.w); ps.meta = __float_as_uint(qT.w);
+        ProbeState pr;
+        pr.o = pr.d = pr.w = mk3(0.0f, 0.0f, 0.0f);
+        if (ps.meta & kFlagProbe) { pr.o = mk3(pr_o[i]); pr.d = mk3(pr_d[i]); pr.w = mk3(pr_w[i]); }
+        for (;;) {
+            const HitRec h = traverse<0>(sc, ps.o, ps.d, FLT_MAX);
+            n_ext++;
+            if (h.slot < 0) break;
+            if (ps.meta & kFlagProbe) {
+                const HitRec ph = traverse<0>(sc, pr.o, pr.d, FLT_MAX);
+                n_pr++;
+                probe_resolve(sc, ph.slot, pr.w, ps.pixel, accum);
+            }
+            PathState nx;
+            ProbeState npr;
+            const uint32_t pixel = ps.pixel;
+            const bool alive = shade_vertex_compat(
+                sc, p, ps, h.t, h.slot, accum,
+                [&](bool needs_trace, V3 pos, float t_to_light, V3 dir, V3 contrib) {
+                    if (!needs_trace) return;
+                    const HitRec b = traverse<1>(sc, pos, normalize(dir), t_to_light);
+                    n_sh++;
+                    if (b.slot < 0) accum_add(accum, pixel, contrib);
+                },
+                nx, npr);
+            if (!alive) break;
+            ps = nx;
+            if (nx.meta & kFlagProbe) pr = npr;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_ext += __shfl_down_sync(0xffffffffu, n_ext, o);
+        n_sh += __shfl_down_sync(0xffffffffu, n_sh, o);
+        n_pr += __shfl_down_sync(0xffffffffu, n_pr, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_ext) atomicAdd(&c->stat_extend, n_ext);
+        if (n_sh) atomicAdd(&c->stat_shadow, n_sh);
+        if (n_pr) atomicAdd(&c->stat_probe, n_pr);
     }
 }
 
@@ -541,14 +636,24 @@ int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wav
     CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, 128, 0));
     w->grid_trace = num_sms() * std::max(occ, 1);
     w->grid_shade = num_sms() * 8;
+    CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tail, 128, 0));
+    w->grid_tail = num_sms() * std::max(occ, 1);
     *out = w;
     return CRT_OK;
 }
 
-static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs) {
-    uint32_t pool = env_u32("CRT_POOL", 1u << 20);
+// Pool = paths in flight. Measured on B200 (cornell-box 1920x1080 spp 16, tools/pool_sweep.py): 2^20 paths
+// 916 Msamples/s, 2^22 1227, 2^23 1294, 2^24 1331 - every persistent lane gets more rays per launch, so the
+// drain at the end of each launch and the per-iteration launches weigh less. HBM holds it easily
+// (2^24 paths: 1.6 GB of path queues + 48 B per shadow ray).
+static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, unsigned long long work_items) {
+    uint32_t pool = env_u32("CRT_POOL", 0);
+    if (pool == 0) {
+        pool = 1u << 20;
+        while (pool < (1u << 24) && pool < work_items) pool <<= 1;
+    }
     uint64_t per_vertex = (uint64_t)std::max<uint32_t>(ds.n_lights, 1) * std::max<uint32_t>(rs.light_sample_n, 1);
-    const uint64_t shadow_budget = 1ull << 25;        // 32 Mi shadow rays in flight at most (1.5 GiB)
+    const uint64_t shadow_budget = 1ull << 26;        // 64 Mi shadow rays in flight at most (3 GiB)
     while (pool > 4096 && (uint64_t)pool * per_vertex > shadow_budget) pool >>= 1;
     uint64_t shadow_cap = (uint64_t)pool * per_vertex;
     if (shadow_cap > 0xffffffffull) { set_error("light_sample_n x lights too large"); return CRT_ERR_INVALID; }
@@ -604,12 +709,12 @@ long long* wavefront_accum(Wavefront* w) { return w->accum; }
 int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
                      float tan_half, cudaStream_t st, crt_render_stats* stats) {
     if (rs.estimator != CRT_ESTIMATOR_COMPAT) { set_error("estimator not implemented"); return CRT_ERR_INVALID; }
-    int rc = ensure_pool(w, ds, rs);
-    if (rc != CRT_OK) return rc;
     const size_t npix = (size_t)w->width * w->height;
     const unsigned long long work_all = (unsigned long long)npix * rs.spp;
     const unsigned long long w_begin = rs.range_set ? std::min(rs.work_begin, work_all) : 0;
     const unsigned long long w_end = rs.range_set ? std::min(rs.work_end, work_all) : work_all;
+    int rc = ensure_pool(w, ds, rs, w_end > w_begin ? w_end - w_begin : 0);
+    if (rc != CRT_OK) return rc;
     RenderParamsDev p;
     memcpy(p.eye, eye, sizeof(p.eye));
     memcpy(p.M, M, sizeof(p.M));
@@ -628,8 +733,9 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     CRT_CUDA(cudaMemcpyAsync(w->counters, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     const SceneView sv = ds.view();
     uint64_t launches = 0;
-    float ms_stage[4] = {0, 0, 0, 0};
-    cudaEvent_t se[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float ms_stage[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t se[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const uint32_t tail_max = rs.stage_timing ? 0u : env_u32("CRT_TAIL", kTailDefault);
     if (rs.stage_timing) for (auto& e : se) cudaEventCreate(&e);
     uint32_t it = 0;
     for (;; ++it) {
@@ -638,7 +744,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
             if (w->status_host->done) break;
         }
         const int cur = it & 1, nxt = cur ^ 1;
-        k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, w->status_dev);
+        k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, tail_max, w->status_dev);
         if (rs.stage_timing) cudaEventRecord(se[0], st);
         k_generate<<<w->grid_shade, 256, 0, st>>>(w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur]);
         if (rs.stage_timing) cudaEventRecord(se[1], st);
@@ -655,11 +761,14 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
                                                        w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum);
         if (rs.stage_timing) cudaEventRecord(se[3], st);
         k_shadow<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum);
-        launches += 2;
+        if (rs.stage_timing) cudaEventRecord(se[4], st);
+        k_tail<<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->pr_o[cur], w->pr_d[cur],
+                                             w->pr_w[cur], w->accum);
+        launches += 3;
         if (rs.stage_timing) {
-            cudaEventRecord(se[4], st);
-            cudaEventSynchronize(se[4]);
-            for (int k = 0; k < 4; ++k) { float ms = 0; cudaEventElapsedTime(&ms, se[k], se[k + 1]); ms_stage[k] += ms; }
+            cudaEventRecord(se[5], st);
+            cudaEventSynchronize(se[5]);
+            for (int k = 0; k < 5; ++k) { float ms = 0; cudaEventElapsedTime(&ms, se[k], se[k + 1]); ms_stage[k] += ms; }
         }
         CRT_CUDA(cudaEventRecord(w->ev[it & 3], st));
         CRT_CUDA(cudaGetLastError());
@@ -678,6 +787,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         stats->kernel_launches = launches;
         CRT_CUDA(cudaEventElapsedTime(&stats->ms_total, w->ev_begin, w->ev_end));
         stats->ms_generate = ms_stage[0]; stats->ms_extend = ms_stage[1]; stats->ms_shade = ms_stage[2]; stats->ms_shadow = ms_stage[3];
+        stats->ms_tail = ms_stage[4];
     }
     return CRT_OK;
 }

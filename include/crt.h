@@ -81,6 +81,7 @@ typedef struct crt_render_stats {
     uint64_t kernel_launches;/* kernels launched by the last run_view */
     float ms_total;          /* CUDA-event time of the last run_view, first launch to accumulation final */
     float ms_extend, ms_shade, ms_shadow, ms_generate;   /* per-stage totals when stage timing is on */
+    float ms_tail;           /* k_tail (paths finished in place at the end of the frame) */
 } crt_render_stats;
 
 const char* crt_last_error(void);

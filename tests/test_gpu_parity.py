@@ -220,6 +220,23 @@ def test_pool_smaller_than_frame(gpu, orc, scene_files, monkeypatch):
     assert R.stats()["iterations"] > 12
 
 
+@pytest.mark.parametrize("tail", ["0", "1", "3000", "1000000"])
+def test_tail_switch_point_does_not_change_the_image(gpu, orc, scene_files, monkeypatch, tail):
+    """k_tail (remaining paths finished in place, one lane per path) may take over at any point of the
+    frame: never, for the last path only, mid-way, or straight after the first wavefront."""
+    monkeypatch.setenv("CRT_TAIL", tail)
+    cfg, a, b = _pair(gpu, orc, scene_files, "veach-mis")
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    R, acc, oacc, ost = _render_pair(gpu, orc, a, b, cfg.eye_pos, M, cfg.fovy_rad, 160, 120, 3, 0.8, 2)
+    st = R.stats()
+    assert np.array_equal(acc, oacc)
+    assert (st["extend_rays"], st["shadow_rays"], st["probe_rays"]) == (ost["extend_rays"], ost["shadow_rays"], ost["probe_rays"])
+    if tail == "1000000":
+        assert st["iterations"] == 2                          # one wavefront for the camera rays, then the tail
+    if tail == "0":
+        assert st["iterations"] > 8
+
+
 def test_save_png_and_cli(gpu, scene_files, tmp_path):
     import subprocess
     import struct
