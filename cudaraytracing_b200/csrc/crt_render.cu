@@ -620,6 +620,10 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return (uint32_t)strtoul(v, nullptr, 0);
 }
 
+#ifdef CRT_EXP_SORT
+#include "experiments/exp_sort.cuh"   // ray-ordering experiment, not part of the product build
+#endif
+
 int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wavefront** out) {
     Wavefront* w = new Wavefront();
     w->width = width; w->height = height;
@@ -759,9 +763,15 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
                                                        w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt], w->q_d[nxt],
                                                        w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
                                                        w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum);
+#ifdef CRT_EXP_SORT
+        exp_sort(ds, w->counters, 1, w->sh_o, w->sh_d, w->sh_c, w->shadow_cap, st);
+#endif
         if (rs.stage_timing) cudaEventRecord(se[3], st);
         k_shadow<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum);
         if (rs.stage_timing) cudaEventRecord(se[4], st);
+#ifdef CRT_EXP_SORT
+        exp_sort(ds, w->counters, 0, w->q_o[nxt], w->q_d[nxt], w->q_T[nxt], w->pool, st);
+#endif
         k_tail<<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->pr_o[cur], w->pr_d[cur],
                                              w->pr_w[cur], w->accum);
         launches += 3;
