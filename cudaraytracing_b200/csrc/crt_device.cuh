@@ -215,7 +215,7 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
 // load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result.
 static constexpr int kDone = 0x7ffffffe;
 #ifndef CRT_REFILL_LANES
-#define CRT_REFILL_LANES 8
+#define CRT_REFILL_LANES 12
 #endif
 static constexpr int kRefillLanes = CRT_REFILL_LANES;
 #ifndef CRT_NODE_BREAK
@@ -324,6 +324,186 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
             }
         }
     }
+}
+
+// ---- persistent lanes with a per-warp leaf queue (STRAT 2) --------------------------------------
+// Same BVH, same box and triangle tests, same result (closest: smallest (t, face); any: blocked or
+// not) - but node steps and triangle tests are decoupled, because in the while-while loop above only
+// ~10 of 32 lanes are active in the node loop (ncu, profiles/r01_c3.md): every lane waits for the
+// lane with the longest walk to its next leaf.
+//   * a lane that reaches a leaf does not test it: it appends (lane, first slot) to a queue in shared
+//     memory and goes on with the next entry of its stack, so every live lane does a node step in
+//     every iteration;
+//   * when 32 leaves are queued (or no lane has a node left) the whole warp tests them, one queue
+//     entry per lane, against the owners' rays (mirrored in shared memory); the owners' best hits are
+//     combined with a 64-bit shared-memory atomicMin on (t bits, face id), which is exactly the
+//     "smaller t, ties -> lower face id" rule;
+//   * the price is speculation: a lane keeps walking with the t-limit of the last flush, so it visits
+//     somewhat more nodes than the sequential rule (the oracle's counts are the algorithmic minimum).
+#ifndef CRT_QFLUSH
+#define CRT_QFLUSH 16
+#endif
+#ifndef CRT_QSTEPS
+#define CRT_QSTEPS 6
+#endif
+static constexpr int kQueueFlush = CRT_QFLUSH;       // queued leaves that trigger a flush
+static constexpr int kQueueSteps = CRT_QSTEPS;       // node steps between two looks at the queue
+static constexpr int kQueueCap = kQueueFlush + 32 * kQueueSteps;
+struct WarpLeafQueue {
+    float ox[32], oy[32], oz[32], dx[32], dy[32], dz[32], tmax[32];
+    unsigned long long best[32];
+    int best_slot[32];
+    int q_slot[kQueueCap];
+    unsigned char q_lane[kQueueCap];
+    int count;
+};
+
+template <int MODE, typename Load, typename Done>
+CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    __shared__ WarpLeafQueue s_wq[4];                      // launched with 128 threads per block
+    WarpLeafQueue& q = s_wq[threadIdx.x >> 5];
+    const unsigned kFull = 0xffffffffu;
+    const unsigned long long kNoHit = ((unsigned long long)0x7f7fffffu << 32) | 0x7fffffffull;   // t = FLT_MAX
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int stack[kStackSize];
+    int sp = 0, cur = kDone;                               // kDone: no node in hand and the stack is empty
+    uint32_t idx = 0;
+    V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
+    float tlimit = 0.0f;
+    int pending = 0;
+    bool have = false, exhausted = false;
+    if (lane == 0) q.count = 0;
+    __syncwarp();
+    for (;;) {
+        // A. node steps; a leaf in hand goes to the queue and the lane takes the next entry of its stack
+#pragma unroll
+        for (int r = 0; r < kQueueSteps; ++r) {
+            if (cur < 0) {
+                const int pos = atomicAdd(&q.count, 1);
+                q.q_slot[pos] = ~cur;
+                q.q_lane[pos] = (unsigned char)lane;
+                pending++;
+                cur = sp ? stack[--sp] : kDone;
+            }
+            if (cur >= 0 && cur != kDone) {
+                if (cur == kEmptyChild) {
+                    cur = sp ? stack[--sp] : kDone;
+                } else {
+                    const float4 n0 = __ldg(sc.nodes + 4 * (size_t)cur + 0);
+                    const float4 n1 = __ldg(sc.nodes + 4 * (size_t)cur + 1);
+                    const float4 n2 = __ldg(sc.nodes + 4 * (size_t)cur + 2);
+                    const float4 n3 = __ldg(sc.nodes + 4 * (size_t)cur + 3);
+                    const float lim = tlimit * 1.0001f;
+                    float e0, e1;
+                    const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);
+                    const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1);
+                    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                    if (h0 && h1) {
+                        int nearc = c0, farc = c1;
+                        if (e1 < e0) { nearc = c1; farc = c0; }
+                        stack[sp++] = farc;
+                        cur = nearc;
+                    } else if (h0) cur = c0;
+                    else if (h1) cur = c1;
+                    else cur = sp ? stack[--sp] : kDone;
+                }
+            }
+        }
+        // B. flush the leaf queue when it is full enough, or when no lane has a node or leaf in hand
+        const unsigned walking = __ballot_sync(kFull, cur != kDone);
+        __syncwarp();
+        const int q_count = q.count;
+        if (q_count >= kQueueFlush || (walking == 0 && q_count > 0)) {
+            for (int base = 0; base < q_count; base += 32) {
+                const int k = base + lane;
+                unsigned long long mykey = kNoHit;
+                int myslot = -1, owner = 0;
+                if (k < q_count) {
+                    owner = q.q_lane[k];
+                    int slot = q.q_slot[k];
+                    const V3 ro = mk3(q.ox[owner], q.oy[owner], q.oz[owner]), rd = mk3(q.dx[owner], q.dy[owner], q.dz[owner]);
+                    const float rtmax = q.tmax[owner];
+                    for (;; ++slot) {
+                        const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
+                        const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
+                        const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
+                        const uint32_t fw = __float_as_uint(a.w);
+                        float t;
+                        if (tri_test(mk3(a), mk3(b), mk3(c), ro, rd, &t) && t > kEps && (MODE == 0 || rtmax - t > kEps)) {
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (fw & ~kLastBit);
+                            if (key < mykey) { mykey = key; myslot = slot; }
+                        }
+                        if (fw & kLastBit) break;
+                    }
+                    if (myslot >= 0) atomicMin(&q.best[owner], mykey);
+                }
+                __syncwarp();
+                if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
+                __syncwarp();
+            }
+            if (lane == 0) q.count = 0;
+            pending = 0;
+            if (have) {
+                const unsigned long long b = q.best[lane];
+                if (MODE == 0) tlimit = __uint_as_float((uint32_t)(b >> 32));
+                else if (b != kNoHit) { cur = kDone; sp = 0; }      // blocked: nothing left to learn
+            }
+            __syncwarp();
+        }
+        // C. finished rays
+        if (have && cur == kDone && pending == 0) {
+            const unsigned long long b = q.best[lane];
+            HitRec h;
+            h.t = __uint_as_float((uint32_t)(b >> 32));
+            h.face = b == kNoHit ? -1 : (int)(uint32_t)b;
+            h.slot = b == kNoHit ? -1 : q.best_slot[lane];
+            done(idx, h);
+            have = false;
+        }
+        // D. refill idle lanes from the ray queue
+        const unsigned idle = __ballot_sync(kFull, !have);
+        if (idle) {
+            const int n_idle = __popc(idle);
+            if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
+                base = __shfl_sync(kFull, base, leader);
+                if (!have) {
+                    const uint32_t i = base + __popc(idle & lt_mask);
+                    if (i < n) {
+                        idx = i;
+                        V3 d;
+                        float tmax;
+                        const bool live = load(i, o, d, tmax);
+                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        tlimit = MODE == 0 ? FLT_MAX : tmax;
+                        q.ox[lane] = o.x; q.oy[lane] = o.y; q.oz[lane] = o.z;
+                        q.dx[lane] = d.x; q.dy[lane] = d.y; q.dz[lane] = d.z;
+                        q.tmax[lane] = tmax;
+                        q.best[lane] = kNoHit;
+                        q.best_slot[lane] = -1;
+                        sp = 0;
+                        pending = 0;
+                        cur = (live && sc.n_nodes) ? 0 : kDone;
+                        have = true;
+                    }
+                }
+                if (base + (uint32_t)n_idle >= n) exhausted = true;
+                __syncwarp();
+            }
+            if (idle == kFull && !__any_sync(kFull, have)) {
+                if (exhausted) break;
+            }
+        }
+    }
+}
+
+template <int MODE, int STRAT, typename Load, typename Done>
+CRT_DEV void trace_rays_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    if (STRAT == 2) trace_persistent_queue<MODE>(sc, n, fetch, load, done);
+    else trace_persistent<MODE, STRAT>(sc, n, fetch, load, done);
 }
 
 // ---- fixed-point accumulation (DESIGN.md "Accumulation"): radiance * 2^32 summed in int64, which

@@ -10,8 +10,14 @@
 // The estimator arithmetic mirrors oracle/orc_render.cpp operation by operation (-fmad=false).
 #include "crt_gpu.h"
 
+// Traversal scheduling: 2 = persistent lanes + per-warp leaf queue (default), 0 = while-while, 1 = if-if
+// (crt_device.cuh; measured alternatives in DESIGN.md "Traversal scheduling").
 #ifndef CRT_STRAT
-#define CRT_STRAT 0
+#define CRT_STRAT 2
+#endif
+
+#ifndef CRT_MINB
+#define CRT_MINB 1     // __launch_bounds__ min blocks/SM of the traversal kernels (register cap experiment)
 #endif
 
 #include <algorithm>
@@ -112,10 +118,10 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene
 // ray batches
 // =============================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(128) k_trace_batch(SceneView sc, const float4* __restrict__ rays, uint32_t n,
+__global__ void __launch_bounds__(128, CRT_MINB) k_trace_batch(SceneView sc, const float4* __restrict__ rays, uint32_t n,
                                                      float* __restrict__ t_out, int* __restrict__ face_out,
                                                      uint32_t* __restrict__ fetch) {
-    trace_persistent<MODE, CRT_STRAT>(
+    trace_rays_persistent<MODE, CRT_STRAT>(
         sc, n, fetch,
         [&](uint32_t i, V3& o, V3& d, float& tmax) {
             const float4 ro = __ldg(rays + 2 * (size_t)i), rd = __ldg(rays + 2 * (size_t)i + 1);
@@ -310,21 +316,21 @@ __global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c
     }
 }
 
-__global__ void __launch_bounds__(128) k_extend(SceneView sc, Counters* c, const float4* __restrict__ q_o,
+__global__ void __launch_bounds__(128, CRT_MINB) k_extend(SceneView sc, Counters* c, const float4* __restrict__ q_o,
                                                 const float4* __restrict__ q_d, float* __restrict__ hit_t,
                                                 int* __restrict__ hit_slot) {
-    trace_persistent<0, CRT_STRAT>(
+    trace_rays_persistent<0, CRT_STRAT>(
         sc, c->n_cur, &c->fetch_extend,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
         [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });
 }
 
 // SPECULAR probe rays (reference Render.cuh:303): traced only when the continuation ray hit.
-__global__ void __launch_bounds__(128) k_probe(SceneView sc, Counters* c, const uint32_t* __restrict__ list,
+__global__ void __launch_bounds__(128, CRT_MINB) k_probe(SceneView sc, Counters* c, const uint32_t* __restrict__ list,
                                                const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
                                                const int* __restrict__ hit_slot, int* __restrict__ pr_hit) {
     unsigned long long traced = 0;
-    trace_persistent<0, CRT_STRAT>(
+    trace_rays_persistent<0, CRT_STRAT>(
         sc, c->n_probe_cur, &c->fetch_probe,
         [&](uint32_t k, V3& o, V3& d, float& tmax) {
             const uint32_t i = list[k];
@@ -580,10 +586,10 @@ __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderP
 }
 
 // Shadow rays: the decision of blocked() (reference Render.cuh:19-27) with an any-hit traversal.
-__global__ void __launch_bounds__(128) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
+__global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
                                                 const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
                                                 long long* __restrict__ accum) {
-    trace_persistent<1, CRT_STRAT>(
+    trace_rays_persistent<1, CRT_STRAT>(
         sc, c->n_shadow, &c->fetch_shadow,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { const float4 a = sh_o[i]; o = mk3(a); tmax = a.w; d = mk3(sh_d[i]); return true; },
         [&](uint32_t i, const HitRec& h) {

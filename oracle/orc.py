@@ -55,6 +55,7 @@ def lib():
     L.orc_newbvh_build.argtypes = [vp, C.c_uint, C.c_int]
     L.orc_newbvh_get.argtypes = [vp, vp, vp, vp, vp]
     L.orc_trace.argtypes = [vp, C.c_int, C.c_int, f32p, C.c_int64, f32p, i32p, vp, C.c_int]
+    L.orc_tri_test.argtypes = [vp, f32p, i32p, C.c_int64, f32p, vp]
     L.orc_primary_rays.argtypes = [f32p, f32p, C.c_float, C.c_int, C.c_int, f32p]
     L.orc_inverse_view_matrix.argtypes = [f32p, f32p, f32p, f32p]
     L.orc_render.argtypes = [vp, f32p, f32p, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_float,
@@ -180,6 +181,31 @@ class Scene:
         if want_stats:
             return t, face, dict(zip(("inner", "boxes", "tris", "max_stack", "rays"), (int(x) for x in stats)))
         return t, face
+
+    def tri_test(self, rays, faces):
+        """Canonical triangle test of faces[k] against rays[k]: (t, inside)."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        faces = np.ascontiguousarray(faces, np.int32)
+        t = np.zeros(len(faces), np.float32)
+        inside = np.zeros(len(faces), np.uint8)
+        self.L.orc_tri_test(self.h, rays, faces, len(faces), t, _ptr(inside))
+        return t, inside.astype(bool)
+
+    def check_any_hits(self, rays, t, face):
+        """Any-hit results are 'a blocker or none' (which blocker is found first depends on warp scheduling):
+        blocked status must equal this oracle's, a reported blocker must pass the canonical test with
+        t > 1e-5 and tmax - t > 1e-5 (reference Render.cuh:19-27), and its t must be bit-exact."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        ot, of = self.trace(rays, which=0, mode=1)
+        assert np.array_equal(face >= 0, of >= 0), "blocked status differs for %d rays" % int(((face >= 0) != (of >= 0)).sum())
+        miss = face < 0
+        assert np.all(t[miss] == np.float32(3.4028234663852886e38))
+        tt, inside = self.tri_test(rays, face)
+        b = ~miss
+        eps = np.float32(0.00001)
+        assert np.all(inside[b]) and np.array_equal(tt[b].view(np.uint32), t[b].view(np.uint32))
+        assert np.all(t[b] > eps) and np.all(rays[b, 3] - t[b] > eps)
+        return True
 
     def render(self, eye, M, fovy_rad, width, height, s_begin, s_end, p_rr, light_sample_n, seed=0, estimator=0,
                threads=None, accum=None):

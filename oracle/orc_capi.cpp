@@ -152,6 +152,22 @@ int orc_trace(orc_scene* h, int which, int mode, const float* rays, int64_t n, f
     return 0;
 }
 
+// Canonical triangle test of face faces[k] against ray k (checks a reported any-hit blocker):
+// t_out = t of the Moeller-Trumbore statement, inside_out = 1 when the strict-inside rule accepts it.
+int orc_tri_test(orc_scene* h, const float* rays, const int* faces, int64_t n, float* t_out, unsigned char* inside_out) {
+    for (int64_t k = 0; k < n; ++k) {
+        const float* r = rays + 8 * k;
+        t_out[k] = FLT_MAX;
+        inside_out[k] = 0;
+        if (faces[k] < 0 || faces[k] >= (int)h->s.tris.size()) continue;
+        float t;
+        bool in = tri_test(h->s.tris[faces[k]], V3{r[0], r[1], r[2]}, V3{r[4], r[5], r[6]}, &t);
+        t_out[k] = t;
+        inside_out[k] = in ? 1 : 0;
+    }
+    return 0;
+}
+
 // Primary rays for an image: jitter == NULL -> pixel centres (u = 0.5); else jitter[2*pixel..]
 void orc_primary_rays(const float eye[3], const float M[9], float fovy_rad, int width, int height, float* rays) {
     Camera cam;

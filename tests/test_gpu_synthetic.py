@@ -55,6 +55,9 @@ def test_c5_random_rays_match_numpy_statement_and_oracle(gpu, orc):
         d_f = torch.empty(n, dtype=torch.int32, device="cuda")
         mode = gpu.RAY_ANY if any_hit else gpu.RAY_CLOSEST
         a.trace_rays_device(d_rays.data_ptr(), n, mode, d_t.data_ptr(), d_f.data_ptr())
+        if any_hit:
+            assert b.check_any_hits(rays, d_t.cpu().numpy(), d_f.cpu().numpy())
+            continue
         ot, of = b.trace(rays, which=0, mode=mode)
         assert np.array_equal(d_f.cpu().numpy(), of) and np.array_equal(d_t.cpu().numpy().view(np.uint32), ot.view(np.uint32))
     assert abs(np.linalg.norm(rays[:, 4:7], axis=1) - 1).max() < 1e-6
