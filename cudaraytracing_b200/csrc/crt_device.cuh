@@ -102,6 +102,37 @@ CRT_DEV void sincos_rad(float x, float* s, float* c) {
     quadrant((int)n, ss, cc, s, c);
 }
 
+// ---- deterministic log2 / exp2 / pow and luminance (mis estimator; statement: oracle/orc_math.h)
+CRT_DEV float det_log2(float x) {
+    const uint32_t b = __float_as_uint(x);
+    int e = (int)(b >> 23) - 127;
+    float m = __uint_as_float((b & 0x7fffffu) | 0x3f800000u);
+    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    const float f = m - 1.0f;
+    const float sq = f / (2.0f + f);
+    const float s2 = sq * sq;
+    float p = fmaf(s2, 0.11111111f, 0.14285715f);
+    p = fmaf(p, s2, 0.2f);
+    p = fmaf(p, s2, 0.33333334f);
+    const float r = fmaf(sq * s2, p, sq);
+    return fmaf(r, 2.8853900f, (float)e);
+}
+CRT_DEV float det_exp2(float y) {
+    if (!(y >= -126.0f)) return 0.0f;
+    if (y > 127.0f) y = 127.0f;
+    const float n = rintf(y);
+    const float r = y - n;
+    float p = fmaf(r, 1.5403530e-4f, 1.3333558e-3f);
+    p = fmaf(p, r, 9.6181291e-3f);
+    p = fmaf(p, r, 5.5504109e-2f);
+    p = fmaf(p, r, 2.4022651e-1f);
+    p = fmaf(p, r, 6.9314718e-1f);
+    p = fmaf(p, r, 1.0f);
+    return p * __uint_as_float((uint32_t)((int)n + 127) << 23);
+}
+CRT_DEV float det_pow(float x, float y) { return det_exp2(y * det_log2(x)); }
+CRT_DEV float lumf(V3 c) { return fmaf(0.0722f, c.z, fmaf(0.7152f, c.y, 0.2126f * c.x)); }
+
 // ---- scene view passed to kernels by value
 struct SceneView {
     const float4* __restrict__ nodes;       // 4 x 16 B per node (crt_bvh_node)
@@ -110,8 +141,10 @@ struct SceneView {
     const float4* __restrict__ mats;        // 4 x 16 B per material, see MatRec
     const float4* __restrict__ light_tris;  // 4 x 16 B per light triangle: (v1,ke.r) (v2,ke.g) (v3,ke.b) (n, 0)
     const int4* __restrict__ lights;        // per light object: (first light tri, count, area bits, 0)
+    const float* __restrict__ light_cdf;    // mis estimator: CDF over light_tris, P ~ area * luminance(Ke)
     int n_nodes;
     int n_lights;
+    int n_light_tris;
 };
 
 // Canonical triangle test: Moeller-Trumbore of reference DeviceTriangle.cuh:39-65 (strict inside).

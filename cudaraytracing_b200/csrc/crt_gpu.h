@@ -31,12 +31,14 @@ struct DeviceScene {
     float4* mats = nullptr;         // n_mats * 4
     float4* light_tris = nullptr;   // n_light_tris * 4
     int4* lights = nullptr;         // n_lights
+    float* light_cdf = nullptr;     // n_light_tris (mis estimator)
     float bounds[6] = {0, 0, 0, 0, 0, 0};
     bool has_specular = false;
     SceneView view() const {
         SceneView v;
         v.nodes = nodes; v.tri_geom = tri_geom; v.tri_shade = tri_shade; v.mats = mats;
         v.light_tris = light_tris; v.lights = lights; v.n_nodes = (int)n_nodes; v.n_lights = (int)n_lights;
+        v.light_cdf = light_cdf; v.n_light_tris = (int)n_light_tris;
         return v;
     }
     void release();

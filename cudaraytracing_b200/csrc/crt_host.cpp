@@ -133,6 +133,20 @@ void finish_objects(HostScene& s) {
         }
         s.lights[light_of_obj[o]].faces.push_back((int32_t)t);
     }
+    // mis estimator tables: weights in double, summed in table order, rounded once
+    auto lum = [](const float* c) { return fmaf(0.0722f, c[2], fmaf(0.7152f, c[1], 0.2126f * c[0])); };
+    double W = 0.0;
+    for (const HostLight& L : s.lights)
+        for (int32_t f : L.faces) W += (double)s.area[f] * (double)lum(s.mats[s.mat[f]].ke);
+    s.light_cdf.clear();
+    double acc = 0.0;
+    for (const HostLight& L : s.lights)
+        for (int32_t f : L.faces) {
+            acc += (double)s.area[f] * (double)lum(s.mats[s.mat[f]].ke);
+            s.light_cdf.push_back(W > 0.0 ? (float)(acc / W) : 1.0f);
+        }
+    if (!s.light_cdf.empty()) s.light_cdf.back() = 1.0f;
+    for (HostMaterial& m : s.mats) m.pdf_area = (m.has_emit && W > 0.0) ? (float)((double)lum(m.ke) / W) : 0.0f;
 }
 
 int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {

@@ -17,6 +17,7 @@ struct HostMaterial {
     int has_emit = 0;          // Material.h:36-39
     int mode = 0;              // 0 DIFFUSE, 1 SPECULAR (Loader.h:107)
     float probe_dtheta = 0, probe_dphi = 0, probe_shin = 1;   // Render.cuh:296-300,306-307
+    float pdf_area = 0;        // mis estimator: light-sampling density per unit area on triangles of this material
     std::string name;
 };
 
@@ -34,6 +35,8 @@ struct HostScene {
     std::vector<int32_t> mat, obj;
     std::vector<HostMaterial> mats;
     std::vector<HostLight> lights;
+    // mis estimator: CDF over all light triangles (light order, then face order), P ~ area * luminance(Ke)
+    std::vector<float> light_cdf;
     int n_objects = 0;
     size_t n_tris() const { return mat.size(); }
 };

@@ -34,7 +34,8 @@ namespace crt {
 // =============================================================================================
 void DeviceScene::release() {
     cudaFree(nodes); cudaFree(tri_geom); cudaFree(tri_shade); cudaFree(order); cudaFree(last);
-    cudaFree(mats); cudaFree(light_tris); cudaFree(lights);
+    cudaFree(mats); cudaFree(light_tris); cudaFree(lights); cudaFree(light_cdf);
+    light_cdf = nullptr;
     nodes = tri_geom = tri_shade = mats = light_tris = nullptr;
     order = nullptr; last = nullptr; lights = nullptr;
     n_tris = n_nodes = n_mats = n_lights = n_light_tris = 0;
@@ -48,7 +49,7 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene
     ds.device = device;
     const size_t n = hs.n_tris();
     if (n > 0x7fffffffu / 4) { set_error("scene too large (more than 2^29 triangles)"); return CRT_ERR_INVALID; }
-    // materials: (kd, ns) (ke, flags) (probe_dtheta, probe_dphi, probe_shin, 0) (ks, 0)
+    // materials: (kd, ns) (ke, flags) (probe_dtheta, probe_dphi, probe_shin, 0) (ks, mis light-sampling density per area)
     std::vector<float4> mats(hs.mats.size() * 4);
     ds.has_specular = false;
     for (size_t m = 0; m < hs.mats.size(); ++m) {
@@ -58,7 +59,7 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene
         mats[4 * m + 0] = make_float4(hm.kd[0], hm.kd[1], hm.kd[2], hm.ns);
         mats[4 * m + 1] = make_float4(hm.ke[0], hm.ke[1], hm.ke[2], bits_f(flags));
         mats[4 * m + 2] = make_float4(hm.probe_dtheta, hm.probe_dphi, hm.probe_shin, 0.0f);
-        mats[4 * m + 3] = make_float4(hm.ks[0], hm.ks[1], hm.ks[2], 0.0f);
+        mats[4 * m + 3] = make_float4(hm.ks[0], hm.ks[1], hm.ks[2], hm.pdf_area);
     }
     // lights (DeviceLights.cuh:63-87): object table + flat triangle table
     std::vector<int4> lights;
@@ -78,7 +79,7 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene
             ltris.push_back(make_float4(v[0], v[1], v[2], hm.ke[0]));
             ltris.push_back(make_float4(v[3], v[4], v[5], hm.ke[1]));
             ltris.push_back(make_float4(v[6], v[7], v[8], hm.ke[2]));
-            ltris.push_back(make_float4(nn[0], nn[1], nn[2], 0.0f));
+            ltris.push_back(make_float4(nn[0], nn[1], nn[2], hm.pdf_area));
         }
     }
     ds.n_mats = (uint32_t)hs.mats.size();
@@ -93,6 +94,9 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene
         CRT_CUDA(cudaMemcpy(ds.lights, lights.data(), sizeof(int4) * lights.size(), cudaMemcpyHostToDevice));
         CRT_CUDA(cudaMalloc(&ds.light_tris, sizeof(float4) * ltris.size()));
         CRT_CUDA(cudaMemcpy(ds.light_tris, ltris.data(), sizeof(float4) * ltris.size(), cudaMemcpyHostToDevice));
+        if (hs.light_cdf.size() != ltris.size() / 4) { set_error("light table out of date (finish_objects not called)"); return CRT_ERR_STATE; }
+        CRT_CUDA(cudaMalloc(&ds.light_cdf, sizeof(float) * hs.light_cdf.size()));
+        CRT_CUDA(cudaMemcpy(ds.light_cdf, hs.light_cdf.data(), sizeof(float) * hs.light_cdf.size(), cudaMemcpyHostToDevice));
     }
     // geometry in face order for the builder
     float* d_verts = nullptr;
@@ -243,6 +247,7 @@ struct Wavefront {
     uint32_t shadow_cap = 0;
     bool has_probe = false;
     float4 *q_o[2] = {nullptr, nullptr}, *q_d[2] = {nullptr, nullptr}, *q_T[2] = {nullptr, nullptr};
+    float* q_pdf[2] = {nullptr, nullptr};      // mis: density of the BSDF sample that produced the ray
     float* hit_t = nullptr;
     int* hit_slot = nullptr;
     float4 *pr_o[2] = {nullptr, nullptr}, *pr_d[2] = {nullptr, nullptr}, *pr_w[2] = {nullptr, nullptr};
@@ -294,7 +299,7 @@ __global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostSta
 // Primary rays: reference Render.cuh:338-347 + Ray.cuh:12-15. Work item w -> (sample, pixel) with
 // consecutive items on consecutive pixels of one sample index (coherent warps, distinct pixels).
 __global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c, RenderParamsDev p, float4* __restrict__ q_o,
-                                                  float4* __restrict__ q_d, float4* __restrict__ q_T) {
+                                                  float4* __restrict__ q_d, float4* __restrict__ q_T, float* __restrict__ q_pdf) {
     const uint32_t count = c->gen_count, base = c->gen_base;
     const unsigned long long w0 = c->gen_work0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
@@ -313,6 +318,7 @@ __global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c
         q_o[base + k] = make_float4(p.eye[0], p.eye[1], p.eye[2], __uint_as_float(pixel));
         q_d[base + k] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
         q_T[base + k] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+        if (q_pdf) q_pdf[base + k] = 0.0f;
     }
 }
 
@@ -396,7 +402,7 @@ CRT_DEV V3 sample_probe_lobe(V3 out, float dtheta, float dphi, float u1, float u
 //   reached this vertex; when needs_trace it must trace the any-hit ray and add contrib if unblocked.
 // Returns true when the path continues; then nx / npr hold the next path state (npr only if
 // nx.meta has kFlagProbe).
-struct PathState { V3 o, d, T; uint32_t pixel, sample, meta; };
+struct PathState { V3 o, d, T; uint32_t pixel, sample, meta; float pdf; };   // pdf: mis only (density of the last BSDF sample)
 struct ProbeState { V3 o, d, w; };
 
 template <typename ShadowFn>
@@ -440,7 +446,7 @@ CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, 
             float t_to_light = dist.x / dir.x;                  // :272
             bool needs_trace = live && (t_to_light == t_to_light);
             if (live && !needs_trace) accum_add(accum, pixel, contrib);   // NaN: never blocked, :19-27
-            shadow(needs_trace, pos, t_to_light, dir, contrib);
+            shadow(needs_trace, pos, t_to_light, normalize(dir), contrib);     // Ray ctor normalises again
         }
     }
     if (bounce == (uint32_t)(p.max_vertices - 1)) return false;  // bounce stack full, :210
@@ -468,6 +474,129 @@ CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, 
     return true;
 }
 
+// mis estimator, one path vertex (statement: oracle/orc_render.cpp path_mis; DESIGN.md "mis"): two-sided
+// modified-Phong surfaces, one-sided emitters, light triangles picked ~ area * luminance(Ke), power
+// heuristic between light_sample_n light samples and the BSDF sample, Russian roulette at P_RR.
+CRT_DEV int pick_light(const float* __restrict__ cdf, int n, float u) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(cdf + mid) >= u) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+CRT_DEV void phong_eval(V3 kd, V3 ks, float ns, float pd, bool has_spec, float cos_s, float ca, V3* f, float* pdf) {
+    const V3 fd = kd / kPi;
+    const float pdf_d = cos_s / kPi;
+    if (has_spec) {
+        const float pw = det_pow(ca, ns);
+        *f = fd + ks * ((ns + 2.0f) / kTwoPi * pw);
+        const float pdf_s = (ns + 1.0f) / kTwoPi * pw;
+        *pdf = fmaf(pd, pdf_d, (1.0f - pd) * pdf_s);
+    } else {
+        *f = fd;
+        *pdf = pdf_d;
+    }
+}
+
+template <typename ShadowFn>
+CRT_DEV bool shade_vertex_mis(const SceneView& sc, const RenderParamsDev& p, const PathState& ps, float t, int slot,
+                              long long* __restrict__ accum, ShadowFn&& shadow, PathState& nx) {
+    const uint32_t pixel = ps.pixel, sample = ps.sample, bounce = ps.meta & 0xffu;
+    const float lsn_f = (float)p.light_sample_n;
+    const float4 sh = __ldg(sc.tri_shade + slot);
+    const uint32_t mat = __float_as_uint(sh.w);
+    const float4 m0 = __ldg(sc.mats + 4 * mat + 0), m1 = __ldg(sc.mats + 4 * mat + 1), m3 = __ldg(sc.mats + 4 * mat + 3);
+    const V3 n = mk3(sh), d = ps.d, T = ps.T;
+    const float dn = dot(n, d);
+    if (__float_as_uint(m1.w) & 1u) {                            // emitter: seen from its front side only
+        if (dn < 0.0f) {
+            if (bounce == 0) accum_add(accum, pixel, mk3(m1));
+            else {
+                const float pl = m3.w * (t * t) / (-dn);
+                const float pls = lsn_f * pl;
+                const float w = (ps.pdf * ps.pdf) / fmaf(ps.pdf, ps.pdf, pls * pls);
+                accum_add(accum, pixel, cmul(T, mk3(m1)) * w);
+            }
+        }
+        return false;
+    }
+    const V3 ns = dn > 0.0f ? mk3(-n.x, -n.y, -n.z) : n;
+    const V3 wo = mk3(-d.x, -d.y, -d.z);
+    const V3 pos = ps.o + t * d;
+    const float off = 1.0e-4f * (1.0f + fmaxf(fmaxf(fabsf(pos.x), fabsf(pos.y)), fabsf(pos.z)));
+    const V3 org = pos + off * ns;
+    const float cos_o = dot(ns, wo);
+    const V3 refl = normalize((2.0f * cos_o) * ns - wo);
+    const V3 kd = mk3(m0), ks = mk3(m3);
+    const float mns = m0.w;
+    const float lkd = lumf(kd), lks = lumf(ks);
+    const float lsum = lkd + lks;
+    if (!(lsum > 0.0f)) return false;
+    const float pd = lkd / lsum;
+    const bool has_spec = lks > 0.0f;
+    for (int sj = 0; sj < p.light_sample_n && sc.n_light_tris > 0; ++sj) {
+        const uint4 q = draw(pixel, sample, bounce, 2u + (uint32_t)sj, p.seed);
+        const int k = pick_light(sc.light_cdf, sc.n_light_tris, u01(q.x));
+        const float4* lt = sc.light_tris + 4 * (size_t)k;
+        const float4 a = __ldg(lt), b = __ldg(lt + 1), cc = __ldg(lt + 2), ln = __ldg(lt + 3);
+        const float su = sqrtf(u01(q.y));
+        const float b0 = 1.0f - su, b1 = u01(q.z) * su;
+        const float b2 = (1.0f - b0) - b1;
+        const V3 lp = (b0 * mk3(a) + b1 * mk3(b)) + b2 * mk3(cc);
+        const V3 dist = lp - org;
+        const float d2 = dot(dist, dist);
+        const float d1 = sqrtf(d2);
+        const V3 wi = dist / d1;
+        const float cos_s = dot(ns, wi);
+        const float cos_l = -dot(mk3(ln), wi);
+        bool needs_trace = cos_s > 0.0f && cos_l > 0.0f;
+        V3 contrib = mk3(0.0f, 0.0f, 0.0f);
+        if (needs_trace) {
+            const float ca = fmaxf(0.0f, dot(refl, wi));
+            V3 f;
+            float pb;
+            phong_eval(kd, ks, mns, pd, has_spec, cos_s, ca, &f, &pb);
+            const float pl = ln.w * d2 / cos_l;
+            const float pls = lsn_f * pl;
+            const float w = (pls * pls) / fmaf(pls, pls, pb * pb);
+            contrib = cmul(cmul(T, f), mk3(a.w, b.w, cc.w)) * (cos_s * w / pls);
+            needs_trace = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);
+        }
+        shadow(needs_trace, org, d1 * 0.999f, wi, contrib);
+    }
+    if (bounce == (uint32_t)(p.max_vertices - 1)) return false;
+    const uint4 q = draw(pixel, sample, bounce, 0, p.seed);
+    if (u01(q.x) > p.p_rr) return false;
+    const float u1 = u01(q.z), u2 = u01(q.w);
+    float sn, cs;
+    sincos_2pi(u2, &sn, &cs);
+    V3 wi;
+    if (u01(q.y) <= pd) {
+        const float rr = sqrtf(u1);
+        const float z = sqrtf(1.0f - u1);
+        wi = to_world(mk3(rr * cs, rr * sn, z), ns);
+    } else {
+        const float ca0 = det_pow(u1, 1.0f / (mns + 1.0f));
+        const float sa0 = sqrtf(fmaxf(0.0f, 1.0f - ca0 * ca0));
+        wi = to_world(mk3(sa0 * cs, sa0 * sn, ca0), refl);
+    }
+    wi = normalize(wi);
+    const float cos_s = dot(ns, wi);
+    if (!(cos_s > 0.0f)) return false;
+    const float ca = fmaxf(0.0f, dot(refl, wi));
+    V3 f;
+    float pb;
+    phong_eval(kd, ks, mns, pd, has_spec, cos_s, ca, &f, &pb);
+    if (!(pb > 0.0f)) return false;
+    nx.o = org;
+    nx.d = wi;
+    nx.T = cmul(T, f) * (cos_s / pb / p.p_rr);
+    nx.pixel = pixel; nx.sample = sample; nx.meta = bounce + 1u;
+    nx.pdf = pb;
+    return true;
+}
+
 // SPECULAR probe of the previous vertex (reference Render.cuh:304-313): the probe hit an emitter.
 CRT_DEV void probe_resolve(const SceneView& sc, int probe_slot, V3 w, uint32_t pixel, long long* __restrict__ accum) {
     if (probe_slot < 0) return;
@@ -476,9 +605,12 @@ CRT_DEV void probe_resolve(const SceneView& sc, int probe_slot, V3 w, uint32_t p
     if (__float_as_uint(m1.w) & 1u) accum_add(accum, pixel, cmul(w, mk3(m1)));
 }
 
-__global__ void __launch_bounds__(128) k_shade_compat(SceneView sc, Counters* c, RenderParamsDev p,
+// EST: CRT_ESTIMATOR_COMPAT (0) or CRT_ESTIMATOR_MIS (1)
+template <int EST>
+__global__ void __launch_bounds__(128) k_shade(SceneView sc, Counters* c, RenderParamsDev p,
                                                       const float4* __restrict__ q_o, const float4* __restrict__ q_d,
-                                                      const float4* __restrict__ q_T, const float* __restrict__ hit_t,
+                                                      const float4* __restrict__ q_T, const float* __restrict__ q_pdf,
+                                                      float* __restrict__ n_pdf, const float* __restrict__ hit_t,
                                                       const int* __restrict__ hit_slot, const float4* __restrict__ pr_w_cur,
                                                       const int* __restrict__ pr_hit, float4* __restrict__ n_o,
                                                       float4* __restrict__ n_d, float4* __restrict__ n_T,
@@ -492,27 +624,28 @@ __global__ void __launch_bounds__(128) k_shade_compat(SceneView sc, Counters* c,
         PathState ps;
         ps.o = mk3(qo); ps.d = mk3(qd); ps.T = mk3(qT);
         ps.pixel = __float_as_uint(qo.w); ps.sample = __float_as_uint(qd.w); ps.meta = __float_as_uint(qT.w);
+        ps.pdf = EST == CRT_ESTIMATOR_MIS ? q_pdf[i] : 0.0f;
         const int slot = hit_slot[i];
         if (slot < 0) continue;                                     // miss, :210 (a pending probe is dropped, :294)
-        if (ps.meta & kFlagProbe) probe_resolve(sc, pr_hit[i], mk3(pr_w_cur[i]), ps.pixel, accum);
+        if (EST == CRT_ESTIMATOR_COMPAT && (ps.meta & kFlagProbe)) probe_resolve(sc, pr_hit[i], mk3(pr_w_cur[i]), ps.pixel, accum);
         PathState nx;
         ProbeState npr;
         const uint32_t pixel = ps.pixel;
-        const bool alive = shade_vertex_compat(
-            sc, p, ps, hit_t[i], slot, accum,
-            [&](bool needs_trace, V3 pos, float t_to_light, V3 dir, V3 contrib) {
-                int k = warp_append(&c->n_shadow, needs_trace);
-                if (k >= 0) {
-                    V3 rd = normalize(dir);                          // Ray ctor normalises again
-                    sh_o[k] = make_float4(pos.x, pos.y, pos.z, t_to_light);
-                    sh_d[k] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(pixel));
-                    sh_c[k] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
-                }
-            },
-            nx, npr);
+        auto shadow = [&](bool needs_trace, V3 pos, float tmax, V3 dir, V3 contrib) {
+            int k = warp_append(&c->n_shadow, needs_trace);
+            if (k >= 0) {
+                sh_o[k] = make_float4(pos.x, pos.y, pos.z, tmax);
+                sh_d[k] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pixel));
+                sh_c[k] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+            }
+        };
+        bool alive;
+        if (EST == CRT_ESTIMATOR_MIS) alive = shade_vertex_mis(sc, p, ps, hit_t[i], slot, accum, shadow, nx);
+        else alive = shade_vertex_compat(sc, p, ps, hit_t[i], slot, accum, shadow, nx, npr);
         int k = warp_append(&c->n_next, alive);
         if (k < 0) continue;
-        if (nx.meta & kFlagProbe) {
+        if (EST == CRT_ESTIMATOR_MIS) n_pdf[k] = nx.pdf;
+        if (EST == CRT_ESTIMATOR_COMPAT && (nx.meta & kFlagProbe)) {
             pr_o_next[k] = make_float4(npr.o.x, npr.o.y, npr.o.z, 0.0f);
             pr_d_next[k] = make_float4(npr.d.x, npr.d.y, npr.d.z, 0.0f);
             pr_w_next[k] = make_float4(npr.w.x, npr.w.y, npr.w.z, 0.0f);
@@ -530,9 +663,10 @@ __global__ void __launch_bounds__(128) k_shade_compat(SceneView sc, Counters* c,
 // launches per bounce for ever smaller wavefronts. Same per-vertex statement as above, same Philox
 // keys and the same order-independent accumulation, so the image does not depend on where the
 // switch happens.
+template <int EST>
 __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderParamsDev p, const float4* __restrict__ q_o,
                                               const float4* __restrict__ q_d, const float4* __restrict__ q_T,
-                                              const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
+                                              const float* __restrict__ q_pdf, const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
                                               const float4* __restrict__ pr_w, long long* __restrict__ accum) {
     const uint32_t n = c->tail_n;
     if (n == 0) return;
@@ -544,14 +678,15 @@ __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderP
         PathState ps;
         ps.o = mk3(qo); ps.d = mk3(qd); ps.T = mk3(qT);
         ps.pixel = __float_as_uint(qo.w); ps.sample = __float_as_uint(qd.w); ps.meta = __float_as_uint(qT.w);
+        ps.pdf = EST == CRT_ESTIMATOR_MIS ? q_pdf[i] : 0.0f;
         ProbeState pr;
         pr.o = pr.d = pr.w = mk3(0.0f, 0.0f, 0.0f);
-        if (ps.meta & kFlagProbe) { pr.o = mk3(pr_o[i]); pr.d = mk3(pr_d[i]); pr.w = mk3(pr_w[i]); }
+        if (EST == CRT_ESTIMATOR_COMPAT && (ps.meta & kFlagProbe)) { pr.o = mk3(pr_o[i]); pr.d = mk3(pr_d[i]); pr.w = mk3(pr_w[i]); }
         for (;;) {
             const HitRec h = traverse<0>(sc, ps.o, ps.d, FLT_MAX);
             n_ext++;
             if (h.slot < 0) break;
-            if (ps.meta & kFlagProbe) {
+            if (EST == CRT_ESTIMATOR_COMPAT && (ps.meta & kFlagProbe)) {
                 const HitRec ph = traverse<0>(sc, pr.o, pr.d, FLT_MAX);
                 n_pr++;
                 probe_resolve(sc, ph.slot, pr.w, ps.pixel, accum);
@@ -559,18 +694,18 @@ __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderP
             PathState nx;
             ProbeState npr;
             const uint32_t pixel = ps.pixel;
-            const bool alive = shade_vertex_compat(
-                sc, p, ps, h.t, h.slot, accum,
-                [&](bool needs_trace, V3 pos, float t_to_light, V3 dir, V3 contrib) {
-                    if (!needs_trace) return;
-                    const HitRec b = traverse<1>(sc, pos, normalize(dir), t_to_light);
-                    n_sh++;
-                    if (b.slot < 0) accum_add(accum, pixel, contrib);
-                },
-                nx, npr);
+            auto shadow = [&](bool needs_trace, V3 pos, float tmax, V3 dir, V3 contrib) {
+                if (!needs_trace) return;
+                const HitRec b = traverse<1>(sc, pos, dir, tmax);
+                n_sh++;
+                if (b.slot < 0) accum_add(accum, pixel, contrib);
+            };
+            bool alive;
+            if (EST == CRT_ESTIMATOR_MIS) alive = shade_vertex_mis(sc, p, ps, h.t, h.slot, accum, shadow, nx);
+            else alive = shade_vertex_compat(sc, p, ps, h.t, h.slot, accum, shadow, nx, npr);
             if (!alive) break;
             ps = nx;
-            if (nx.meta & kFlagProbe) pr = npr;
+            if (EST == CRT_ESTIMATOR_COMPAT && (nx.meta & kFlagProbe)) pr = npr;
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -646,7 +781,7 @@ int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wav
     CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, 128, 0));
     w->grid_trace = num_sms() * std::max(occ, 1);
     w->grid_shade = num_sms() * 8;
-    CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tail, 128, 0));
+    CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tail<CRT_ESTIMATOR_MIS>, 128, 0));
     w->grid_tail = num_sms() * std::max(occ, 1);
     *out = w;
     return CRT_OK;
@@ -669,10 +804,10 @@ static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings
     if (shadow_cap > 0xffffffffull) { set_error("light_sample_n x lights too large"); return CRT_ERR_INVALID; }
     if (w->pool == pool && w->shadow_cap >= shadow_cap) return CRT_OK;
     for (int b = 0; b < 2; ++b) {
-        cudaFree(w->q_o[b]); cudaFree(w->q_d[b]); cudaFree(w->q_T[b]);
+        cudaFree(w->q_o[b]); cudaFree(w->q_d[b]); cudaFree(w->q_T[b]); cudaFree(w->q_pdf[b]);
         cudaFree(w->pr_o[b]); cudaFree(w->pr_d[b]); cudaFree(w->pr_w[b]); cudaFree(w->pr_list[b]);
         w->q_o[b] = w->q_d[b] = w->q_T[b] = w->pr_o[b] = w->pr_d[b] = w->pr_w[b] = nullptr;
-        w->pr_list[b] = nullptr;
+        w->pr_list[b] = nullptr; w->q_pdf[b] = nullptr;
     }
     cudaFree(w->hit_t); cudaFree(w->hit_slot); cudaFree(w->pr_hit); cudaFree(w->sh_o); cudaFree(w->sh_d); cudaFree(w->sh_c);
     w->hit_t = nullptr; w->hit_slot = nullptr; w->pr_hit = nullptr; w->sh_o = w->sh_d = w->sh_c = nullptr;
@@ -680,6 +815,7 @@ static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings
         CRT_CUDA(cudaMalloc(&w->q_o[b], sizeof(float4) * pool));
         CRT_CUDA(cudaMalloc(&w->q_d[b], sizeof(float4) * pool));
         CRT_CUDA(cudaMalloc(&w->q_T[b], sizeof(float4) * pool));
+        CRT_CUDA(cudaMalloc(&w->q_pdf[b], sizeof(float) * pool));
         if (w->has_probe) {
             CRT_CUDA(cudaMalloc(&w->pr_o[b], sizeof(float4) * pool));
             CRT_CUDA(cudaMalloc(&w->pr_d[b], sizeof(float4) * pool));
@@ -701,7 +837,7 @@ static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings
 void wavefront_destroy(Wavefront* w) {
     if (!w) return;
     for (int b = 0; b < 2; ++b) {
-        cudaFree(w->q_o[b]); cudaFree(w->q_d[b]); cudaFree(w->q_T[b]);
+        cudaFree(w->q_o[b]); cudaFree(w->q_d[b]); cudaFree(w->q_T[b]); cudaFree(w->q_pdf[b]);
         cudaFree(w->pr_o[b]); cudaFree(w->pr_d[b]); cudaFree(w->pr_w[b]); cudaFree(w->pr_list[b]);
     }
     cudaFree(w->hit_t); cudaFree(w->hit_slot); cudaFree(w->pr_hit);
@@ -718,7 +854,8 @@ long long* wavefront_accum(Wavefront* w) { return w->accum; }
 
 int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
                      float tan_half, cudaStream_t st, crt_render_stats* stats) {
-    if (rs.estimator != CRT_ESTIMATOR_COMPAT) { set_error("estimator not implemented"); return CRT_ERR_INVALID; }
+    if (rs.estimator != CRT_ESTIMATOR_COMPAT && rs.estimator != CRT_ESTIMATOR_MIS) { set_error("unknown estimator"); return CRT_ERR_INVALID; }
+    const bool mis = rs.estimator == CRT_ESTIMATOR_MIS;
     const size_t npix = (size_t)w->width * w->height;
     const unsigned long long work_all = (unsigned long long)npix * rs.spp;
     const unsigned long long w_begin = rs.range_set ? std::min(rs.work_begin, work_all) : 0;
@@ -756,19 +893,25 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         const int cur = it & 1, nxt = cur ^ 1;
         k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, tail_max, w->status_dev);
         if (rs.stage_timing) cudaEventRecord(se[0], st);
-        k_generate<<<w->grid_shade, 256, 0, st>>>(w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur]);
+        k_generate<<<w->grid_shade, 256, 0, st>>>(w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], mis ? w->q_pdf[cur] : nullptr);
         if (rs.stage_timing) cudaEventRecord(se[1], st);
         k_extend<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->q_o[cur], w->q_d[cur], w->hit_t, w->hit_slot);
         launches += 3;
-        if (w->has_probe) {
+        if (w->has_probe && !mis) {
             k_probe<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->pr_list[cur], w->pr_o[cur], w->pr_d[cur], w->hit_slot, w->pr_hit);
             launches++;
         }
         if (rs.stage_timing) cudaEventRecord(se[2], st);
-        k_shade_compat<<<w->grid_shade, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->hit_t,
-                                                       w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt], w->q_d[nxt],
-                                                       w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
-                                                       w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum);
+        if (mis)
+            k_shade<CRT_ESTIMATOR_MIS><<<w->grid_shade, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
+                                                                       w->q_pdf[nxt], w->hit_t, w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt],
+                                                                       w->q_d[nxt], w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
+                                                                       w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum);
+        else
+            k_shade<CRT_ESTIMATOR_COMPAT><<<w->grid_shade, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
+                                                                          w->q_pdf[nxt], w->hit_t, w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt],
+                                                                          w->q_d[nxt], w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
+                                                                          w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum);
 #ifdef CRT_EXP_SORT
         exp_sort(ds, w->counters, 1, w->sh_o, w->sh_d, w->sh_c, w->shadow_cap, st);
 #endif
@@ -778,8 +921,12 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
 #ifdef CRT_EXP_SORT
         exp_sort(ds, w->counters, 0, w->q_o[nxt], w->q_d[nxt], w->q_T[nxt], w->pool, st);
 #endif
-        k_tail<<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->pr_o[cur], w->pr_d[cur],
-                                             w->pr_w[cur], w->accum);
+        if (mis)
+            k_tail<CRT_ESTIMATOR_MIS><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
+                                                                     w->pr_o[cur], w->pr_d[cur], w->pr_w[cur], w->accum);
+        else
+            k_tail<CRT_ESTIMATOR_COMPAT><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
+                                                                        w->pr_o[cur], w->pr_d[cur], w->pr_w[cur], w->accum);
         launches += 3;
         if (rs.stage_timing) {
             cudaEventRecord(se[5], st);

@@ -40,7 +40,7 @@ def lib():
     L.orc_scene_error.restype = C.c_char_p
     L.orc_scene_error.argtypes = [vp]
     L.orc_scene_add_obj.argtypes = [vp, C.c_char_p, C.c_char_p]
-    L.orc_scene_add_arrays.argtypes = [vp, f32p, i32p, i32p, C.c_int, f32p, C.c_int]
+    L.orc_scene_add_arrays.argtypes = [vp, f32p, i32p, i32p, C.c_int, f32p, C.c_int, C.c_int]
     for n in ("n_tris", "n_mats", "n_lights", "n_objects"):
         getattr(L, "orc_scene_" + n).argtypes = [vp]
     L.orc_scene_get_tris.argtypes = [vp] + [vp] * 6
@@ -64,6 +64,9 @@ def lib():
     L.orc_philox.argtypes = [u32p, u32p, u32p]
     L.orc_u01.argtypes = [C.c_uint32]
     L.orc_u01.restype = C.c_float
+    for fn, na in (("orc_det_log2", 1), ("orc_det_exp2", 1), ("orc_det_pow", 2)):
+        getattr(L, fn).argtypes = [C.c_float] * na
+        getattr(L, fn).restype = C.c_float
     L.orc_sincos_2pi.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.orc_sincos_rad.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _LIB = L
@@ -116,9 +119,10 @@ class Scene:
 
     def add_arrays(self, verts, mat_id, obj_id, mats):
         verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
-        mats = np.ascontiguousarray(mats, np.float32).reshape(-1, 7)
+        mats = np.ascontiguousarray(mats, np.float32)          # rows of (kd, ke, ns) or (kd, ks, ke, ns)
+        assert mats.ndim == 2 and mats.shape[1] in (7, 10)
         self.L.orc_scene_add_arrays(self.h, verts, np.ascontiguousarray(mat_id, np.int32),
-                                    np.ascontiguousarray(obj_id, np.int32), verts.shape[0], mats, mats.shape[0])
+                                    np.ascontiguousarray(obj_id, np.int32), verts.shape[0], mats, mats.shape[0], mats.shape[1])
         return self
 
     @property
@@ -245,3 +249,15 @@ def sincos_rad(x):
     s, c = C.c_float(), C.c_float()
     lib().orc_sincos_rad(x, C.byref(s), C.byref(c))
     return s.value, c.value
+
+
+def det_log2(x):
+    return float(lib().orc_det_log2(float(x)))
+
+
+def det_exp2(x):
+    return float(lib().orc_det_exp2(float(x)))
+
+
+def det_pow(x, y):
+    return float(lib().orc_det_pow(float(x), float(y)))

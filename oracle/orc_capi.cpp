@@ -28,15 +28,17 @@ int orc_scene_add_obj(orc_scene* h, const char* obj_path, const char* mtl_dir) {
 
 // Synthetic scenes: verts T*9, mat_id T, obj_id T (objects numbered 0..n_obj-1 in first-use order),
 // mats n_mat*7 = kd(3), ke(3), ns.
+// mats: n_mats rows of mat_cols floats: 7 = (kd, ke, ns), 10 = (kd, ks, ke, ns)
 int orc_scene_add_arrays(orc_scene* h, const float* verts, const int* mat_id, const int* obj_id, int n_tris,
-                         const float* mats, int n_mats) {
+                         const float* mats, int n_mats, int mat_cols) {
     Scene& s = h->s;
     int mat0 = (int)s.mats.size(), obj0 = s.n_objects, max_obj = -1;
     for (int m = 0; m < n_mats; ++m) {
         Material mm;
-        mm.kd = V3{mats[7 * m + 0], mats[7 * m + 1], mats[7 * m + 2]};
-        mm.ke = V3{mats[7 * m + 3], mats[7 * m + 4], mats[7 * m + 5]};
-        mm.ns = mats[7 * m + 6];
+        const float* r = mats + (size_t)mat_cols * m;
+        mm.kd = V3{r[0], r[1], r[2]};
+        if (mat_cols == 10) { mm.ks = V3{r[3], r[4], r[5]}; mm.ke = V3{r[6], r[7], r[8]}; mm.ns = r[9]; }
+        else { mm.ke = V3{r[3], r[4], r[5]}; mm.ns = r[6]; }
         finish_material(mm);
         s.mats.push_back(mm);
     }
@@ -152,6 +154,10 @@ int orc_trace(orc_scene* h, int which, int mode, const float* rays, int64_t n, f
     return 0;
 }
 
+float orc_det_log2(float x) { return det_log2(x); }
+float orc_det_exp2(float x) { return det_exp2(x); }
+float orc_det_pow(float x, float y) { return det_pow(x, y); }
+
 // Canonical triangle test of face faces[k] against ray k (checks a reported any-hit blocker):
 // t_out = t of the Moeller-Trumbore statement, inside_out = 1 when the strict-inside rule accepts it.
 int orc_tri_test(orc_scene* h, const float* rays, const int* faces, int64_t n, float* t_out, unsigned char* inside_out) {
@@ -191,7 +197,7 @@ int orc_render(orc_scene* h, const float eye[3], const float M[9], float fovy_ra
                uint32_t s_begin, uint32_t s_end, float p_rr, int light_sample_n, uint32_t seed, int estimator,
                int64_t* accum, uint64_t* stats12, int n_threads) {
     if (!h->has_new) return -1;
-    if (estimator != ESTIMATOR_COMPAT) return -2;
+    if (estimator < ESTIMATOR_COMPAT || estimator > ESTIMATOR_MIS_BSDF_ONLY) return -2;
     Camera cam;
     cam.eye = V3{eye[0], eye[1], eye[2]};
     memcpy(cam.M, M, sizeof(cam.M));

@@ -122,6 +122,53 @@ static inline void sincos_rad(float x, float* s, float* c) {
     }
 }
 
+static inline uint32_t f2u(float f);
+static inline float u2f(uint32_t u);
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic log2 / exp2 / pow for the Phong lobe of the `mis` estimator (never libm).
+//   log2: x = m * 2^e with m in [sqrt(1/2), sqrt(2)); log2(m) = 2/ln2 * atanh(s), s = (m-1)/(m+1),
+//         odd series up to s^9 (|s| <= 0.1716: truncation < 4e-10);
+//   exp2: y = n + r, |r| <= 1/2, 2^r by the degree-6 Taylor polynomial of exp(r ln2), scaled by 2^n
+//         through the exponent field; y < -126 gives 0.
+// ---------------------------------------------------------------------------------------------
+static inline float det_log2(float x) {
+    uint32_t b;
+    memcpy(&b, &x, 4);
+    int e = (int)(b >> 23) - 127;
+    uint32_t mb = (b & 0x7fffffu) | 0x3f800000u;
+    float m;
+    memcpy(&m, &mb, 4);
+    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    float f = m - 1.0f;
+    float sq = f / (2.0f + f);
+    float s2 = sq * sq;
+    float p = fmaf(s2, 0.11111111f, 0.14285715f);
+    p = fmaf(p, s2, 0.2f);
+    p = fmaf(p, s2, 0.33333334f);
+    float r = fmaf(sq * s2, p, sq);
+    return fmaf(r, 2.8853900f, (float)e);
+}
+static inline float det_exp2(float y) {
+    if (!(y >= -126.0f)) return 0.0f;
+    if (y > 127.0f) y = 127.0f;
+    float n = rintf(y);
+    float r = y - n;
+    float p = fmaf(r, 1.5403530e-4f, 1.3333558e-3f);
+    p = fmaf(p, r, 9.6181291e-3f);
+    p = fmaf(p, r, 5.5504109e-2f);
+    p = fmaf(p, r, 2.4022651e-1f);
+    p = fmaf(p, r, 6.9314718e-1f);
+    p = fmaf(p, r, 1.0f);
+    uint32_t sb = (uint32_t)((int)n + 127) << 23;
+    float sc;
+    memcpy(&sc, &sb, 4);
+    return p * sc;
+}
+static inline float det_pow(float x, float y) { return det_exp2(y * det_log2(x)); }
+// Rec. 709 luminance, used only to choose between lobes and between light triangles
+static inline float lumf(V3 c) { return fmaf(0.0722f, c.z, fmaf(0.7152f, c.y, 0.2126f * c.x)); }
+
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 

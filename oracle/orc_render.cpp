@@ -192,6 +192,150 @@ static void path_compat(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sam
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// `mis` estimator (north star (c): BRDFs from Kd/Ks/Ns, next-event estimation against the emissive
+// triangles with multiple importance sampling, Russian roulette at P_RR). Not the reference's
+// estimator (the reference has no MIS); its oracle is this function.
+//   surface   two-sided: n_s faces the incoming ray; emission is one-sided (front of the light triangle)
+//   BRDF      modified Phong: kd/pi + ks (Ns+2)/(2 pi) max(0, r.wi)^Ns, r = mirror direction of wo
+//   lights    a triangle is picked with probability ~ area * luminance(Ke) (CDF, binary search), a point
+//             uniformly on it; density per area = luminance(Ke) / sum(area * luminance)
+//   BSDF      lobe chosen with probability lum(kd) / (lum(kd) + lum(ks)): cosine hemisphere or Phong lobe
+//   MIS       power heuristic between light_sample_n light samples and the one BSDF sample
+//   RR        continue with probability P_RR after every vertex (as the reference does, Render.cuh:216-221)
+// ---------------------------------------------------------------------------------------------
+static inline int pick_light(const std::vector<float>& cdf, float u) {
+    int lo = 0, hi = (int)cdf.size() - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cdf[mid] >= u) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+static inline void phong_eval(const Material& m, float pd, bool has_spec, float cos_s, float ca, V3* f, float* pdf) {
+    V3 fd = m.kd / kPi;
+    float pdf_d = cos_s / kPi;
+    if (has_spec) {
+        float pw = det_pow(ca, m.ns);
+        *f = fd + m.ks * ((m.ns + 2.0f) / kTwoPi * pw);
+        float pdf_s = (m.ns + 1.0f) / kTwoPi * pw;
+        *pdf = fmaf(pd, pdf_d, (1.0f - pd) * pdf_s);
+    } else {
+        *f = fd;
+        *pdf = pdf_d;
+    }
+}
+
+static void path_mis(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sample, int64_t* px, RenderStats* st) {
+    const Scene& s = c.s;
+    const RenderParams& p = c.p;
+    U4 r = draw(pixel, sample, kCameraBounce, 0, p.seed);
+    Ray ray = primary_ray(c.cam, p.width, p.height, i, j, u01(r.x), u01(r.y));
+    V3 T{1.0f, 1.0f, 1.0f};
+    float pdf_b = 0.0f;
+    const float lsn_f = (float)p.light_sample_n;
+    const int n_lt = (int)s.light_flat.size();
+    // validation variants of this oracle only (never on the GPU): the same integral with light samples
+    // alone or with BSDF samples alone; all three must converge to the same image (tests/test_oracle.py)
+    const int variant = p.estimator;
+    for (int bnc = 0; bnc < p.max_vertices; ++bnc) {
+        Hit h = new_intersect(s, c.b, ray, 0, &st->closest);
+        st->extend_rays++;
+        if (h.face < 0) break;
+        const Tri& tri = s.tris[h.face];
+        const Material& m = s.mats[tri.mat];
+        V3 n = tri.normal;
+        float dn = dot(n, ray.d);
+        if (m.has_emit) {
+            if (dn < 0.0f) {
+                if (bnc == 0) add_contrib(px, m.ke);
+                else {
+                    float pl = m.pdf_area * (h.t * h.t) / (-dn);
+                    float pls = lsn_f * pl;
+                    float w = (pdf_b * pdf_b) / fmaf(pdf_b, pdf_b, pls * pls);
+                    if (variant == ESTIMATOR_MIS_LIGHT_ONLY) w = 0.0f;
+                    if (variant == ESTIMATOR_MIS_BSDF_ONLY) w = 1.0f;
+                    add_contrib(px, cmul(T, m.ke) * w);
+                }
+            }
+            break;
+        }
+        V3 ns = dn > 0.0f ? neg(n) : n;
+        V3 wo = neg(ray.d);
+        V3 pos = ray.o + h.t * ray.d;
+        float off = 1.0e-4f * (1.0f + fmaxf(fmaxf(fabsf(pos.x), fabsf(pos.y)), fabsf(pos.z)));
+        V3 org = pos + off * ns;
+        float cos_o = dot(ns, wo);
+        V3 refl = normalize((2.0f * cos_o) * ns - wo);
+        float lkd = lumf(m.kd), lks = lumf(m.ks);
+        float lsum = lkd + lks;
+        if (!(lsum > 0.0f)) break;
+        float pd = lkd / lsum;
+        bool has_spec = lks > 0.0f;
+        for (int sj = 0; sj < p.light_sample_n && n_lt > 0; ++sj) {
+            U4 q = draw(pixel, sample, (uint32_t)bnc, 2u + (uint32_t)sj, p.seed);
+            int k = pick_light(s.light_cdf, u01(q.x));
+            const Tri& lt = s.tris[s.light_flat[k]];
+            const Material& lm = s.mats[lt.mat];
+            float su = sqrtf(u01(q.y));
+            float b0 = 1.0f - su, b1 = u01(q.z) * su;
+            float b2 = (1.0f - b0) - b1;
+            V3 lp = (b0 * lt.v1 + b1 * lt.v2) + b2 * lt.v3;
+            V3 dist = lp - org;
+            float d2 = dot(dist, dist);
+            float d1 = sqrtf(d2);
+            V3 wi = dist / d1;
+            float cos_s = dot(ns, wi);
+            float cos_l = -dot(lt.normal, wi);
+            if (!(cos_s > 0.0f && cos_l > 0.0f)) continue;
+            float ca = fmaxf(0.0f, dot(refl, wi));
+            V3 f;
+            float pb;
+            phong_eval(m, pd, has_spec, cos_s, ca, &f, &pb);
+            float pl = lm.pdf_area * d2 / cos_l;
+            float pls = lsn_f * pl;
+            float w = (pls * pls) / fmaf(pls, pls, pb * pb);
+            if (variant == ESTIMATOR_MIS_LIGHT_ONLY) w = 1.0f;
+            if (variant == ESTIMATOR_MIS_BSDF_ONLY) w = 0.0f;
+            V3 contrib = cmul(cmul(T, f), lm.ke) * (cos_s * w / pls);
+            if (contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f) continue;
+            Ray sh{org, wi, d1 * 0.999f};
+            Hit bh = new_intersect(s, c.b, sh, 1, &st->any);
+            st->shadow_rays++;
+            if (bh.face >= 0) continue;
+            add_contrib(px, contrib);
+        }
+        if (bnc == p.max_vertices - 1) break;
+        U4 q = draw(pixel, sample, (uint32_t)bnc, 0, p.seed);
+        if (u01(q.x) > p.p_rr) break;
+        float u1 = u01(q.z), u2 = u01(q.w);
+        float sn, cs;
+        sincos_2pi(u2, &sn, &cs);
+        V3 wi;
+        if (u01(q.y) <= pd) {
+            float rr = sqrtf(u1);
+            float z = sqrtf(1.0f - u1);
+            wi = to_world(V3{rr * cs, rr * sn, z}, ns);
+        } else {
+            float ca0 = det_pow(u1, 1.0f / (m.ns + 1.0f));
+            float sa0 = sqrtf(fmaxf(0.0f, 1.0f - ca0 * ca0));
+            wi = to_world(V3{sa0 * cs, sa0 * sn, ca0}, refl);
+        }
+        wi = normalize(wi);
+        float cos_s = dot(ns, wi);
+        if (!(cos_s > 0.0f)) break;
+        float ca = fmaxf(0.0f, dot(refl, wi));
+        V3 f;
+        float pb;
+        phong_eval(m, pd, has_spec, cos_s, ca, &f, &pb);
+        if (!(pb > 0.0f)) break;
+        T = cmul(T, f) * (cos_s / pb / p.p_rr);
+        pdf_b = pb;
+        ray = Ray{org, wi, FLT_MAX};
+    }
+}
+
 void render(const Scene& s, const NewBVH& b, const Camera& cam, const RenderParams& p, int64_t* accum,
             RenderStats* stats, int n_threads) {
     Ctx c{s, b, cam, p};
@@ -206,7 +350,8 @@ void render(const Scene& s, const NewBVH& b, const Camera& cam, const RenderPara
 #endif
         int i = pix % p.width, j = pix / p.width;
         for (uint32_t sm = p.s_begin; sm < p.s_end; ++sm) {
-            path_compat(c, (uint32_t)pix, i, j, sm, accum + 3 * (size_t)pix, &tls[tid]);
+            if (p.estimator != ESTIMATOR_COMPAT) path_mis(c, (uint32_t)pix, i, j, sm, accum + 3 * (size_t)pix, &tls[tid]);
+            else path_compat(c, (uint32_t)pix, i, j, sm, accum + 3 * (size_t)pix, &tls[tid]);
             tls[tid].samples++;
         }
     }

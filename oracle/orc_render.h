@@ -11,7 +11,8 @@
 
 namespace orc {
 
-enum Estimator { ESTIMATOR_COMPAT = 0, ESTIMATOR_MIS = 1 };
+// 2 and 3 exist in the oracle only: the mis integral estimated with light samples alone / BSDF samples alone
+enum Estimator { ESTIMATOR_COMPAT = 0, ESTIMATOR_MIS = 1, ESTIMATOR_MIS_LIGHT_ONLY = 2, ESTIMATOR_MIS_BSDF_ONLY = 3 };
 
 struct Camera {
     V3 eye;

@@ -68,13 +68,27 @@ void finish_objects(Scene& s) {
         }
         s.lights[it->second].tris.push_back(i);
     }
+    // mis estimator tables (DESIGN.md "mis"): weights in double, sequential, then rounded once
+    s.light_flat.clear();
+    s.light_cdf.clear();
+    for (const LightObj& L : s.lights)
+        for (int f : L.tris) s.light_flat.push_back(f);
+    double W = 0.0;
+    for (int f : s.light_flat) W += (double)s.tris[f].area * (double)lumf(s.mats[s.tris[f].mat].ke);
+    double acc = 0.0;
+    for (int f : s.light_flat) {
+        acc += (double)s.tris[f].area * (double)lumf(s.mats[s.tris[f].mat].ke);
+        s.light_cdf.push_back(W > 0.0 ? (float)(acc / W) : 1.0f);
+    }
+    if (!s.light_cdf.empty()) s.light_cdf.back() = 1.0f;
+    for (Material& m : s.mats) m.pdf_area = (m.has_emit && W > 0.0) ? (float)((double)lumf(m.ke) / W) : 0.0f;
 }
 
 namespace {
 struct Shape {                       // OBJLoader.h:12-39
     std::string material_id;
     std::vector<std::vector<uint64_t>> vs;
-    float kd[3] = {0, 0, 0}, ke[3] = {0, 0, 0};
+    float kd[3] = {0, 0, 0}, ks[3] = {0, 0, 0}, ke[3] = {0, 0, 0};
     float ns = 1.0f;                 // reference leaves _ns uninitialised without an Ns line; 1 here
 };
 }  // namespace
@@ -136,6 +150,10 @@ bool load_obj(Scene& s, const std::string& obj_path, const std::string& mtl_dir)
             float k[3] = {0, 0, 0};
             ls >> k[0] >> k[1] >> k[2];
             for (auto i : ids) { shapes[i].kd[0] = k[0]; shapes[i].kd[1] = k[1]; shapes[i].kd[2] = k[2]; }
+        } else if (prefix == "Ks") {     // dropped by the reference (Loader.h:45-47,107); kept for the mis estimator only
+            float k[3] = {0, 0, 0};
+            ls >> k[0] >> k[1] >> k[2];
+            for (auto i : ids) { shapes[i].ks[0] = k[0]; shapes[i].ks[1] = k[1]; shapes[i].ks[2] = k[2]; }
         } else if (prefix == "Ke") {
             float k[3] = {0, 0, 0};
             ls >> k[0] >> k[1] >> k[2];
@@ -145,13 +163,14 @@ bool load_obj(Scene& s, const std::string& obj_path, const std::string& mtl_dir)
             ls >> ns;
             for (auto i : ids) shapes[i].ns = ns;
         }
-        // Ks is parsed and dropped (Loader.h:45-47,107); Ka, Tr, Ni, illum are ignored;
+        // Ka, Tr, Ni, illum are ignored;
         // map_Kd (Loader.h:55-59,78-105) is out of scope (no shipped scene has one).
     }
     // Loader.h:40-124 + main.cu:131-144: one Object per shape, in shape order.
     for (const Shape& sh : shapes) {
         Material m;
         m.kd = V3{sh.kd[0], sh.kd[1], sh.kd[2]};
+        m.ks = V3{sh.ks[0], sh.ks[1], sh.ks[2]};
         m.ke = V3{sh.ke[0], sh.ke[1], sh.ke[2]};
         m.ns = sh.ns;
         m.name = sh.material_id;

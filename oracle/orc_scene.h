@@ -16,7 +16,9 @@ enum Mode { DIFFUSE = 0, SPECULAR = 1 };   // include/Material.h:7-10
 
 struct Material {            // include/Material.h:11-40, as filled by Loader.h:45-47,107
     V3 kd{0, 0, 0};
+    V3 ks{0, 0, 0};          // kept for the `mis` estimator only; `compat` ignores it like Loader.h:45-47
     V3 ke{0, 0, 0};
+    float pdf_area = 0.0f;   // mis: density (per unit area) of light sampling on a triangle of this material
     float ns = 1.0f;
     int has_emit = 0;        // !(ke.x<eps && ke.y<eps && ke.z<eps), Material.h:36-39
     int mode = DIFFUSE;      // ns > 1 ? SPECULAR : DIFFUSE, Loader.h:107
@@ -45,6 +47,10 @@ struct Scene {
     std::vector<Tri> tris;            // Scene::triangles order (face id = index)
     std::vector<Material> mats;
     std::vector<LightObj> lights;     // Scene::light_objs order
+    // mis estimator: all light triangles in (light object, object order), and the CDF that picks one with
+    // probability proportional to area * luminance(Ke)
+    std::vector<int> light_flat;
+    std::vector<float> light_cdf;
     int n_objects = 0;
     std::string error;
 };

@@ -241,6 +241,63 @@ def test_tail_switch_point_does_not_change_the_image(gpu, orc, scene_files, monk
         assert st["iterations"] > 8
 
 
+def _mis_pair(gpu, orc, a, b, eye, M, fovy, W, H, spp, p_rr, lsn, seed=0):
+    R = gpu.Render(a, W, H, spp, p_rr, lsn)
+    R.set_seed(seed)
+    R.set_estimator(gpu.ESTIMATOR_MIS)
+    R.run_view(eye, M, fovy)
+    oacc, ost = b.render(eye, M, float(fovy), W, H, 0, spp, p_rr, lsn, seed=seed, estimator=1)
+    return R, R.get_accum_i64(), oacc, ost
+
+
+@pytest.mark.parametrize("name,W,H", [("veach-mis", 800, 600), ("cornell-box", 400, 300)])
+def test_mis_estimator_matched_seed(gpu, orc, scene_files, name, W, H):
+    """North star (c): NEE with MIS, Phong lobes from Kd/Ks/Ns. C2 (veach-mis) at its full shipped size; the
+    fixed-point buffers are identical to the CPU statement (stated tolerance: 1e-4 relative per pixel)."""
+    cfg, a, b = _pair(gpu, orc, scene_files, name)
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    R, acc, oacc, ost = _mis_pair(gpu, orc, a, b, cfg.eye_pos, M, cfg.fovy_rad, W, H, cfg.spp, cfg.P_RR, cfg.light_sample_n)
+    st = R.stats()
+    assert (st["extend_rays"], st["shadow_rays"], st["probe_rays"]) == (ost["extend_rays"], ost["shadow_rays"], 0)
+    lin = R.get_accum().reshape(-1)
+    olin, _ = orc.resolve(oacc, W * H, cfg.spp)
+    assert (np.abs(lin - olin) / np.maximum(np.abs(olin), 1e-6)).max() <= 1e-4
+    assert np.array_equal(acc, oacc)
+    assert acc.any()
+
+
+@pytest.mark.parametrize("tail", ["0", "2000", "1000000"])
+def test_mis_estimator_options_and_tail(gpu, orc, monkeypatch, tail):
+    monkeypatch.setenv("CRT_TAIL", tail)
+    verts, mat, obj, mats7 = box_scene(np.random.default_rng(3), 300)
+    mats = np.zeros((len(mats7), 10), np.float32)                       # (kd, ks, ke, ns)
+    mats[:, 0:3] = mats7[:, 0:3]; mats[:, 6:9] = mats7[:, 3:6]; mats[:, 9] = mats7[:, 6]
+    mats[4, 3:6] = [0.5, 0.4, 0.3]; mats[4, 9] = 60.0                    # glossy plate
+    mats[5, 3:6] = [0.2, 0.2, 0.2]; mats[5, 9] = 8.0                     # glossy soup
+    a = gpu.Scene().add_triangles(verts, mat.astype(np.uint32), obj.astype(np.uint32), mats)
+    a.set_BVH(2)
+    b = orc.Scene().add_arrays(verts, mat, obj, mats)
+    b.build_new_bvh(2)
+    M = gpu.inverse_view_matrix(BOX_CAMERA["eye"], BOX_CAMERA["lookat"], BOX_CAMERA["up"])
+    for (W, H, spp, p_rr, lsn, seed) in [(96, 64, 6, 0.7, 2, 0), (33, 17, 3, 0.95, 1, 5), (64, 48, 2, 1.0, 3, 9), (40, 30, 4, 0.0, 1, 2)]:
+        R, acc, oacc, ost = _mis_pair(gpu, orc, a, b, BOX_CAMERA["eye"], M, BOX_CAMERA["fovy"], W, H, spp, p_rr, lsn, seed)
+        assert np.array_equal(acc, oacc), (W, H, spp, p_rr, lsn, seed)
+        assert R.stats()["shadow_rays"] == ost["shadow_rays"] and ost["shadow_rays"] > 0
+    # shards of the work index space add up for mis too
+    R = gpu.Render(a, 64, 48, 4, 0.7, 2)
+    R.set_estimator(gpu.ESTIMATOR_MIS)
+    R.run_view(BOX_CAMERA["eye"], M, BOX_CAMERA["fovy"])
+    full = R.get_accum_i64()
+    from cudaraytracing_b200.distributed import shard_work
+    total = np.zeros_like(full)
+    for r in range(3):
+        w0, w1 = shard_work(64 * 48, 4, r, 3)
+        R.set_work_range(w0, w1)
+        R.run_view(BOX_CAMERA["eye"], M, BOX_CAMERA["fovy"])
+        total += R.get_accum_i64()
+    assert np.array_equal(total, full)
+
+
 def test_save_png_and_cli(gpu, scene_files, tmp_path):
     import subprocess
     import struct

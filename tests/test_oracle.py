@@ -205,3 +205,42 @@ def test_compat_estimator_converges_to_analytic_value(orc):
     assert np.allclose(means[0], means[1], rtol=0.1)
     # direct light at the floor centre from a 2x2 light of radiance 10 at height 5: E ~ L*A*cos*cos/d^2 = 10*4/25
     assert 0.05 < means[0][0] < 10 * 4 / 25 * 0.5 / math.pi * 3
+
+
+def test_det_log2_exp2_pow_accuracy(orc):
+    """The Phong lobe of the mis estimator uses these instead of libm (bit-identical on CPU and GPU)."""
+    xs = np.concatenate([np.linspace(1e-6, 1, 500), np.linspace(0.99, 1, 500), [2.0, 3.5, 1000.0]]).astype(np.float32)
+    assert max(abs(orc.det_log2(x) - math.log2(float(x))) for x in xs) < 1e-6
+    ys = np.linspace(-120, 20, 1001).astype(np.float32)
+    assert max(abs(orc.det_exp2(y) / 2.0 ** float(y) - 1) for y in ys) < 5e-7
+    assert orc.det_pow(0.5, 2.0) == 0.25 and orc.det_pow(1.0, 5000.0) == 1.0 and orc.det_pow(0.0, 5000.0) == 0.0
+    assert orc.det_exp2(-200.0) == 0.0
+    assert abs(orc.det_pow(0.999, 5000.0) / 0.999 ** 5000 - 1) < 1e-3
+
+
+def test_mis_estimator_is_consistent(orc, scene_files):
+    """mis = the same integral as 'light samples only' and 'BSDF samples only' (oracle-only variants 2, 3): on
+    veach-mis (glossy plates, four light sizes) the three images converge to the same mean; MIS has the
+    lowest variance of the three on the plates."""
+    import cudaraytracing_b200 as crt
+    f = scene_files["veach-mis"]
+    cfg = crt.load_config(f["cfg_path"])
+    S = orc.Scene().add_obj(f["obj"], f["dir"])
+    S.build_new_bvh(cfg.bvh_thresh_n)
+    M = orc.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    W, H, spp = 64, 48, 700
+    means, lows = [], []
+    for est in (1, 2, 3):
+        acc, st = S.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 0, spp, cfg.P_RR, cfg.light_sample_n, estimator=est)
+        lin, _ = orc.resolve(acc, W * H, spp)
+        im = lin.reshape(H, W, 3)
+        means.append(im.mean())
+        lows.append(im[H // 2:].mean())
+        assert st["samples"] == W * H * spp
+    assert max(means) / min(means) < 1.03, means
+    assert max(lows) / min(lows) < 1.06, lows
+    # the split of the spp range is exact for mis too
+    a1, _ = S.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 0, 3, cfg.P_RR, 2, estimator=1)
+    a2, _ = S.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 3, 8, cfg.P_RR, 2, estimator=1)
+    a3, _ = S.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 0, 8, cfg.P_RR, 2, estimator=1)
+    assert np.array_equal(a1 + a2, a3)
