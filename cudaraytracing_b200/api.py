@@ -17,6 +17,7 @@ _LIB = None
 
 ESTIMATOR_COMPAT, ESTIMATOR_MIS = 0, 1
 RAY_CLOSEST, RAY_ANY = 0, 1
+BUILDER_LBVH, BUILDER_LBVH8 = 0, 1
 MAX_OBJ_PATHS, PATH_LEN = 16, 1024
 
 
@@ -48,6 +49,11 @@ BVH_NODE = np.dtype([("c0lox", "<f4"), ("c0hix", "<f4"), ("c0loy", "<f4"), ("c0h
                      ("c1lox", "<f4"), ("c1hix", "<f4"), ("c1loy", "<f4"), ("c1hiy", "<f4"),
                      ("c0loz", "<f4"), ("c0hiz", "<f4"), ("c1loz", "<f4"), ("c1hiz", "<f4"),
                      ("c0", "<i4"), ("c1", "<i4"), ("n0", "<i4"), ("n1", "<i4")])
+# crt_bvh8_node (include/crt.h): 80 bytes
+BVH8_NODE = np.dtype([("origin", "<f4", 3), ("exp", "u1", 3), ("imask", "u1"), ("child_base", "<u4"), ("tri_base", "<u4"),
+                      ("meta", "u1", 8), ("qlo_x", "u1", 8), ("qlo_y", "u1", 8), ("qlo_z", "u1", 8),
+                      ("qhi_x", "u1", 8), ("qhi_y", "u1", 8), ("qhi_z", "u1", 8)])
+assert BVH8_NODE.itemsize == 80
 
 
 def lib_path():
@@ -81,6 +87,8 @@ def load_library():
         "crt_scene_export_mats": [vp, vp],
         "crt_scene_export_light": [vp, u32, vp, C.POINTER(u32), C.POINTER(f32)],
         "crt_scene_export_bvh": [vp, vp, vp, vp, vp],
+        "crt_scene_export_bvh8": [vp, vp, vp, vp, vp],
+        "crt_scene_bvh_kind": [vp, C.POINTER(i32)],
         "crt_scene_destroy": [vp],
         "crt_trace_rays": [vp, vp, u64, i32, vp, vp, C.POINTER(f32)],
         "crt_trace_rays_device": [vp, vp, u64, i32, vp, vp, vp, C.POINTER(f32)],
@@ -241,13 +249,21 @@ class Scene:
             res.append((faces, area.value))
         return res
 
+    def bvh_kind(self):
+        k = C.c_int()
+        _check(self.L.crt_scene_bvh_kind(self.h, C.byref(k)))
+        return k.value
+
     def export_bvh(self):
+        """nodes (BVH_NODE, or BVH8_NODE for a scene built with BUILDER_LBVH8), order, last, bounds."""
         c = self.counts()
-        nodes = np.zeros(c["n_nodes"], BVH_NODE)
+        wide = self.bvh_kind() == BUILDER_LBVH8
+        nodes = np.zeros(c["n_nodes"], BVH8_NODE if wide else BVH_NODE)
         order = np.zeros(c["n_tris"], np.int32)
         last = np.zeros(c["n_tris"], np.uint8)
         bounds = np.zeros(6, np.float32)
-        _check(self.L.crt_scene_export_bvh(self.h, _p(nodes), _p(order), _p(last), _p(bounds)))
+        fn = self.L.crt_scene_export_bvh8 if wide else self.L.crt_scene_export_bvh
+        _check(fn(self.h, _p(nodes), _p(order), _p(last), _p(bounds)))
         return nodes, order, last, bounds
 
     def trace_rays(self, rays, mode=RAY_CLOSEST):

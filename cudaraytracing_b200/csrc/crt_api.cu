@@ -110,11 +110,11 @@ int crt_scene_add_triangles(crt_scene* s, const float* verts, const uint32_t* ma
 
 int crt_scene_build_bvh(crt_scene* s, uint32_t thresh_n, int builder, int device, float* build_ms) {
     CHECK_ARG(s, "crt_scene_build_bvh: null scene");
-    CHECK_ARG(builder == CRT_BUILDER_LBVH, "crt_scene_build_bvh: unknown builder");
+    CHECK_ARG(builder == CRT_BUILDER_LBVH || builder == CRT_BUILDER_LBVH8, "crt_scene_build_bvh: unknown builder");
     int n = crt_device_count();
     if (n <= 0) { set_error("crt_scene_build_bvh: no CUDA device (there is no CPU fallback)"); return CRT_ERR_CUDA; }
     CHECK_ARG(device >= 0 && device < n, "crt_scene_build_bvh: device out of range");
-    int rc = upload_scene(s->host, thresh_n, device, s->dev, build_ms);
+    int rc = upload_scene(s->host, thresh_n, builder, device, s->dev, build_ms);
     s->built = rc == CRT_OK;
     s->thresh_n = thresh_n;
     return rc;
@@ -169,11 +169,32 @@ int crt_scene_export_light(crt_scene* s, uint32_t li, int32_t* faces, uint32_t* 
 int crt_scene_export_bvh(crt_scene* s, crt_bvh_node* nodes, int32_t* tri_order, uint8_t* last, float bounds[6]) {
     CHECK_ARG(s, "crt_scene_export_bvh: null scene");
     if (!s->built) { set_error("crt_scene_export_bvh: BVH not built"); return CRT_ERR_STATE; }
+    if (s->dev.wide) { set_error("crt_scene_export_bvh: the scene has 8-wide nodes (use crt_scene_export_bvh8)"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(s->dev.device));
     if (nodes && s->dev.n_nodes) CRT_CUDA(cudaMemcpy(nodes, s->dev.nodes, sizeof(crt_bvh_node) * s->dev.n_nodes, cudaMemcpyDeviceToHost));
     if (tri_order && s->dev.n_tris) CRT_CUDA(cudaMemcpy(tri_order, s->dev.order, sizeof(int32_t) * s->dev.n_tris, cudaMemcpyDeviceToHost));
     if (last && s->dev.n_tris) CRT_CUDA(cudaMemcpy(last, s->dev.last, s->dev.n_tris, cudaMemcpyDeviceToHost));
     if (bounds) memcpy(bounds, s->dev.bounds, sizeof(float) * 6);
+    return CRT_OK;
+}
+
+int crt_scene_export_bvh8(crt_scene* s, crt_bvh8_node* nodes, int32_t* tri_order, uint8_t* last, float bounds[6]) {
+    static_assert(sizeof(crt_bvh8_node) == 80, "crt_bvh8_node must be 80 bytes");
+    CHECK_ARG(s, "crt_scene_export_bvh8: null scene");
+    if (!s->built) { set_error("crt_scene_export_bvh8: BVH not built"); return CRT_ERR_STATE; }
+    if (!s->dev.wide) { set_error("crt_scene_export_bvh8: the scene has child-pair nodes (use crt_scene_export_bvh)"); return CRT_ERR_STATE; }
+    CRT_CUDA(cudaSetDevice(s->dev.device));
+    if (nodes && s->dev.n_nodes) CRT_CUDA(cudaMemcpy(nodes, s->dev.nodes, sizeof(crt_bvh8_node) * s->dev.n_nodes, cudaMemcpyDeviceToHost));
+    if (tri_order && s->dev.n_tris) CRT_CUDA(cudaMemcpy(tri_order, s->dev.order, sizeof(int32_t) * s->dev.n_tris, cudaMemcpyDeviceToHost));
+    if (last && s->dev.n_tris) CRT_CUDA(cudaMemcpy(last, s->dev.last, s->dev.n_tris, cudaMemcpyDeviceToHost));
+    if (bounds) memcpy(bounds, s->dev.bounds, sizeof(float) * 6);
+    return CRT_OK;
+}
+
+int crt_scene_bvh_kind(crt_scene* s, int* builder) {
+    CHECK_ARG(s && builder, "crt_scene_bvh_kind: null argument");
+    if (!s->built) { set_error("crt_scene_bvh_kind: BVH not built"); return CRT_ERR_STATE; }
+    *builder = s->dev.wide ? CRT_BUILDER_LBVH8 : CRT_BUILDER_LBVH;
     return CRT_OK;
 }
 

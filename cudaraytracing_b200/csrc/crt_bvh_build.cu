@@ -13,6 +13,7 @@
 // Every float operation is exact (min/max) or a single rounding shared with the CPU statement
 // (this file is compiled with -fmad=false), so the result does not depend on thread scheduling.
 #include "crt_gpu.h"
+#include "crt_wide.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -376,6 +377,199 @@ __global__ void k_emit_tris(uint32_t n, const uint32_t* __restrict__ order, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// 8-wide compressed nodes (builder CRT_BUILDER_LBVH8): collapse of the radix tree, one wide-tree level
+// per pass. CPU statement: oracle/orc_bvh.cpp build_wide8_bvh (byte-identical output required).
+//   k_wide_collapse  one thread per wide node of the level: greedy collapse (largest-area expandable
+//                    child first) and greedy slot assignment by octant; counts its internal children
+//                    and leaf triangles
+//   (two exclusive scans: where the children / leaf triangles of every node of the level start)
+//   k_wide_emit      quantises the child boxes outwards in double arithmetic, writes the 80-byte node,
+//                    the next level's work list and the leaf triangles' slots
+// ------------------------------------------------------------------------------------------
+static constexpr int kWideEmpty = 0x7fffffff;
+static constexpr int kWideWholeScene = 0x7ffffffe;     // the only child of the root when n <= thresh
+
+struct WideBuildView {
+    const int *left, *right, *first, *last;
+    const float4 *blo, *bhi, *tlo, *thi;
+    const uint32_t* order;                 // Morton-sorted slot -> face id
+    const float* scene_bounds;
+    int n_tris;
+    uint32_t thresh;
+};
+
+__device__ __forceinline__ float wide_area(float4 lo, float4 hi) {
+    float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return (ex * ey + ey * ez) + ez * ex;
+}
+__device__ __forceinline__ void wide_child_box(const WideBuildView& v, int ref, float4& lo, float4& hi) {
+    if (ref == kWideWholeScene) {
+        lo = make_float4(v.scene_bounds[0], v.scene_bounds[1], v.scene_bounds[2], 0.0f);
+        hi = make_float4(v.scene_bounds[3], v.scene_bounds[4], v.scene_bounds[5], 0.0f);
+    } else if (ref < 0) {
+        const uint32_t f = v.order[~ref];
+        lo = v.tlo[f]; hi = v.thi[f];
+    } else {
+        lo = v.blo[ref]; hi = v.bhi[ref];
+    }
+}
+__device__ __forceinline__ void wide_make_child(const WideBuildView& v, int c, int& ref, int& cnt, float& sa) {
+    ref = c;
+    sa = 0.0f;
+    if (c < 0) { cnt = 1; return; }
+    const int m = v.last[c] - v.first[c] + 1;
+    if ((uint32_t)m > v.thresh) { cnt = 0; sa = wide_area(v.blo[c], v.bhi[c]); }     // expandable
+    else cnt = m;
+}
+
+__global__ void k_wide_collapse(WideBuildView v, uint32_t n_level, const int* __restrict__ work, int* __restrict__ tmp_ref,
+                                int* __restrict__ tmp_cnt, uint32_t* __restrict__ cnt_int, uint32_t* __restrict__ cnt_tri) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_level) return;
+    const int r = work[i];
+    int ref[8], cnt[8];
+    float sa[8];
+    int k = 0;
+    float4 nlo, nhi;
+    if (r < 0) {
+        ref[0] = kWideWholeScene; cnt[0] = v.n_tris; sa[0] = 0.0f;
+        k = 1;
+        wide_child_box(v, kWideWholeScene, nlo, nhi);
+    } else {
+        wide_make_child(v, v.left[r], ref[0], cnt[0], sa[0]);
+        wide_make_child(v, v.right[r], ref[1], cnt[1], sa[1]);
+        k = 2;
+        nlo = v.blo[r]; nhi = v.bhi[r];
+        while (k < 8) {
+            int best = -1;
+            float best_area = 0.0f;
+            for (int j = 0; j < k; ++j) {
+                if (cnt[j] != 0) continue;
+                if (best < 0 || sa[j] > best_area) { best = j; best_area = sa[j]; }
+            }
+            if (best < 0) break;
+            const int c = ref[best];
+            for (int j = k; j > best + 1; --j) { ref[j] = ref[j - 1]; cnt[j] = cnt[j - 1]; sa[j] = sa[j - 1]; }
+            wide_make_child(v, v.left[c], ref[best], cnt[best], sa[best]);
+            wide_make_child(v, v.right[c], ref[best + 1], cnt[best + 1], sa[best + 1]);
+            ++k;
+        }
+    }
+    // greedy slot assignment: largest +-(child centre - node centre) sum first
+    const float cx = (nlo.x + nhi.x) * 0.5f, cy = (nlo.y + nhi.y) * 0.5f, cz = (nlo.z + nhi.z) * 0.5f;
+    float dx[8], dy[8], dz[8];
+    for (int j = 0; j < k; ++j) {
+        float4 lo, hi;
+        wide_child_box(v, ref[j], lo, hi);
+        dx[j] = (lo.x + hi.x) * 0.5f - cx;
+        dy[j] = (lo.y + hi.y) * 0.5f - cy;
+        dz[j] = (lo.z + hi.z) * 0.5f - cz;
+    }
+    int slot_of[8], child_in[8];
+    for (int j = 0; j < 8; ++j) { slot_of[j] = -1; child_in[j] = -1; }
+    for (int it = 0; it < k; ++it) {
+        int bj = -1, bs = -1;
+        float bc = 0.0f;
+        for (int j = 0; j < k; ++j) {
+            if (slot_of[j] >= 0) continue;
+            for (int sl = 0; sl < 8; ++sl) {
+                if (child_in[sl] >= 0) continue;
+                const float tx = (sl & 1) ? dx[j] : -dx[j], ty = (sl & 2) ? dy[j] : -dy[j], tz = (sl & 4) ? dz[j] : -dz[j];
+                const float c = (tx + ty) + tz;
+                if (bj < 0 || c > bc) { bj = j; bs = sl; bc = c; }
+            }
+        }
+        slot_of[bj] = bs;
+        child_in[bs] = bj;
+    }
+    uint32_t ni = 0, nt = 0;
+    for (int sl = 0; sl < 8; ++sl) {
+        const int j = child_in[sl];
+        tmp_ref[8 * (size_t)i + sl] = j < 0 ? kWideEmpty : ref[j];
+        tmp_cnt[8 * (size_t)i + sl] = j < 0 ? 0 : cnt[j];
+        if (j >= 0) { if (cnt[j] == 0) ++ni; else nt += (uint32_t)cnt[j]; }
+    }
+    cnt_int[i] = ni;
+    cnt_tri[i] = nt;
+}
+
+__device__ __forceinline__ int exp_of_double(double x) {        // floor(log2 x), x a positive normal double
+    return (int)((__double_as_longlong(x) >> 52) & 0x7ff) - 1023;
+}
+
+__global__ void k_wide_emit(WideBuildView v, uint32_t n_level, uint32_t level_start, uint32_t next_start, uint32_t tri_cursor,
+                            const int* __restrict__ work, const int* __restrict__ tmp_ref, const int* __restrict__ tmp_cnt,
+                            const uint32_t* __restrict__ off_int, const uint32_t* __restrict__ off_tri, uint4* __restrict__ nodes,
+                            int* __restrict__ work_next, uint32_t* __restrict__ order8, uint8_t* __restrict__ last8) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_level) return;
+    const int r = work[i];
+    float4 nlo, nhi;
+    if (r < 0) wide_child_box(v, kWideWholeScene, nlo, nhi);
+    else { nlo = v.blo[r]; nhi = v.bhi[r]; }
+    const float plo[3] = {nlo.x, nlo.y, nlo.z}, phi[3] = {nhi.x, nhi.y, nhi.z};
+    uint32_t eb[3];
+    double cell[3];
+    for (int a = 0; a < 3; ++a) {
+        const double ext = (double)phi[a] - (double)plo[a];
+        if (!(ext > 0.0)) { eb[a] = 0; cell[a] = 0.0; continue; }
+        int e = exp_of_double(ext / 255.0);
+        if (ldexp(255.0, e) < ext) e += 1;
+        int b = e + 127;
+        if (b < 1) b = 1;
+        if (b > 254) b = 254;
+        eb[a] = (uint32_t)b;
+        cell[a] = ldexp(1.0, b - 127);
+    }
+    const uint32_t child_base = next_start + off_int[i];
+    const uint32_t tri_base = tri_cursor + off_tri[i];
+    uint32_t meta[2] = {0, 0}, q[6][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    uint32_t imask = 0, n_internal = 0, tri_off = 0;
+    for (int sl = 0; sl < 8; ++sl) {
+        const int ref = tmp_ref[8 * (size_t)i + sl];
+        const int cnt = tmp_cnt[8 * (size_t)i + sl];
+        const int sh = 8 * (sl & 3), w = sl >> 2;
+        if (ref == kWideEmpty) {
+            for (int a = 0; a < 3; ++a) q[a][w] |= 255u << sh;              // inverted box: lo 255, hi 0
+            continue;
+        }
+        float4 lo, hi;
+        wide_child_box(v, ref, lo, hi);
+        const float clo[3] = {lo.x, lo.y, lo.z}, chi[3] = {hi.x, hi.y, hi.z};
+        for (int a = 0; a < 3; ++a) {
+            int ql = 0, qh = 0;
+            if (cell[a] > 0.0) {
+                const double fl = floor(((double)clo[a] - (double)plo[a]) / cell[a]);
+                const double fh = ceil(((double)chi[a] - (double)plo[a]) / cell[a]);
+                ql = fl < 0.0 ? 0 : (fl > 255.0 ? 255 : (int)fl);
+                qh = fh < 0.0 ? 0 : (fh > 255.0 ? 255 : (int)fh);
+            }
+            q[a][w] |= (uint32_t)ql << sh;
+            q[3 + a][w] |= (uint32_t)qh << sh;
+        }
+        if (cnt == 0) {
+            meta[w] |= 0x80u << sh;
+            imask |= 1u << sl;
+            work_next[off_int[i] + n_internal] = ref;
+            ++n_internal;
+        } else {
+            meta[w] |= (1u + tri_off) << sh;
+            const int first = ref == kWideWholeScene ? 0 : (ref < 0 ? ~ref : v.first[ref]);
+            for (int t = 0; t < cnt; ++t) order8[tri_base + tri_off + t] = v.order[first + t];
+            last8[tri_base + tri_off + cnt - 1] = 1;
+            tri_off += (uint32_t)cnt;
+        }
+    }
+    uint4* o = nodes + 5 * (size_t)(level_start + i);
+    o[0] = make_uint4(__float_as_uint(plo[0]), __float_as_uint(plo[1]), __float_as_uint(plo[2]),
+                      eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+    o[1] = make_uint4(child_base, tri_base, meta[0], meta[1]);
+    o[2] = make_uint4(q[0][0], q[0][1], q[1][0], q[1][1]);
+    o[3] = make_uint4(q[2][0], q[2][1], q[3][0], q[3][1]);
+    o[4] = make_uint4(q[4][0], q[4][1], q[5][0], q[5][1]);
+}
+
+// ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
 #define BUILD_CHECK(x)                                                                           \
@@ -385,9 +579,15 @@ __global__ void k_emit_tris(uint32_t n, const uint32_t* __restrict__ order, cons
     } while (0)
 
 int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face_shade, uint32_t n, uint32_t thresh_n,
-                     cudaStream_t st, float* build_ms) {
+                     int builder, cudaStream_t st, float* build_ms) {
     int rc = CRT_OK;
+    const bool wide = builder == CRT_BUILDER_LBVH8;
     if (thresh_n < 1) thresh_n = 1;
+    if (wide && thresh_n > 15) thresh_n = 15;            // 7-bit leaf offsets inside a wide node
+    uint4* wnodes = nullptr;
+    int *work0 = nullptr, *work1 = nullptr, *tmp_ref = nullptr, *tmp_cnt = nullptr;
+    uint32_t *cnt_int = nullptr, *cnt_tri = nullptr, *off_int = nullptr, *off_tri = nullptr, *order8 = nullptr, *d_tot2 = nullptr;
+    uint8_t* last8 = nullptr;
     const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
     const int nb = (int)((n + 255) / 256);
     float4 *tlo = nullptr, *thi = nullptr, *blo = nullptr, *bhi = nullptr;
@@ -402,6 +602,7 @@ int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face
 
     ds.n_tris = n;
     ds.n_nodes = 0;
+    ds.wide = wide;
     if (n == 0) { if (build_ms) *build_ms = 0; return CRT_OK; }
 
     BUILD_CHECK(cudaEventCreate(&ev0));
@@ -445,8 +646,10 @@ int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face
 
     if (n <= thresh_n) {
         n_kept = 1;
-        BUILD_CHECK(cudaMalloc(&ds.nodes, sizeof(float4) * 4));
-        k_emit_single_leaf<<<1, 1, 0, st>>>((int)n, bounds, ds.nodes, ds.last);
+        if (!wide) {
+            BUILD_CHECK(cudaMalloc(&ds.nodes, sizeof(float4) * 4));
+            k_emit_single_leaf<<<1, 1, 0, st>>>((int)n, bounds, ds.nodes, ds.last);
+        }
     } else {
         const uint32_t ni = n - 1;
         const int nbi = (int)((ni + 255) / 256);
@@ -468,9 +671,60 @@ int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face
         BUILD_CHECK(exclusive_scan_u32(keep, rank, ni, scratch, d_total, st));
         BUILD_CHECK(cudaMemcpyAsync(&n_kept, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         BUILD_CHECK(cudaStreamSynchronize(st));
-        BUILD_CHECK(cudaMalloc(&ds.nodes, sizeof(float4) * 4 * (size_t)n_kept));
-        k_emit_nodes<<<nbi, 256, 0, st>>>((int)ni, keep, rank, left, right, first, last, ds.order, tlo, thi, blo, bhi, ds.nodes,
-                                          ds.last);
+        if (!wide) {
+            BUILD_CHECK(cudaMalloc(&ds.nodes, sizeof(float4) * 4 * (size_t)n_kept));
+            k_emit_nodes<<<nbi, 256, 0, st>>>((int)ni, keep, rank, left, right, first, last, ds.order, tlo, thi, blo, bhi, ds.nodes,
+                                              ds.last);
+        }
+    }
+    if (wide) {
+        // breadth-first collapse into 80-byte nodes; at most one wide node per expandable radix node
+        const size_t cap = std::max<uint32_t>(n_kept, 1);
+        BUILD_CHECK(cudaMalloc(&wnodes, sizeof(uint4) * 5 * cap));
+        BUILD_CHECK(cudaMalloc(&work0, sizeof(int) * cap));
+        BUILD_CHECK(cudaMalloc(&work1, sizeof(int) * cap));
+        BUILD_CHECK(cudaMalloc(&tmp_ref, sizeof(int) * 8 * cap));
+        BUILD_CHECK(cudaMalloc(&tmp_cnt, sizeof(int) * 8 * cap));
+        BUILD_CHECK(cudaMalloc(&cnt_int, sizeof(uint32_t) * cap));
+        BUILD_CHECK(cudaMalloc(&cnt_tri, sizeof(uint32_t) * cap));
+        BUILD_CHECK(cudaMalloc(&off_int, sizeof(uint32_t) * cap));
+        BUILD_CHECK(cudaMalloc(&off_tri, sizeof(uint32_t) * cap));
+        BUILD_CHECK(cudaMalloc(&d_tot2, sizeof(uint32_t) * 2));
+        BUILD_CHECK(cudaMalloc(&order8, sizeof(uint32_t) * n));
+        BUILD_CHECK(cudaMalloc(&last8, n));
+        BUILD_CHECK(cudaMemsetAsync(last8, 0, n, st));
+        WideBuildView v;
+        v.left = left; v.right = right; v.first = first; v.last = last; v.blo = blo; v.bhi = bhi; v.tlo = tlo; v.thi = thi;
+        v.order = ds.order; v.scene_bounds = bounds; v.n_tris = (int)n; v.thresh = thresh_n;
+        const int root = n <= thresh_n ? -1 : 0;
+        BUILD_CHECK(cudaMemcpyAsync(work0, &root, sizeof(int), cudaMemcpyHostToDevice, st));
+        uint32_t level_start = 0, n_level = 1, tri_cursor = 0, levels = 0;
+        int *wcur = work0, *wnext = work1;
+        while (n_level > 0) {
+            // the traversal stack holds one entry per level (crt_wide.cuh kWideStack)
+            if (++levels > (uint32_t)kWideStack) { set_error("wide BVH: tree deeper than the traversal stack"); rc = CRT_ERR_STATE; goto done; }
+            if ((size_t)level_start + n_level > cap) { set_error("wide BVH: node bound exceeded"); rc = CRT_ERR_STATE; goto done; }
+            const int nbl = (int)((n_level + 127) / 128);
+            k_wide_collapse<<<nbl, 128, 0, st>>>(v, n_level, wcur, tmp_ref, tmp_cnt, cnt_int, cnt_tri);
+            BUILD_CHECK(exclusive_scan_u32(cnt_int, off_int, n_level, scratch, d_tot2, st));
+            BUILD_CHECK(exclusive_scan_u32(cnt_tri, off_tri, n_level, scratch, d_tot2 + 1, st));
+            uint32_t tot[2] = {0, 0};
+            BUILD_CHECK(cudaMemcpyAsync(tot, d_tot2, sizeof(tot), cudaMemcpyDeviceToHost, st));
+            BUILD_CHECK(cudaStreamSynchronize(st));
+            k_wide_emit<<<nbl, 128, 0, st>>>(v, n_level, level_start, level_start + n_level, tri_cursor, wcur, tmp_ref, tmp_cnt, off_int,
+                                             off_tri, wnodes, wnext, order8, last8);
+            BUILD_CHECK(cudaGetLastError());
+            level_start += n_level;
+            n_level = tot[0];
+            tri_cursor += tot[1];
+            std::swap(wcur, wnext);
+        }
+        if (tri_cursor != n) { set_error("wide BVH: triangle count mismatch"); rc = CRT_ERR_STATE; goto done; }
+        n_kept = level_start;
+        BUILD_CHECK(cudaMalloc(&ds.nodes, sizeof(uint4) * 5 * (size_t)n_kept));
+        BUILD_CHECK(cudaMemcpyAsync(ds.nodes, wnodes, sizeof(uint4) * 5 * (size_t)n_kept, cudaMemcpyDeviceToDevice, st));
+        std::swap(ds.order, order8);
+        std::swap(ds.last, last8);
     }
     k_emit_tris<<<nb, 256, 0, st>>>(n, ds.order, ds.last, d_verts, d_face_shade, ds.tri_geom, ds.tri_shade);
     BUILD_CHECK(cudaGetLastError());
@@ -485,6 +739,8 @@ done:
     cudaFree(keys0); cudaFree(keys1); cudaFree(vals0); cudaFree(vals1); cudaFree(ghist); cudaFree(scratch);
     cudaFree(flags); cudaFree(keep); cudaFree(rank); cudaFree(d_total);
     cudaFree(left); cudaFree(right); cudaFree(first); cudaFree(last); cudaFree(pnode); cudaFree(pleaf);
+    cudaFree(wnodes); cudaFree(work0); cudaFree(work1); cudaFree(tmp_ref); cudaFree(tmp_cnt); cudaFree(cnt_int); cudaFree(cnt_tri);
+    cudaFree(off_int); cudaFree(off_tri); cudaFree(order8); cudaFree(last8); cudaFree(d_tot2);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     return rc;

@@ -23,7 +23,8 @@ int cuda_fail(cudaError_t e, const char* what);
 struct DeviceScene {
     int device = 0;
     uint32_t n_tris = 0, n_nodes = 0, n_mats = 0, n_lights = 0, n_light_tris = 0;
-    float4* nodes = nullptr;        // n_nodes * 4
+    bool wide = false;              // nodes are 80-byte 8-wide compressed nodes (5 x 16 B) instead of 64-byte pairs
+    float4* nodes = nullptr;        // n_nodes * 4 (pairs) or n_nodes * 5 (wide)
     float4* tri_geom = nullptr;     // n_tris * 3, BVH slot order
     float4* tri_shade = nullptr;    // n_tris, BVH slot order
     uint32_t* order = nullptr;      // slot -> face id
@@ -46,10 +47,10 @@ struct DeviceScene {
 
 // GPU BVH build; d_verts: n*9 floats (face order), d_face_shade: n float4 (normal, mat bits).
 int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face_shade, uint32_t n, uint32_t thresh_n,
-                     cudaStream_t st, float* build_ms);
+                     int builder, cudaStream_t st, float* build_ms);
 
 // Uploads materials and lights, builds the BVH. Leaves the device selected.
-int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene& ds, float* build_ms);
+int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device, DeviceScene& ds, float* build_ms);
 
 // Ray batches (device pointers). rays: n * 2 float4 {o,tmax}{d,0}.
 int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,

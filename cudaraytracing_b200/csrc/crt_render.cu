@@ -9,11 +9,16 @@
 // dimension), and an order-independent fixed-point accumulation buffer.
 // The estimator arithmetic mirrors oracle/orc_render.cpp operation by operation (-fmad=false).
 #include "crt_gpu.h"
+#include "crt_wide.cuh"
 
 // Traversal scheduling: 2 = persistent lanes + per-warp leaf queue (default), 0 = while-while, 1 = if-if
 // (crt_device.cuh; measured alternatives in DESIGN.md "Traversal scheduling").
 #ifndef CRT_STRAT
 #define CRT_STRAT 2
+#endif
+// Same for the 8-wide nodes (crt_wide.cuh): 2 = leaf queue, 0 = while-while
+#ifndef CRT_WSTRAT
+#define CRT_WSTRAT 2
 #endif
 
 #ifndef CRT_MINB
@@ -43,7 +48,7 @@ void DeviceScene::release() {
 
 static inline float bits_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene& ds, float* build_ms) {
+int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device, DeviceScene& ds, float* build_ms) {
     CRT_CUDA(cudaSetDevice(device));
     ds.release();
     ds.device = device;
@@ -112,20 +117,34 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int device, DeviceScene
         cudaMemcpy(d_verts, hs.verts.data(), sizeof(float) * 9 * n, cudaMemcpyHostToDevice);
         cudaMemcpy(d_shade, shade.data(), sizeof(float4) * n, cudaMemcpyHostToDevice);
     }
-    rc = build_bvh_device(ds, d_verts, d_shade, (uint32_t)n, thresh_n, 0, build_ms);
+    rc = build_bvh_device(ds, d_verts, d_shade, (uint32_t)n, thresh_n, builder, 0, build_ms);
     cudaFree(d_verts);
     cudaFree(d_shade);
     return rc;
 }
 
 // =============================================================================================
+// node-layout dispatch: WIDE = false: 64-byte child-pair nodes, true: 80-byte 8-wide compressed nodes
+// =============================================================================================
+template <int MODE, bool WIDE, typename Load, typename Done>
+CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    if (WIDE) trace_rays_persistent_wide<MODE, CRT_WSTRAT>(sc, n, fetch, load, done);
+    else trace_rays_persistent<MODE, CRT_STRAT>(sc, n, fetch, load, done);
+}
+template <int MODE, bool WIDE>
+CRT_DEV HitRec trace_one(const SceneView& sc, V3 o, V3 d, float tmax) {
+    if (WIDE) return traverse_wide<MODE>(sc, o, d, tmax);
+    return traverse<MODE>(sc, o, d, tmax);
+}
+
+// =============================================================================================
 // ray batches
 // =============================================================================================
-template <int MODE>
+template <int MODE, bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_trace_batch(SceneView sc, const float4* __restrict__ rays, uint32_t n,
                                                      float* __restrict__ t_out, int* __restrict__ face_out,
                                                      uint32_t* __restrict__ fetch) {
-    trace_rays_persistent<MODE, CRT_STRAT>(
+    trace_queue<MODE, WIDE>(
         sc, n, fetch,
         [&](uint32_t i, V3& o, V3& d, float& tmax) {
             const float4 ro = __ldg(rays + 2 * (size_t)i), rd = __ldg(rays + 2 * (size_t)i + 1);
@@ -156,7 +175,8 @@ int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, i
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0>, 128, 0);
+    if (ds.wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0, true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0, false>, 128, 0);
     const int blocks = num_sms() * std::max(occ, 1);
     const uint64_t chunk = 1ull << 30;                   // queue indices are 32-bit
     float ms_total = 0;
@@ -165,10 +185,15 @@ int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, i
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, n - off);
         cudaMemsetAsync(fetch, 0, sizeof(uint32_t), st);
         cudaEventRecord(a, st);
-        if (mode == CRT_RAY_CLOSEST)
-            k_trace_batch<0><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, d_t ? d_t + off : nullptr, d_face ? d_face + off : nullptr, fetch);
-        else
-            k_trace_batch<1><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, d_t ? d_t + off : nullptr, d_face ? d_face + off : nullptr, fetch);
+        float* t_o = d_t ? d_t + off : nullptr;
+        int* f_o = d_face ? d_face + off : nullptr;
+        if (mode == CRT_RAY_CLOSEST) {
+            if (ds.wide) k_trace_batch<0, true><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, t_o, f_o, fetch);
+            else k_trace_batch<0, false><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, t_o, f_o, fetch);
+        } else {
+            if (ds.wide) k_trace_batch<1, true><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, t_o, f_o, fetch);
+            else k_trace_batch<1, false><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, t_o, f_o, fetch);
+        }
         cudaEventRecord(b, st);
         e = cudaStreamSynchronize(st);
         float ms = 0;
@@ -322,21 +347,23 @@ __global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c
     }
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_extend(SceneView sc, Counters* c, const float4* __restrict__ q_o,
                                                 const float4* __restrict__ q_d, float* __restrict__ hit_t,
                                                 int* __restrict__ hit_slot) {
-    trace_rays_persistent<0, CRT_STRAT>(
+    trace_queue<0, WIDE>(
         sc, c->n_cur, &c->fetch_extend,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
         [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });
 }
 
 // SPECULAR probe rays (reference Render.cuh:303): traced only when the continuation ray hit.
+template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_probe(SceneView sc, Counters* c, const uint32_t* __restrict__ list,
                                                const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
                                                const int* __restrict__ hit_slot, int* __restrict__ pr_hit) {
     unsigned long long traced = 0;
-    trace_rays_persistent<0, CRT_STRAT>(
+    trace_queue<0, WIDE>(
         sc, c->n_probe_cur, &c->fetch_probe,
         [&](uint32_t k, V3& o, V3& d, float& tmax) {
             const uint32_t i = list[k];
@@ -663,7 +690,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneView sc, Counters* c, Render
 // launches per bounce for ever smaller wavefronts. Same per-vertex statement as above, same Philox
 // keys and the same order-independent accumulation, so the image does not depend on where the
 // switch happens.
-template <int EST>
+template <int EST, bool WIDE>
 __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderParamsDev p, const float4* __restrict__ q_o,
                                               const float4* __restrict__ q_d, const float4* __restrict__ q_T,
                                               const float* __restrict__ q_pdf, const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
@@ -683,11 +710,11 @@ __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderP
         pr.o = pr.d = pr.w = mk3(0.0f, 0.0f, 0.0f);
         if (EST == CRT_ESTIMATOR_COMPAT && (ps.meta & kFlagProbe)) { pr.o = mk3(pr_o[i]); pr.d = mk3(pr_d[i]); pr.w = mk3(pr_w[i]); }
         for (;;) {
-            const HitRec h = traverse<0>(sc, ps.o, ps.d, FLT_MAX);
+            const HitRec h = trace_one<0, WIDE>(sc, ps.o, ps.d, FLT_MAX);
             n_ext++;
             if (h.slot < 0) break;
             if (EST == CRT_ESTIMATOR_COMPAT && (ps.meta & kFlagProbe)) {
-                const HitRec ph = traverse<0>(sc, pr.o, pr.d, FLT_MAX);
+                const HitRec ph = trace_one<0, WIDE>(sc, pr.o, pr.d, FLT_MAX);
                 n_pr++;
                 probe_resolve(sc, ph.slot, pr.w, ps.pixel, accum);
             }
@@ -696,7 +723,7 @@ __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderP
             const uint32_t pixel = ps.pixel;
             auto shadow = [&](bool needs_trace, V3 pos, float tmax, V3 dir, V3 contrib) {
                 if (!needs_trace) return;
-                const HitRec b = traverse<1>(sc, pos, dir, tmax);
+                const HitRec b = trace_one<1, WIDE>(sc, pos, dir, tmax);
                 n_sh++;
                 if (b.slot < 0) accum_add(accum, pixel, contrib);
             };
@@ -721,10 +748,11 @@ __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderP
 }
 
 // Shadow rays: the decision of blocked() (reference Render.cuh:19-27) with an any-hit traversal.
+template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
                                                 const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
                                                 long long* __restrict__ accum) {
-    trace_rays_persistent<1, CRT_STRAT>(
+    trace_queue<1, WIDE>(
         sc, c->n_shadow, &c->fetch_shadow,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { const float4 a = sh_o[i]; o = mk3(a); tmax = a.w; d = mk3(sh_d[i]); return true; },
         [&](uint32_t i, const HitRec& h) {
@@ -778,10 +806,12 @@ int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wav
     CRT_CUDA(cudaEventCreate(&w->ev_begin));
     CRT_CUDA(cudaEventCreate(&w->ev_end));
     int occ = 0;
-    CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, 128, 0));
+    if (ds.wide) CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<true>, 128, 0));
+    else CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, 128, 0));
     w->grid_trace = num_sms() * std::max(occ, 1);
     w->grid_shade = num_sms() * 8;
-    CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tail<CRT_ESTIMATOR_MIS>, 128, 0));
+    if (ds.wide) CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_tail<CRT_ESTIMATOR_MIS, true>), 128, 0));
+    else CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_tail<CRT_ESTIMATOR_MIS, false>), 128, 0));
     w->grid_tail = num_sms() * std::max(occ, 1);
     *out = w;
     return CRT_OK;
@@ -879,6 +909,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     CRT_CUDA(cudaMemsetAsync(w->accum, 0, sizeof(long long) * 3 * npix, st));
     CRT_CUDA(cudaMemcpyAsync(w->counters, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     const SceneView sv = ds.view();
+    const bool wide = ds.wide;
     uint64_t launches = 0;
     float ms_stage[5] = {0, 0, 0, 0, 0};
     cudaEvent_t se[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -895,10 +926,12 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         if (rs.stage_timing) cudaEventRecord(se[0], st);
         k_generate<<<w->grid_shade, 256, 0, st>>>(w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], mis ? w->q_pdf[cur] : nullptr);
         if (rs.stage_timing) cudaEventRecord(se[1], st);
-        k_extend<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->q_o[cur], w->q_d[cur], w->hit_t, w->hit_slot);
+        if (wide) k_extend<true><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->q_o[cur], w->q_d[cur], w->hit_t, w->hit_slot);
+        else k_extend<false><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->q_o[cur], w->q_d[cur], w->hit_t, w->hit_slot);
         launches += 3;
         if (w->has_probe && !mis) {
-            k_probe<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->pr_list[cur], w->pr_o[cur], w->pr_d[cur], w->hit_slot, w->pr_hit);
+            if (wide) k_probe<true><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->pr_list[cur], w->pr_o[cur], w->pr_d[cur], w->hit_slot, w->pr_hit);
+            else k_probe<false><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->pr_list[cur], w->pr_o[cur], w->pr_d[cur], w->hit_slot, w->pr_hit);
             launches++;
         }
         if (rs.stage_timing) cudaEventRecord(se[2], st);
@@ -916,17 +949,18 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         exp_sort(ds, w->counters, 1, w->sh_o, w->sh_d, w->sh_c, w->shadow_cap, st);
 #endif
         if (rs.stage_timing) cudaEventRecord(se[3], st);
-        k_shadow<<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum);
+        if (wide) k_shadow<true><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum);
+        else k_shadow<false><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum);
         if (rs.stage_timing) cudaEventRecord(se[4], st);
 #ifdef CRT_EXP_SORT
         exp_sort(ds, w->counters, 0, w->q_o[nxt], w->q_d[nxt], w->q_T[nxt], w->pool, st);
 #endif
-        if (mis)
-            k_tail<CRT_ESTIMATOR_MIS><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
-                                                                     w->pr_o[cur], w->pr_d[cur], w->pr_w[cur], w->accum);
-        else
-            k_tail<CRT_ESTIMATOR_COMPAT><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
-                                                                        w->pr_o[cur], w->pr_d[cur], w->pr_w[cur], w->accum);
+#define CRT_TAIL_LAUNCH(EST, W)                                                                                              \
+    k_tail<EST, W><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur], w->pr_o[cur], \
+                                                 w->pr_d[cur], w->pr_w[cur], w->accum)
+        if (mis) { if (wide) CRT_TAIL_LAUNCH(CRT_ESTIMATOR_MIS, true); else CRT_TAIL_LAUNCH(CRT_ESTIMATOR_MIS, false); }
+        else { if (wide) CRT_TAIL_LAUNCH(CRT_ESTIMATOR_COMPAT, true); else CRT_TAIL_LAUNCH(CRT_ESTIMATOR_COMPAT, false); }
+#undef CRT_TAIL_LAUNCH
         launches += 3;
         if (rs.stage_timing) {
             cudaEventRecord(se[5], st);

@@ -1,0 +1,415 @@
+// crt_wide.cuh — traversal of the 8-wide compressed BVH (builder CRT_BUILDER_LBVH8).
+//
+// Node layout (80 bytes = five 16-byte words; built by crt_bvh_build.cu, stated on the CPU by
+// oracle/orc_bvh.cpp build_wide8_bvh, byte-identical):
+//   w0: origin p (3 floats), {ex, ey, ez, imask} bytes      scale_k = float with exponent field e_k
+//   w1: child_base, tri_base, meta[0..3], meta[4..7]        meta: 0 empty, 0x80 node, 1 + offset leaf
+//   w2: qlo_x[0..7], qlo_y[0..7]   w3: qlo_z[0..7], qhi_x[0..7]   w4: qhi_y[0..7], qhi_z[0..7]
+// child box k = p + q * scale per axis; the internal child in slot s is node
+// child_base + popcount(imask below s); a leaf child starts at triangle slot tri_base + offset and
+// runs to the terminator bit of tri_geom.
+//
+// Per-ray rule = oracle/orc_bvh.cpp wide8_intersect (same visits in the same order, so the oracle's
+// node/triangle counts are the algorithmic ones): conservative quantised slabs, children visited
+// front to back by slot ^ octant (descending), the leaf children of a node tested before descending,
+// one stack entry per node with hit children left. The (t, face) result equals the pair-node BVH's
+// and brute force's: conservative boxes make the closest hit independent of the tree.
+#pragma once
+#include "crt_device.cuh"
+
+namespace crt {
+
+static constexpr int kWideStack = 48;      // one entry per wide-tree level at most; the builder refuses deeper trees
+
+CRT_DEV float wide_byte(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+
+struct WideStep {
+    uint32_t node_hits, leaf_hits;     // priority space: bit (slot ^ octant), visited in descending order
+    uint32_t child_base, tri_base, meta_lo, meta_hi, imask;
+};
+
+// Box tests of the 8 children of node ni against the ray (o, inv); lim = 1.0001 * current t limit.
+CRT_DEV WideStep wide_node_test(const uint4* __restrict__ nodes, uint32_t ni, V3 o, V3 inv, uint32_t oinv, float lim) {
+    const uint4* p = nodes + 5 * (size_t)ni;
+    const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+    const uint32_t ew = w0.w;
+    const float sx = __uint_as_float((ew & 0xffu) << 23), sy = __uint_as_float(((ew >> 8) & 0xffu) << 23),
+                sz = __uint_as_float(((ew >> 16) & 0xffu) << 23);
+    const float ax = (__uint_as_float(w0.x) - o.x) * inv.x, ay = (__uint_as_float(w0.y) - o.y) * inv.y,
+                az = (__uint_as_float(w0.z) - o.z) * inv.z;
+    const float bx = sx * inv.x, by = sy * inv.y, bz = sz * inv.z;
+    float fax = fabsf(ax), fay = fabsf(ay), faz = fabsf(az);
+    if (!(fax <= FLT_MAX)) fax = 0.0f;
+    if (!(fay <= FLT_MAX)) fay = 0.0f;
+    if (!(faz <= FLT_MAX)) faz = 0.0f;
+    const float pad = fmaxf(fmaxf(fax, fay), faz) * 4.76837158203125e-07f;        // 2^-21
+    // near planes: the low ones when the direction component is non-negative
+    const bool px = oinv & 1u, py = oinv & 2u, pz = oinv & 4u;
+    const uint32_t nx[2] = {px ? w2.x : w3.z, px ? w2.y : w3.w}, fx[2] = {px ? w3.z : w2.x, px ? w3.w : w2.y};
+    const uint32_t ny[2] = {py ? w2.z : w4.x, py ? w2.w : w4.y}, fy[2] = {py ? w4.x : w2.z, py ? w4.y : w2.w};
+    const uint32_t nz[2] = {pz ? w3.x : w4.z, pz ? w3.y : w4.w}, fz[2] = {pz ? w4.z : w3.x, pz ? w4.w : w3.y};
+    WideStep r;
+    r.node_hits = 0; r.leaf_hits = 0;
+    r.child_base = w1.x; r.tri_base = w1.y; r.meta_lo = w1.z; r.meta_hi = w1.w; r.imask = ew >> 24;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int w = c >> 2, k = c & 3;
+        const uint32_t m = ((w ? w1.w : w1.z) >> (8 * k)) & 0xffu;
+        const float tnx = fmaf(wide_byte(nx[w], k), bx, ax), tfx = fmaf(wide_byte(fx[w], k), bx, ax);
+        const float tny = fmaf(wide_byte(ny[w], k), by, ay), tfy = fmaf(wide_byte(fy[w], k), by, ay);
+        const float tnz = fmaf(wide_byte(nz[w], k), bz, az), tfz = fmaf(wide_byte(fz[w], k), bz, az);
+        const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+        const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, lim));
+        if (m != 0u && tmin <= fmaf(tmax, 1.0000004f, pad)) {
+            const uint32_t bit = 1u << ((uint32_t)c ^ oinv);
+            if (m & 0x80u) r.node_hits |= bit; else r.leaf_hits |= bit;
+        }
+    }
+    return r;
+}
+
+CRT_DEV uint32_t wide_octant(V3 inv) { return (inv.x < 0.0f ? 0u : 1u) | (inv.y < 0.0f ? 0u : 2u) | (inv.z < 0.0f ? 0u : 4u); }
+// first triangle slot of the leaf child with priority bit lp
+CRT_DEV int wide_leaf_slot(const WideStep& s, int lp, uint32_t oinv) {
+    const uint32_t c = (uint32_t)lp ^ oinv;
+    const uint32_t m = ((c & 4u ? s.meta_hi : s.meta_lo) >> (8u * (c & 3u))) & 0xffu;
+    return (int)(s.tri_base + m - 1u);
+}
+
+// Sequential rule, one ray per call (tail kernel; statement: oracle wide8_intersect).
+template <int MODE>
+CRT_DEV HitRec traverse_wide(const SceneView& sc, V3 o, V3 d, float tmax) {
+    HitRec best;
+    best.t = FLT_MAX; best.slot = -1; best.face = -1;
+    if (sc.n_nodes == 0) return best;
+    const uint4* nodes = (const uint4*)sc.nodes;
+    const V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const uint32_t oinv = wide_octant(inv);
+    float tlimit = MODE == 0 ? FLT_MAX : tmax;
+    uint2 stack[kWideStack];
+    int sp = 0;
+    uint32_t g_base = 0, g_bits = (1u << 8) | (1u << oinv);      // imask << 8 | hit mask; the root as slot 0 of a virtual parent
+    for (;;) {
+        if ((g_bits & 0xffu) == 0u) {
+            if (sp == 0) break;
+            const uint2 e = stack[--sp];
+            g_base = e.x; g_bits = e.y;
+        }
+        const int pr = 31 - __clz((int)(g_bits & 0xffu));
+        g_bits &= ~(1u << pr);
+        const uint32_t sl = (uint32_t)pr ^ oinv;
+        const uint32_t ni = g_base + (uint32_t)__popc((g_bits >> 8) & ((1u << sl) - 1u));
+        WideStep s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f);
+        while (s.leaf_hits) {
+            const int lp = 31 - __clz((int)s.leaf_hits);
+            s.leaf_hits &= ~(1u << lp);
+            int slot = wide_leaf_slot(s, lp, oinv);
+            for (;; ++slot) {
+                const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
+                const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
+                const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
+                const uint32_t fw = __float_as_uint(a.w);
+                const int face = (int)(fw & ~kLastBit);
+                float t;
+                if (tri_test(mk3(a), mk3(b), mk3(c), o, d, &t) && t > kEps) {
+                    if (MODE == 0) {
+                        if (t < best.t || (t == best.t && face < best.face)) {
+                            best.t = t; best.slot = slot; best.face = face;
+                            tlimit = t;
+                        }
+                    } else if (tmax - t > kEps) {
+                        best.t = t; best.slot = slot; best.face = face;
+                        return best;
+                    }
+                }
+                if (fw & kLastBit) break;
+            }
+        }
+        if (s.node_hits) {
+            if (g_bits & 0xffu) stack[sp++] = make_uint2(g_base, g_bits);
+            g_base = s.child_base;
+            g_bits = (s.imask << 8) | s.node_hits;
+        }
+    }
+    return best;
+}
+
+// ---- persistent lanes, while-while (WSTRAT 0): every lane walks wide nodes until one of them has leaf
+// children hit, then the lanes test those leaves. Same per-ray order as traverse_wide.
+template <int MODE, typename Load, typename Done>
+CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    const uint4* nodes = (const uint4*)sc.nodes;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint2 stack[kWideStack];
+    int sp = 0;
+    uint32_t g_base = 0, g_bits = 0, oinv = 0;
+    uint32_t idx = 0;
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0);
+    float tmax = 0.0f, tlimit = 0.0f;
+    HitRec best;
+    best.t = FLT_MAX; best.slot = -1; best.face = -1;
+    WideStep s;
+    s.node_hits = s.leaf_hits = s.child_base = s.tri_base = s.meta_lo = s.meta_hi = s.imask = 0;
+    bool have = false, exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (idle) {
+            const int n_idle = __popc(idle);
+            if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!have) {
+                    const uint32_t i = base + __popc(idle & lt_mask);
+                    if (i < n) {
+                        idx = i;
+                        const bool live = load(i, o, d, tmax);
+                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        oinv = wide_octant(inv);
+                        tlimit = MODE == 0 ? FLT_MAX : tmax;
+                        best.t = FLT_MAX; best.slot = -1; best.face = -1;
+                        sp = 0;
+                        g_base = 0;
+                        g_bits = (live && sc.n_nodes) ? ((1u << 8) | (1u << oinv)) : 0u;
+                        s.leaf_hits = 0;
+                        have = true;
+                    }
+                }
+                if (base + (uint32_t)n_idle >= n) exhausted = true;
+            }
+            if (!__any_sync(0xffffffffu, have)) {
+                if (exhausted) break;
+                continue;
+            }
+        }
+        if (have) {
+            while (s.leaf_hits == 0u) {
+                if ((g_bits & 0xffu) == 0u) {
+                    if (sp == 0) break;
+                    const uint2 e = stack[--sp];
+                    g_base = e.x; g_bits = e.y;
+                }
+                const int pr = 31 - __clz((int)(g_bits & 0xffu));
+                g_bits &= ~(1u << pr);
+                const uint32_t sl = (uint32_t)pr ^ oinv;
+                const uint32_t ni = g_base + (uint32_t)__popc((g_bits >> 8) & ((1u << sl) - 1u));
+                s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f);
+                if (s.node_hits) {
+                    if (g_bits & 0xffu) stack[sp++] = make_uint2(g_base, g_bits);
+                    g_base = s.child_base;
+                    g_bits = (s.imask << 8) | s.node_hits;
+                }
+            }
+            bool stop = false;
+            while (s.leaf_hits) {
+                const int lp = 31 - __clz((int)s.leaf_hits);
+                s.leaf_hits &= ~(1u << lp);
+                int slot = wide_leaf_slot(s, lp, oinv);
+                for (;; ++slot) {
+                    const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
+                    const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
+                    const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
+                    const uint32_t fw = __float_as_uint(a.w);
+                    const int face = (int)(fw & ~kLastBit);
+                    float t;
+                    if (tri_test(mk3(a), mk3(b), mk3(c), o, d, &t) && t > kEps) {
+                        if (MODE == 0) {
+                            if (t < best.t || (t == best.t && face < best.face)) {
+                                best.t = t; best.slot = slot; best.face = face;
+                                tlimit = t;
+                            }
+                        } else if (tmax - t > kEps) {
+                            best.t = t; best.slot = slot; best.face = face;
+                            stop = true;
+                            break;
+                        }
+                    }
+                    if (fw & kLastBit) break;
+                }
+                if (stop) break;
+            }
+            if (stop) { s.leaf_hits = 0; g_bits = 0; sp = 0; }
+            if (s.leaf_hits == 0u && (g_bits & 0xffu) == 0u && sp == 0) {
+                done(idx, best);
+                have = false;
+            }
+        }
+    }
+}
+
+// ---- persistent lanes + per-warp leaf queue (WSTRAT 2), the wide-node version of
+// trace_persistent_queue (crt_device.cuh): the leaf children hit by a node step are appended to a queue
+// in shared memory and the lane goes on with its next node; when kWQFlush leaves are queued (or no lane
+// has a node left) the whole warp tests them, one entry per lane; owners' best hits are combined with a
+// 64-bit shared atomicMin on (t bits, face id). Lanes walk with the t-limit of the last flush.
+#ifndef CRT_WQFLUSH
+#define CRT_WQFLUSH 24
+#endif
+#ifndef CRT_WQSTEPS
+#define CRT_WQSTEPS 2
+#endif
+static constexpr int kWQFlush = CRT_WQFLUSH;
+static constexpr int kWQSteps = CRT_WQSTEPS;
+static constexpr int kWQCap = kWQFlush + 32 * 8 * kWQSteps;
+struct WarpLeafQueueW {
+    float ox[32], oy[32], oz[32], dx[32], dy[32], dz[32], tmax[32];
+    unsigned long long best[32];
+    int best_slot[32];
+    int q_slot[kWQCap];
+    unsigned char q_lane[kWQCap];
+    int count;
+};
+
+template <int MODE, typename Load, typename Done>
+CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    __shared__ WarpLeafQueueW s_wq[4];                     // launched with 128 threads per block
+    WarpLeafQueueW& q = s_wq[threadIdx.x >> 5];
+    const uint4* nodes = (const uint4*)sc.nodes;
+    const unsigned kFull = 0xffffffffu;
+    const unsigned long long kNoHit = ((unsigned long long)0x7f7fffffu << 32) | 0x7fffffffull;   // t = FLT_MAX
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint2 stack[kWideStack];
+    int sp = 0;
+    uint32_t g_base = 0, g_bits = 0, oinv = 0;
+    uint32_t idx = 0;
+    V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
+    float tlimit = 0.0f;
+    int pending = 0;
+    bool have = false, exhausted = false;
+    if (lane == 0) q.count = 0;
+    __syncwarp();
+    for (;;) {
+        // A. node steps; leaf children go to the queue
+#pragma unroll
+        for (int r = 0; r < kWQSteps; ++r) {
+            if ((g_bits & 0xffu) == 0u && sp > 0) {
+                const uint2 e = stack[--sp];
+                g_base = e.x; g_bits = e.y;
+            }
+            if (g_bits & 0xffu) {
+                const int pr = 31 - __clz((int)(g_bits & 0xffu));
+                g_bits &= ~(1u << pr);
+                const uint32_t sl = (uint32_t)pr ^ oinv;
+                const uint32_t ni = g_base + (uint32_t)__popc((g_bits >> 8) & ((1u << sl) - 1u));
+                WideStep s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f);
+                if (s.leaf_hits) {
+                    const int cnt = __popc(s.leaf_hits);
+                    int pos = atomicAdd(&q.count, cnt);
+                    pending += cnt;
+                    while (s.leaf_hits) {
+                        const int lp = 31 - __clz((int)s.leaf_hits);
+                        s.leaf_hits &= ~(1u << lp);
+                        q.q_slot[pos] = wide_leaf_slot(s, lp, oinv);
+                        q.q_lane[pos] = (unsigned char)lane;
+                        ++pos;
+                    }
+                }
+                if (s.node_hits) {
+                    if (g_bits & 0xffu) stack[sp++] = make_uint2(g_base, g_bits);
+                    g_base = s.child_base;
+                    g_bits = (s.imask << 8) | s.node_hits;
+                }
+            }
+        }
+        // B. flush the leaf queue when it is full enough, or when no lane has a node in hand
+        const unsigned walking = __ballot_sync(kFull, (g_bits & 0xffu) != 0u || sp > 0);
+        __syncwarp();
+        const int q_count = q.count;
+        if (q_count >= kWQFlush || (walking == 0 && q_count > 0)) {
+            for (int base = 0; base < q_count; base += 32) {
+                const int k = base + lane;
+                unsigned long long mykey = kNoHit;
+                int myslot = -1, owner = 0;
+                if (k < q_count) {
+                    owner = q.q_lane[k];
+                    int slot = q.q_slot[k];
+                    const V3 ro = mk3(q.ox[owner], q.oy[owner], q.oz[owner]), rd = mk3(q.dx[owner], q.dy[owner], q.dz[owner]);
+                    const float rtmax = q.tmax[owner];
+                    for (;; ++slot) {
+                        const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
+                        const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
+                        const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
+                        const uint32_t fw = __float_as_uint(a.w);
+                        float t;
+                        if (tri_test(mk3(a), mk3(b), mk3(c), ro, rd, &t) && t > kEps && (MODE == 0 || rtmax - t > kEps)) {
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (fw & ~kLastBit);
+                            if (key < mykey) { mykey = key; myslot = slot; }
+                        }
+                        if (fw & kLastBit) break;
+                    }
+                    if (myslot >= 0) atomicMin(&q.best[owner], mykey);
+                }
+                __syncwarp();
+                if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
+                __syncwarp();
+            }
+            if (lane == 0) q.count = 0;
+            pending = 0;
+            if (have) {
+                const unsigned long long b = q.best[lane];
+                if (MODE == 0) tlimit = __uint_as_float((uint32_t)(b >> 32));
+                else if (b != kNoHit) { g_bits = 0; sp = 0; }      // blocked: nothing left to learn
+            }
+            __syncwarp();
+        }
+        // C. finished rays
+        if (have && (g_bits & 0xffu) == 0u && sp == 0 && pending == 0) {
+            const unsigned long long b = q.best[lane];
+            HitRec h;
+            h.t = __uint_as_float((uint32_t)(b >> 32));
+            h.face = b == kNoHit ? -1 : (int)(uint32_t)b;
+            h.slot = b == kNoHit ? -1 : q.best_slot[lane];
+            done(idx, h);
+            have = false;
+        }
+        // D. refill idle lanes from the ray queue
+        const unsigned idle = __ballot_sync(kFull, !have);
+        if (idle) {
+            const int n_idle = __popc(idle);
+            if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
+                base = __shfl_sync(kFull, base, leader);
+                if (!have) {
+                    const uint32_t i = base + __popc(idle & lt_mask);
+                    if (i < n) {
+                        idx = i;
+                        V3 d;
+                        float tmax;
+                        const bool live = load(i, o, d, tmax);
+                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        oinv = wide_octant(inv);
+                        tlimit = MODE == 0 ? FLT_MAX : tmax;
+                        q.ox[lane] = o.x; q.oy[lane] = o.y; q.oz[lane] = o.z;
+                        q.dx[lane] = d.x; q.dy[lane] = d.y; q.dz[lane] = d.z;
+                        q.tmax[lane] = tmax;
+                        q.best[lane] = kNoHit;
+                        q.best_slot[lane] = -1;
+                        sp = 0;
+                        pending = 0;
+                        g_base = 0;
+                        g_bits = (live && sc.n_nodes) ? ((1u << 8) | (1u << oinv)) : 0u;
+                        have = true;
+                    }
+                }
+                if (base + (uint32_t)n_idle >= n) exhausted = true;
+                __syncwarp();
+            }
+            if (idle == kFull && !__any_sync(kFull, have)) {
+                if (exhausted) break;
+            }
+        }
+    }
+}
+
+template <int MODE, int STRAT, typename Load, typename Done>
+CRT_DEV void trace_rays_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    if (STRAT == 2) trace_persistent_wide_queue<MODE>(sc, n, fetch, load, done);
+    else trace_persistent_wide<MODE>(sc, n, fetch, load, done);
+}
+
+}  // namespace crt

@@ -62,7 +62,10 @@ typedef struct crt_config {
 } crt_config;
 
 typedef enum crt_estimator { CRT_ESTIMATOR_COMPAT = 0, CRT_ESTIMATOR_MIS = 1 } crt_estimator;
-typedef enum crt_builder { CRT_BUILDER_LBVH = 0 } crt_builder;
+/* CRT_BUILDER_LBVH: Morton-sorted binary radix tree emitted as 64-byte child-pair nodes (crt_bvh_node).
+ * CRT_BUILDER_LBVH8: the same radix tree collapsed into 80-byte 8-wide nodes with 8-bit quantised child
+ * boxes (crt_bvh8_node); bvh_thresh_n is clamped to 15. Hits and images do not depend on the builder. */
+typedef enum crt_builder { CRT_BUILDER_LBVH = 0, CRT_BUILDER_LBVH8 = 1 } crt_builder;
 typedef enum crt_ray_mode { CRT_RAY_CLOSEST = 0, CRT_RAY_ANY = 1 } crt_ray_mode;
 
 /* 64-byte BVH node as exported by crt_scene_export_bvh (DESIGN.md "Layout"). */
@@ -73,6 +76,18 @@ typedef struct crt_bvh_node {
     int32_t c0, c1;          /* >= 0 node index, < 0 leaf = ~first_slot, 0x7fffffff = absent */
     int32_t n0, n1;          /* triangles below each child */
 } crt_bvh_node;
+
+/* 80-byte 8-wide node as exported by crt_scene_export_bvh8 (DESIGN.md "Wide nodes"). Child k's box is
+ * origin + q * 2^(exp - 127) per axis; the internal child in slot s is node child_base + popcount(imask
+ * below s); a leaf child (meta 1..127) starts at triangle slot tri_base + meta - 1. */
+typedef struct crt_bvh8_node {
+    float origin[3];
+    uint8_t exp[3];          /* exponent field of the per-axis cell size */
+    uint8_t imask;           /* bit s set: slot s holds an internal node */
+    uint32_t child_base, tri_base;
+    uint8_t meta[8];         /* 0 empty, 0x80 internal node, else 1 + triangle offset of a leaf */
+    uint8_t qlo_x[8], qlo_y[8], qlo_z[8], qhi_x[8], qhi_y[8], qhi_z[8];
+} crt_bvh8_node;
 
 typedef struct crt_render_stats {
     uint64_t samples;
@@ -122,6 +137,10 @@ int crt_scene_export_light(crt_scene* s, uint32_t li, int32_t* faces, uint32_t* 
 /* The GPU-built BVH, copied back: nodes[n_nodes], tri_order[n_tris] (slot -> face id),
  * last[n_tris] (leaf terminators), bounds lo(3) hi(3). Any pointer may be NULL. */
 int crt_scene_export_bvh(crt_scene* s, crt_bvh_node* nodes, int32_t* tri_order, uint8_t* last, float bounds[6]);
+/* Same for a scene built with CRT_BUILDER_LBVH8 (CRT_ERR_STATE otherwise; crt_scene_export_bvh likewise
+ * refuses a wide scene). crt_scene_bvh_kind reports the crt_builder the scene was built with. */
+int crt_scene_export_bvh8(crt_scene* s, crt_bvh8_node* nodes, int32_t* tri_order, uint8_t* last, float bounds[6]);
+int crt_scene_bvh_kind(crt_scene* s, int* builder);
 /* Scene::free, include/Scene.h:56-59 */
 int crt_scene_destroy(crt_scene* s);
 

@@ -59,7 +59,9 @@ def lib():
     L.orc_primary_rays.argtypes = [f32p, f32p, C.c_float, C.c_int, C.c_int, f32p]
     L.orc_inverse_view_matrix.argtypes = [f32p, f32p, f32p, f32p]
     L.orc_render.argtypes = [vp, f32p, f32p, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_float,
-                             C.c_int, C.c_uint32, C.c_int, i64p, vp, C.c_int]
+                             C.c_int, C.c_uint32, C.c_int, C.c_int, i64p, vp, C.c_int]
+    L.orc_wide8_build.argtypes = [vp, C.c_uint]
+    L.orc_wide8_get.argtypes = [vp, vp, vp, vp, vp]
     L.orc_resolve.argtypes = [i64p, C.c_int, C.c_uint32, vp, vp]
     L.orc_philox.argtypes = [u32p, u32p, u32p]
     L.orc_u01.argtypes = [C.c_uint32]
@@ -211,13 +213,23 @@ class Scene:
         assert np.all(t[b] > eps) and np.all(rays[b, 3] - t[b] > eps)
         return True
 
+    def build_wide8(self, thresh_n):
+        """8-wide compressed BVH (80-byte nodes): returns nodes (n x 20 uint32), order, last, bounds."""
+        n = self.L.orc_wide8_build(self.h, thresh_n)
+        nodes = np.zeros((n, 20), np.uint32)
+        order = np.zeros(self.n_tris, np.int32)
+        last = np.zeros(self.n_tris, np.uint8)
+        bounds = np.zeros(6, np.float32)
+        self.L.orc_wide8_get(self.h, _ptr(nodes), _ptr(order), _ptr(last), _ptr(bounds))
+        return nodes, order, last, bounds
+
     def render(self, eye, M, fovy_rad, width, height, s_begin, s_end, p_rr, light_sample_n, seed=0, estimator=0,
-               threads=None, accum=None):
+               threads=None, accum=None, wide=False):
         if accum is None:
             accum = np.zeros(width * height * 3, np.int64)
         stats = np.zeros(12, np.uint64)
         rc = self.L.orc_render(self.h, np.asarray(eye, np.float32), np.asarray(M, np.float32), fovy_rad, width, height,
-                               s_begin, s_end, p_rr, light_sample_n, seed, estimator, accum, _ptr(stats),
+                               s_begin, s_end, p_rr, light_sample_n, seed, estimator, 1 if wide else 0, accum, _ptr(stats),
                                threads or max_threads())
         if rc != 0:
             raise RuntimeError("orc_render failed rc=%d" % rc)

@@ -176,49 +176,45 @@ struct Radix {
 };
 }  // namespace
 
-void build_new_bvh(const Scene& s, unsigned thresh_n, int builder, NewBVH& out) {
+// Steps 1-4 above plus the boxes of the radix nodes: shared by the 64-byte pair-node emitter below
+// and by the 8-wide collapse.
+struct RadixTree {
+    int n = 0;
+    V3 lo, hi;                               // scene bounds
+    std::vector<int> order;                  // sorted slot -> face id
+    std::vector<int> left, right;            // per internal node: >= 0 internal node, < 0 ~slot (single triangle)
+    std::vector<int> first, last;            // slot range of each internal node
+    std::vector<V3> blo, bhi;                // boxes of the internal nodes
+};
+
+static void build_radix_tree(const Scene& s, RadixTree& rt) {
     const int n = (int)s.tris.size();
-    out.nodes.clear(); out.order.clear(); out.last.clear();
-    out.builder = builder;
-    if (thresh_n < 1) thresh_n = 1;
-    out.lo = V3{FLT_MAX, FLT_MAX, FLT_MAX};
-    out.hi = V3{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    rt.n = n;
+    rt.lo = V3{FLT_MAX, FLT_MAX, FLT_MAX};
+    rt.hi = V3{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    rt.order.clear(); rt.left.clear(); rt.right.clear(); rt.first.clear(); rt.last.clear(); rt.blo.clear(); rt.bhi.clear();
     if (n == 0) return;
-    for (const Tri& t : s.tris) { out.lo = vmin(out.lo, t.lo); out.hi = vmax(out.hi, t.hi); }
-    V3 ext = out.hi - out.lo;
+    for (const Tri& t : s.tris) { rt.lo = vmin(rt.lo, t.lo); rt.hi = vmax(rt.hi, t.hi); }
+    V3 ext = rt.hi - rt.lo;
     V3 scale{ext.x > 0 ? 2097152.0f / ext.x : 0.0f, ext.y > 0 ? 2097152.0f / ext.y : 0.0f,
              ext.z > 0 ? 2097152.0f / ext.z : 0.0f};
     std::vector<uint64_t> key(n);
     for (int i = 0; i < n; ++i) {
         const Tri& t = s.tris[i];
         V3 c = (t.lo + t.hi) * 0.5f;
-        uint64_t qx = quant21(c.x, out.lo.x, scale.x), qy = quant21(c.y, out.lo.y, scale.y),
-                 qz = quant21(c.z, out.lo.z, scale.z);
+        uint64_t qx = quant21(c.x, rt.lo.x, scale.x), qy = quant21(c.y, rt.lo.y, scale.y),
+                 qz = quant21(c.z, rt.lo.z, scale.z);
         key[i] = (expand21(qx) << 2) | (expand21(qy) << 1) | expand21(qz);
     }
-    out.order.resize(n);
-    std::iota(out.order.begin(), out.order.end(), 0);
-    std::stable_sort(out.order.begin(), out.order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    rt.order.resize(n);
+    std::iota(rt.order.begin(), rt.order.end(), 0);
+    std::stable_sort(rt.order.begin(), rt.order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    if (n < 2) return;
     std::vector<uint64_t> skey(n);
-    for (int i = 0; i < n; ++i) skey[i] = key[out.order[i]];
-    out.last.assign(n, 0);
-
-    auto tri_box = [&](int slot, V3& lo, V3& hi) { lo = s.tris[out.order[slot]].lo; hi = s.tris[out.order[slot]].hi; };
-    auto set_child = [&](PairNode& pn, int which, int ref, int cnt, V3 lo, V3 hi) {
-        if (which == 0) { pn.c0 = ref; pn.n0 = cnt; pn.c0lox = lo.x; pn.c0hix = hi.x; pn.c0loy = lo.y; pn.c0hiy = hi.y; pn.c0loz = lo.z; pn.c0hiz = hi.z; }
-        else { pn.c1 = ref; pn.n1 = cnt; pn.c1lox = lo.x; pn.c1hix = hi.x; pn.c1loy = lo.y; pn.c1hiy = hi.y; pn.c1loz = lo.z; pn.c1hiz = hi.z; }
-    };
-    if ((unsigned)n <= thresh_n) {                         // whole scene is one leaf
-        PairNode pn{};
-        set_child(pn, 0, ~0, n, out.lo, out.hi);
-        set_child(pn, 1, kEmptyChild, 0, V3{FLT_MAX, FLT_MAX, FLT_MAX}, V3{-FLT_MAX, -FLT_MAX, -FLT_MAX});
-        out.nodes.push_back(pn);
-        out.last[n - 1] = 1;
-        return;
-    }
+    for (int i = 0; i < n; ++i) skey[i] = key[rt.order[i]];
     // Karras radix tree: internal nodes 0..n-2
     Radix rx{skey, n};
-    std::vector<int> left(n - 1), right(n - 1), first(n - 1), lastl(n - 1);
+    rt.left.resize(n - 1); rt.right.resize(n - 1); rt.first.resize(n - 1); rt.last.resize(n - 1);
     for (int i = 0; i < n - 1; ++i) {
         int d = (rx.delta(i, i + 1) - rx.delta(i, i - 1)) >= 0 ? 1 : -1;
         int dmin = rx.delta(i, i - d);
@@ -237,30 +233,58 @@ void build_new_bvh(const Scene& s, unsigned thresh_n, int builder, NewBVH& out) 
         } while (t > 1);
         int gamma = i + sp * d + std::min(d, 0);
         int lo_i = std::min(i, j), hi_i = std::max(i, j);
-        first[i] = lo_i; lastl[i] = hi_i;
-        left[i] = (lo_i == gamma) ? ~gamma : gamma;            // ~slot = single-triangle leaf
-        right[i] = (hi_i == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+        rt.first[i] = lo_i; rt.last[i] = hi_i;
+        rt.left[i] = (lo_i == gamma) ? ~gamma : gamma;            // ~slot = single-triangle leaf
+        rt.right[i] = (hi_i == gamma + 1) ? ~(gamma + 1) : gamma + 1;
     }
     // boxes of radix nodes, bottom-up by recursion on an explicit stack (post-order)
-    std::vector<V3> blo(n - 1), bhi(n - 1);
-    {
-        std::vector<std::pair<int, int>> st;   // (node, state)
-        st.emplace_back(0, 0);
-        while (!st.empty()) {
-            auto [nd, state] = st.back();
-            if (state == 0) {
-                st.back().second = 1;
-                if (left[nd] >= 0) st.emplace_back(left[nd], 0);
-                if (right[nd] >= 0) st.emplace_back(right[nd], 0);
-            } else {
-                st.pop_back();
-                V3 llo, lhi, rlo, rhi;
-                if (left[nd] >= 0) { llo = blo[left[nd]]; lhi = bhi[left[nd]]; } else tri_box(~left[nd], llo, lhi);
-                if (right[nd] >= 0) { rlo = blo[right[nd]]; rhi = bhi[right[nd]]; } else tri_box(~right[nd], rlo, rhi);
-                blo[nd] = vmin(llo, rlo);
-                bhi[nd] = vmax(lhi, rhi);
-            }
+    rt.blo.resize(n - 1); rt.bhi.resize(n - 1);
+    auto tri_box = [&](int slot, V3& lo, V3& hi) { lo = s.tris[rt.order[slot]].lo; hi = s.tris[rt.order[slot]].hi; };
+    std::vector<std::pair<int, int>> st;   // (node, state)
+    st.emplace_back(0, 0);
+    while (!st.empty()) {
+        auto [nd, state] = st.back();
+        if (state == 0) {
+            st.back().second = 1;
+            if (rt.left[nd] >= 0) st.emplace_back(rt.left[nd], 0);
+            if (rt.right[nd] >= 0) st.emplace_back(rt.right[nd], 0);
+        } else {
+            st.pop_back();
+            V3 llo, lhi, rlo, rhi;
+            if (rt.left[nd] >= 0) { llo = rt.blo[rt.left[nd]]; lhi = rt.bhi[rt.left[nd]]; } else tri_box(~rt.left[nd], llo, lhi);
+            if (rt.right[nd] >= 0) { rlo = rt.blo[rt.right[nd]]; rhi = rt.bhi[rt.right[nd]]; } else tri_box(~rt.right[nd], rlo, rhi);
+            rt.blo[nd] = vmin(llo, rlo);
+            rt.bhi[nd] = vmax(lhi, rhi);
         }
+    }
+}
+
+void build_new_bvh(const Scene& s, unsigned thresh_n, int builder, NewBVH& out) {
+    const int n = (int)s.tris.size();
+    out.nodes.clear(); out.order.clear(); out.last.clear();
+    out.builder = builder;
+    if (thresh_n < 1) thresh_n = 1;
+    RadixTree rt;
+    build_radix_tree(s, rt);
+    out.lo = rt.lo; out.hi = rt.hi;
+    if (n == 0) return;
+    out.order = rt.order;
+    out.last.assign(n, 0);
+    const std::vector<int>&left = rt.left, &right = rt.right, &first = rt.first, &lastl = rt.last;
+    const std::vector<V3>&blo = rt.blo, &bhi = rt.bhi;
+
+    auto tri_box = [&](int slot, V3& lo, V3& hi) { lo = s.tris[out.order[slot]].lo; hi = s.tris[out.order[slot]].hi; };
+    auto set_child = [&](PairNode& pn, int which, int ref, int cnt, V3 lo, V3 hi) {
+        if (which == 0) { pn.c0 = ref; pn.n0 = cnt; pn.c0lox = lo.x; pn.c0hix = hi.x; pn.c0loy = lo.y; pn.c0hiy = hi.y; pn.c0loz = lo.z; pn.c0hiz = hi.z; }
+        else { pn.c1 = ref; pn.n1 = cnt; pn.c1lox = lo.x; pn.c1hix = hi.x; pn.c1loy = lo.y; pn.c1hiy = hi.y; pn.c1loz = lo.z; pn.c1hiz = hi.z; }
+    };
+    if ((unsigned)n <= thresh_n) {                         // whole scene is one leaf
+        PairNode pn{};
+        set_child(pn, 0, ~0, n, out.lo, out.hi);
+        set_child(pn, 1, kEmptyChild, 0, V3{FLT_MAX, FLT_MAX, FLT_MAX}, V3{-FLT_MAX, -FLT_MAX, -FLT_MAX});
+        out.nodes.push_back(pn);
+        out.last[n - 1] = 1;
+        return;
     }
     // kept nodes: more than thresh_n triangles; rank by radix index
     std::vector<int> rank(n - 1, -1);
@@ -351,6 +375,266 @@ Hit new_intersect(const Scene& s, const NewBVH& b, const Ray& r, int mode, Trace
             }
             if (sp == 0) break;
             cur = stack[--sp];
+        }
+    }
+    if (st) st->max_stack = std::max(st->max_stack, max_sp);
+    return best;
+}
+
+// =============================================================================================
+// 8-wide compressed BVH: collapse of the radix tree, CPU statement (the CUDA builder must
+// reproduce nodes / order / last byte for byte; DESIGN.md "Wide nodes" is the specification).
+//   * a radix node with more than thresh triangles is "expandable"; anything else is a leaf
+//     (single triangle, or a radix node with <= thresh triangles);
+//   * the children of a wide node start as the two children of its radix node; the expandable child
+//     with the largest box area (first one on ties) is replaced in place by its own two children
+//     until there are 8 children or nothing is expandable;
+//   * children go to the 8 slots greedily by the largest sum of +-(child centre - node centre)
+//     components, sign + where the slot's bit is set (bit 0 x, 1 y, 2 z); a ray then visits
+//     slot ^ (its direction octant) in descending order, which is front to back;
+//   * boxes are quantised to 8 bits per plane against the node box with power-of-two cell sizes,
+//     rounded outwards in exact (double) arithmetic;
+//   * nodes are numbered breadth first; the leaf triangles of one node are contiguous, slot order.
+// =============================================================================================
+namespace {
+struct WideChild { int ref; int first, count; V3 lo, hi; bool expandable; };
+static inline float box_area(V3 lo, V3 hi) {
+    float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return (ex * ey + ey * ez) + ez * ex;
+}
+static inline int exp_of_double(double v) {          // floor(log2 v) for a positive normal double
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    return (int)((b >> 52) & 0x7ff) - 1023;
+}
+}  // namespace
+
+void build_wide8_bvh(const Scene& s, unsigned thresh_n, Wide8BVH& out) {
+    const int n = (int)s.tris.size();
+    out.nodes.clear(); out.order.clear(); out.last.clear();
+    if (thresh_n < 1) thresh_n = 1;
+    if (thresh_n > kWideMaxLeaf) thresh_n = kWideMaxLeaf;
+    RadixTree rt;
+    build_radix_tree(s, rt);
+    out.lo = rt.lo; out.hi = rt.hi;
+    if (n == 0) return;
+    out.order.assign(n, -1);
+    out.last.assign(n, 0);
+    auto make_child = [&](int c) {
+        WideChild w;
+        if (c < 0) {
+            const Tri& t = s.tris[rt.order[~c]];
+            w = WideChild{c, ~c, 1, t.lo, t.hi, false};
+        } else {
+            int cnt = rt.last[c] - rt.first[c] + 1;
+            w = WideChild{c, rt.first[c], cnt, rt.blo[c], rt.bhi[c], (unsigned)cnt > thresh_n};
+        }
+        return w;
+    };
+    struct Pending { int radix; };             // radix < 0: the whole scene as one leaf
+    std::vector<Pending> level, next;
+    level.push_back(Pending{(unsigned)n <= thresh_n ? -1 : 0});
+    int tri_cursor = 0;
+    while (!level.empty()) {
+        const int level_start = (int)out.nodes.size();
+        const int next_start = level_start + (int)level.size();
+        next.clear();
+        for (const Pending& pn : level) {
+            WideChild ch[8];
+            int k = 0;
+            V3 nlo, nhi;
+            if (pn.radix < 0) {
+                ch[k++] = WideChild{0, 0, n, rt.lo, rt.hi, false};
+                nlo = rt.lo; nhi = rt.hi;
+            } else {
+                ch[k++] = make_child(rt.left[pn.radix]);
+                ch[k++] = make_child(rt.right[pn.radix]);
+                nlo = rt.blo[pn.radix]; nhi = rt.bhi[pn.radix];
+                while (k < 8) {
+                    int best = -1;
+                    float best_area = 0.0f;
+                    for (int j = 0; j < k; ++j) {
+                        if (!ch[j].expandable) continue;
+                        float a = box_area(ch[j].lo, ch[j].hi);
+                        if (best < 0 || a > best_area) { best = j; best_area = a; }
+                    }
+                    if (best < 0) break;
+                    int c = ch[best].ref;
+                    for (int j = k; j > best + 1; --j) ch[j] = ch[j - 1];
+                    ch[best] = make_child(rt.left[c]);
+                    ch[best + 1] = make_child(rt.right[c]);
+                    ++k;
+                }
+            }
+            // slot assignment
+            V3 cen = (nlo + nhi) * 0.5f;
+            V3 dv[8];
+            for (int j = 0; j < k; ++j) dv[j] = (ch[j].lo + ch[j].hi) * 0.5f - cen;
+            int slot_of[8], child_in[8];
+            for (int j = 0; j < 8; ++j) { slot_of[j] = -1; child_in[j] = -1; }
+            for (int it = 0; it < k; ++it) {
+                int bj = -1, bs = -1;
+                float bc = 0.0f;
+                for (int j = 0; j < k; ++j) {
+                    if (slot_of[j] >= 0) continue;
+                    for (int sl = 0; sl < 8; ++sl) {
+                        if (child_in[sl] >= 0) continue;
+                        float tx = (sl & 1) ? dv[j].x : -dv[j].x, ty = (sl & 2) ? dv[j].y : -dv[j].y,
+                              tz = (sl & 4) ? dv[j].z : -dv[j].z;
+                        float c = (tx + ty) + tz;
+                        if (bj < 0 || c > bc) { bj = j; bs = sl; bc = c; }
+                    }
+                }
+                slot_of[bj] = bs;
+                child_in[bs] = bj;
+            }
+            // quantisation frame
+            uint32_t eb[3];
+            double cell[3];
+            const float plo[3] = {nlo.x, nlo.y, nlo.z}, phi[3] = {nhi.x, nhi.y, nhi.z};
+            for (int a = 0; a < 3; ++a) {
+                double ext = (double)phi[a] - (double)plo[a];
+                if (!(ext > 0.0)) { eb[a] = 0; cell[a] = 0.0; continue; }
+                int e = exp_of_double(ext / 255.0);
+                if (ldexp(255.0, e) < ext) e += 1;
+                int b = e + 127;
+                if (b < 1) b = 1;
+                if (b > 254) b = 254;
+                eb[a] = (uint32_t)b;
+                cell[a] = ldexp(1.0, b - 127);
+            }
+            Wide8Node node;
+            memset(&node, 0, sizeof(node));
+            uint8_t meta[8], q[6][8];
+            uint32_t imask = 0;
+            int n_internal = 0, tri_off = 0;
+            for (int sl = 0; sl < 8; ++sl) {
+                meta[sl] = 0;
+                for (int a = 0; a < 3; ++a) { q[a][sl] = 255; q[3 + a][sl] = 0; }
+                int j = child_in[sl];
+                if (j < 0) continue;
+                const float clo[3] = {ch[j].lo.x, ch[j].lo.y, ch[j].lo.z}, chi[3] = {ch[j].hi.x, ch[j].hi.y, ch[j].hi.z};
+                for (int a = 0; a < 3; ++a) {
+                    int ql = 0, qh = 0;
+                    if (cell[a] > 0.0) {
+                        double fl = floor(((double)clo[a] - (double)plo[a]) / cell[a]);
+                        double fh = ceil(((double)chi[a] - (double)plo[a]) / cell[a]);
+                        ql = fl < 0.0 ? 0 : (fl > 255.0 ? 255 : (int)fl);
+                        qh = fh < 0.0 ? 0 : (fh > 255.0 ? 255 : (int)fh);
+                    }
+                    q[a][sl] = (uint8_t)ql;
+                    q[3 + a][sl] = (uint8_t)qh;
+                }
+                if (ch[j].expandable) {
+                    meta[sl] = 0x80;
+                    imask |= 1u << sl;
+                    next.push_back(Pending{ch[j].ref});
+                    ++n_internal;
+                } else {
+                    meta[sl] = (uint8_t)(1 + tri_off);
+                    for (int t = 0; t < ch[j].count; ++t) out.order[tri_cursor + tri_off + t] = rt.order[ch[j].first + t];
+                    out.last[tri_cursor + tri_off + ch[j].count - 1] = 1;
+                    tri_off += ch[j].count;
+                }
+            }
+            node.w[0] = f2u(plo[0]); node.w[1] = f2u(plo[1]); node.w[2] = f2u(plo[2]);
+            node.w[3] = eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24);
+            node.w[4] = (uint32_t)(next_start + (int)next.size() - n_internal);
+            node.w[5] = (uint32_t)tri_cursor;
+            auto pack4 = [](const uint8_t* b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
+            node.w[6] = pack4(meta); node.w[7] = pack4(meta + 4);
+            for (int a = 0; a < 6; ++a) { node.w[8 + 2 * a] = pack4(q[a]); node.w[9 + 2 * a] = pack4(q[a] + 4); }
+            out.nodes.push_back(node);
+            tri_cursor += tri_off;
+        }
+        level.swap(next);
+    }
+}
+
+// Traversal of the wide BVH, sequential rule (what the tail kernel runs per lane and what the visit counts
+// of the roofline refer to): conservative quantised slabs, children visited front to back by slot ^ octant,
+// leaf children of a node tested before descending, one stack entry per node with hits left.
+Hit wide8_intersect(const Scene& s, const Wide8BVH& b, const Ray& r, int mode, TraceStats* st) {
+    Hit best{FLT_MAX, -1};
+    if (st) st->rays++;
+    if (b.nodes.empty()) return best;
+    const V3 o = r.o, d = r.d;
+    const V3 inv{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    const bool negx = inv.x < 0.0f, negy = inv.y < 0.0f, negz = inv.z < 0.0f;
+    const uint32_t oinv = (negx ? 0u : 1u) | (negy ? 0u : 2u) | (negz ? 0u : 4u);
+    float tlimit = mode == 0 ? FLT_MAX : r.tmax;
+    uint32_t stack_base[64], stack_bits[64];
+    int sp = 0;
+    uint64_t max_sp = 0;
+    uint32_t g_base = 0, g_imask = 1, g_mask = 1u << oinv;     // the root as slot 0 of a virtual parent
+    for (;;) {
+        if (g_mask == 0) {
+            if (sp == 0) break;
+            --sp;
+            g_base = stack_base[sp]; g_imask = stack_bits[sp] >> 8; g_mask = stack_bits[sp] & 0xffu;
+        }
+        const int pr = 31 - __builtin_clz(g_mask);
+        g_mask &= ~(1u << pr);
+        const uint32_t sl = (uint32_t)pr ^ oinv;
+        const Wide8Node& nd = b.nodes[g_base + (uint32_t)__builtin_popcount(g_imask & ((1u << sl) - 1u))];
+        if (st) { st->inner++; st->boxes += 8; }
+        const uint32_t ew = nd.w[3];
+        const float px = u2f(nd.w[0]), py = u2f(nd.w[1]), pz = u2f(nd.w[2]);
+        const float sx = u2f((ew & 0xffu) << 23), sy = u2f(((ew >> 8) & 0xffu) << 23), sz = u2f(((ew >> 16) & 0xffu) << 23);
+        const float ax = (px - o.x) * inv.x, ay = (py - o.y) * inv.y, az = (pz - o.z) * inv.z;
+        const float bx = sx * inv.x, by = sy * inv.y, bz = sz * inv.z;
+        float fax = fabsf(ax), fay = fabsf(ay), faz = fabsf(az);
+        if (!(fax <= FLT_MAX)) fax = 0.0f;
+        if (!(fay <= FLT_MAX)) fay = 0.0f;
+        if (!(faz <= FLT_MAX)) faz = 0.0f;
+        const float pad = fmaxf(fmaxf(fax, fay), faz) * 4.76837158203125e-07f;     // 2^-21
+        const float lim = tlimit * 1.0001f;
+        const uint8_t* bytes = (const uint8_t*)nd.w;
+        const uint8_t* meta = bytes + 24;
+        const uint8_t* qnx = bytes + 32 + (negx ? 24 : 0);      // near planes: hi when the direction is negative
+        const uint8_t* qfx = bytes + 32 + (negx ? 0 : 24);
+        const uint8_t* qny = bytes + 40 + (negy ? 24 : 0);
+        const uint8_t* qfy = bytes + 40 + (negy ? 0 : 24);
+        const uint8_t* qnz = bytes + 48 + (negz ? 24 : 0);
+        const uint8_t* qfz = bytes + 48 + (negz ? 0 : 24);
+        uint32_t node_hits = 0, leaf_hits = 0;                  // priority space
+        for (uint32_t c = 0; c < 8; ++c) {
+            if (meta[c] == 0) continue;
+            const float tnx = fmaf((float)qnx[c], bx, ax), tfx = fmaf((float)qfx[c], bx, ax);
+            const float tny = fmaf((float)qny[c], by, ay), tfy = fmaf((float)qfy[c], by, ay);
+            const float tnz = fmaf((float)qnz[c], bz, az), tfz = fmaf((float)qfz[c], bz, az);
+            const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+            const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, lim));
+            if (tmin <= fmaf(tmax, 1.0000004f, pad)) {
+                if (meta[c] & 0x80) node_hits |= 1u << (c ^ oinv); else leaf_hits |= 1u << (c ^ oinv);
+            }
+        }
+        while (leaf_hits) {
+            const int lp = 31 - __builtin_clz(leaf_hits);
+            leaf_hits &= ~(1u << lp);
+            int slot = (int)(nd.w[5] + (uint32_t)(meta[(uint32_t)lp ^ oinv] - 1));
+            for (;; ++slot) {
+                const int face = b.order[slot];
+                float t;
+                if (st) st->tris++;
+                if (tri_test(s.tris[face], o, d, &t) && t > kEps) {
+                    if (mode == 0) {
+                        if (t < best.t || (t == best.t && face < best.face)) { best = Hit{t, face}; tlimit = t; }
+                    } else if (r.tmax - t > kEps) {
+                        if (st) st->max_stack = std::max(st->max_stack, max_sp);
+                        return Hit{t, face};
+                    }
+                }
+                if (b.last[slot]) break;
+            }
+        }
+        if (node_hits) {
+            if (g_mask) {
+                stack_base[sp] = g_base; stack_bits[sp] = (g_imask << 8) | g_mask;
+                ++sp;
+                if ((uint64_t)sp > max_sp) max_sp = sp;
+            }
+            g_base = nd.w[4]; g_imask = ew >> 24; g_mask = node_hits;
         }
     }
     if (st) st->max_stack = std::max(st->max_stack, max_sp);

@@ -63,4 +63,22 @@ Hit new_intersect(const Scene& s, const NewBVH& b, const Ray& r, int mode, Trace
 
 Hit brute_intersect(const Scene& s, const Ray& r, int mode);
 
+// ---------------------------------------------------------------- 8-wide compressed BVH (DESIGN.md "Wide nodes")
+// 80-byte node = five 16-byte words:
+//   w0: origin p (3 floats), {ex, ey, ez, imask} bytes          scale_k = float with exponent field e_k
+//   w1: child_base, tri_base, meta[0..3], meta[4..7]            meta: 0 empty, 0x80 node, 1 + offset leaf
+//   w2: qlo_x[0..7], qlo_y[0..7]   w3: qlo_z[0..7], qhi_x[0..7]   w4: qhi_y[0..7], qhi_z[0..7]
+// child box k = p + q * scale (per axis), internal child in slot s = node child_base + popcount(imask below s),
+// leaf child = triangle slots tri_base + offset .. up to the terminator in `last`.
+struct Wide8Node { uint32_t w[20]; };
+struct Wide8BVH {
+    std::vector<Wide8Node> nodes;     // breadth-first, node 0 is the root
+    std::vector<int> order;           // slot -> face id (leaf triangles of one node are contiguous)
+    std::vector<uint8_t> last;
+    V3 lo, hi;
+};
+static const unsigned kWideMaxLeaf = 15;      // a leaf holds at most this many triangles (7-bit offsets)
+void build_wide8_bvh(const Scene& s, unsigned thresh_n, Wide8BVH& out);
+Hit wide8_intersect(const Scene& s, const Wide8BVH& b, const Ray& r, int mode, TraceStats* st);
+
 }  // namespace orc

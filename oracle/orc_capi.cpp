@@ -13,7 +13,8 @@ struct orc_scene {
     Scene s;
     RefBVH ref;
     NewBVH nb;
-    bool has_ref = false, has_new = false;
+    Wide8BVH wb;
+    bool has_ref = false, has_new = false, has_wide = false;
 };
 
 extern "C" {
@@ -117,14 +118,28 @@ void orc_newbvh_get(orc_scene* h, void* nodes64, int* order, uint8_t* last, floa
     if (bounds6) { bounds6[0] = h->nb.lo.x; bounds6[1] = h->nb.lo.y; bounds6[2] = h->nb.lo.z; bounds6[3] = h->nb.hi.x; bounds6[4] = h->nb.hi.y; bounds6[5] = h->nb.hi.z; }
 }
 
+// ---- 8-wide BVH
+int orc_wide8_build(orc_scene* h, unsigned thresh_n) {
+    build_wide8_bvh(h->s, thresh_n, h->wb);
+    h->has_wide = true;
+    return (int)h->wb.nodes.size();
+}
+void orc_wide8_get(orc_scene* h, void* nodes80, int* order, uint8_t* last, float* bounds6) {
+    if (nodes80) memcpy(nodes80, h->wb.nodes.data(), h->wb.nodes.size() * sizeof(Wide8Node));
+    if (order) memcpy(order, h->wb.order.data(), h->wb.order.size() * sizeof(int));
+    if (last) memcpy(last, h->wb.last.data(), h->wb.last.size());
+    if (bounds6) { bounds6[0] = h->wb.lo.x; bounds6[1] = h->wb.lo.y; bounds6[2] = h->wb.lo.z; bounds6[3] = h->wb.hi.x; bounds6[4] = h->wb.hi.y; bounds6[5] = h->wb.hi.z; }
+}
+
 // ---- tracing. rays n*8 floats: o(3) tmax d(3) pad ; out t[n], face[n]
 // which: 0 = new BVH, 1 = reference BVH + reference rule (canonical ties), 2 = reference rule literal
-//        ties, 3 = brute force.  mode: 0 closest, 1 any-hit (which 0 and 3 only).
+//        ties, 3 = brute force, 4 = 8-wide BVH.  mode: 0 closest, 1 any-hit (which 0, 3 and 4 only).
 // stats5 (optional): inner, boxes, tris, max_stack, rays
 int orc_trace(orc_scene* h, int which, int mode, const float* rays, int64_t n, float* t_out, int* face_out,
               uint64_t* stats5, int n_threads) {
     if (which == 0 && !h->has_new) return -1;
     if ((which == 1 || which == 2) && !h->has_ref) return -1;
+    if (which == 4 && !h->has_wide) return -1;
     if (n_threads < 1) n_threads = 1;
     std::vector<TraceStats> tls(n_threads);
 #pragma omp parallel for schedule(dynamic, 256) num_threads(n_threads)
@@ -139,6 +154,7 @@ int orc_trace(orc_scene* h, int which, int mode, const float* rays, int64_t n, f
         if (which == 0) hit = new_intersect(h->s, h->nb, ray, mode, &tls[tid]);
         else if (which == 1) hit = ref_intersect(h->s, h->ref, ray.o, ray.d, true, &tls[tid]);
         else if (which == 2) hit = ref_intersect(h->s, h->ref, ray.o, ray.d, false, &tls[tid]);
+        else if (which == 4) hit = wide8_intersect(h->s, h->wb, ray, mode, &tls[tid]);
         else hit = brute_intersect(h->s, ray, mode);
         if (t_out) t_out[k] = hit.t;
         if (face_out) face_out[k] = hit.face;
@@ -194,7 +210,7 @@ void orc_inverse_view_matrix(const float eye[3], const float lookat[3], const fl
 
 // stats12: samples, extend, shadow, probe, closest{inner,tris,rays,max_stack}, any{inner,tris,rays,max_stack}
 int orc_render(orc_scene* h, const float eye[3], const float M[9], float fovy_rad, int width, int height,
-               uint32_t s_begin, uint32_t s_end, float p_rr, int light_sample_n, uint32_t seed, int estimator,
+               uint32_t s_begin, uint32_t s_end, float p_rr, int light_sample_n, uint32_t seed, int estimator, int use_wide,
                int64_t* accum, uint64_t* stats12, int n_threads) {
     if (!h->has_new) return -1;
     if (estimator < ESTIMATOR_COMPAT || estimator > ESTIMATOR_MIS_BSDF_ONLY) return -2;
@@ -206,7 +222,8 @@ int orc_render(orc_scene* h, const float eye[3], const float M[9], float fovy_ra
     p.width = width; p.height = height; p.s_begin = s_begin; p.s_end = s_end;
     p.p_rr = p_rr; p.light_sample_n = light_sample_n; p.seed = seed; p.estimator = estimator;
     RenderStats st;
-    render(h->s, h->nb, cam, p, accum, &st, n_threads);
+    if (use_wide && !h->has_wide) return -1;
+    render(h->s, h->nb, cam, p, accum, &st, n_threads, use_wide ? &h->wb : nullptr);
     if (stats12) {
         uint64_t v[12] = {st.samples, st.extend_rays, st.shadow_rays, st.probe_rays,
                           st.closest.inner, st.closest.tris, st.closest.rays, st.closest.max_stack,

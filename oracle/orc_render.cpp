@@ -97,7 +97,11 @@ struct Ctx {
     const NewBVH& b;
     const Camera& cam;
     const RenderParams& p;
+    const Wide8BVH* wide;          // when set, rays go through the 8-wide BVH (same hits, other visit counts)
 };
+static inline Hit trace(const Ctx& c, const Ray& r, int mode, TraceStats* st) {
+    return c.wide ? wide8_intersect(c.s, *c.wide, r, mode, st) : new_intersect(c.s, c.b, r, mode, st);
+}
 }  // namespace
 
 // One camera path of the compat estimator. Reference: cast_ray_v2, Render.cuh:199-328.
@@ -116,12 +120,12 @@ static void path_compat(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sam
     V3 probe_w{};
     const float lsn_f = (float)p.light_sample_n;
     for (int bnc = 0; bnc < p.max_vertices; ++bnc) {
-        Hit h = new_intersect(s, c.b, ray, 0, &st->closest);
+        Hit h = trace(c, ray, 0, &st->closest);
         st->extend_rays++;
         if (have_probe) {
             // Render.cuh:294-314 — evaluated only when the path continued to a real hit
             if (h.face >= 0) {
-                Hit ph = new_intersect(s, c.b, probe_ray, 0, &st->closest);
+                Hit ph = trace(c, probe_ray, 0, &st->closest);
                 st->probe_rays++;
                 if (ph.face >= 0) {
                     const Material& pm = s.mats[s.tris[ph.face].mat];
@@ -164,7 +168,7 @@ static void path_compat(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sam
                 float t_to_light = dist.x / dir.x;                        // :272
                 if (t_to_light == t_to_light) {                           // NaN => never "blocked" (:19-27)
                     Ray sh{pos, normalize(dir), t_to_light};
-                    Hit bh = new_intersect(s, c.b, sh, 1, &st->any);
+                    Hit bh = trace(c, sh, 1, &st->any);
                     st->shadow_rays++;
                     if (bh.face >= 0) continue;
                 }
@@ -240,7 +244,7 @@ static void path_mis(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sample
     // alone or with BSDF samples alone; all three must converge to the same image (tests/test_oracle.py)
     const int variant = p.estimator;
     for (int bnc = 0; bnc < p.max_vertices; ++bnc) {
-        Hit h = new_intersect(s, c.b, ray, 0, &st->closest);
+        Hit h = trace(c, ray, 0, &st->closest);
         st->extend_rays++;
         if (h.face < 0) break;
         const Tri& tri = s.tris[h.face];
@@ -301,7 +305,7 @@ static void path_mis(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sample
             V3 contrib = cmul(cmul(T, f), lm.ke) * (cos_s * w / pls);
             if (contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f) continue;
             Ray sh{org, wi, d1 * 0.999f};
-            Hit bh = new_intersect(s, c.b, sh, 1, &st->any);
+            Hit bh = trace(c, sh, 1, &st->any);
             st->shadow_rays++;
             if (bh.face >= 0) continue;
             add_contrib(px, contrib);
@@ -337,8 +341,8 @@ static void path_mis(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sample
 }
 
 void render(const Scene& s, const NewBVH& b, const Camera& cam, const RenderParams& p, int64_t* accum,
-            RenderStats* stats, int n_threads) {
-    Ctx c{s, b, cam, p};
+            RenderStats* stats, int n_threads, const Wide8BVH* wide) {
+    Ctx c{s, b, cam, p, wide};
     const int npix = p.width * p.height;
     if (n_threads < 1) n_threads = 1;
     std::vector<RenderStats> tls(n_threads);

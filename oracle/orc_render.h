@@ -39,7 +39,7 @@ static const double kFixedScale = 4294967296.0;   // 2^32
 
 // Adds the samples [s_begin, s_end) of every pixel into accum[W*H*3].
 void render(const Scene& s, const NewBVH& b, const Camera& cam, const RenderParams& p, int64_t* accum,
-            RenderStats* stats, int n_threads);
+            RenderStats* stats, int n_threads, const Wide8BVH* wide = nullptr);
 
 // Single primary ray of pixel (i,j) with jitter (u1,u2): Render.cuh:344-347 + Ray.cuh:12-15.
 Ray primary_ray(const Camera& cam, int width, int height, int i, int j, float u1, float u2);

@@ -244,3 +244,127 @@ def test_mis_estimator_is_consistent(orc, scene_files):
     a2, _ = S.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 3, 8, cfg.P_RR, 2, estimator=1)
     a3, _ = S.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 0, 8, cfg.P_RR, 2, estimator=1)
     assert np.array_equal(a1 + a2, a3)
+
+
+# ---- 8-wide compressed BVH (CPU statement of builder LBVH8; the GPU build must equal it byte for byte)
+def _wide_fields(nodes):
+    """nodes: n x 20 uint32 -> dict of per-node arrays."""
+    b = nodes.view(np.uint8).reshape(len(nodes), 80)
+    return dict(origin=nodes[:, 0:3].view(np.float32), exp=b[:, 12:15], imask=b[:, 15], child_base=nodes[:, 4], tri_base=nodes[:, 5],
+                meta=b[:, 24:32], qlo=b[:, 32:56].reshape(-1, 3, 8), qhi=b[:, 56:80].reshape(-1, 3, 8))
+
+
+def test_wide8_structure_and_boxes(orc):
+    rng = np.random.default_rng(5)
+    n = 3000
+    verts = soup(rng, n)
+    verts[100:140] = verts[100]
+    S = orc.Scene().add_arrays(verts, np.zeros(n, np.int32), np.zeros(n, np.int32), [[.5, .5, .5, 0, 0, 0, 1]])
+    tri = verts.reshape(n, 3, 3)
+    tlo, thi = tri.min(axis=1).astype(np.float64), tri.max(axis=1).astype(np.float64)
+    for thresh in (1, 2, 4, 15, 64):
+        nodes, order, last, bounds = S.build_wide8(thresh)
+        f = _wide_fields(nodes)
+        assert sorted(order.tolist()) == list(range(n))
+        eff = min(thresh, 15)
+        seen = np.zeros(n, np.int32)
+        child_seen = np.zeros(len(nodes), np.int32)
+        child_seen[0] = 1
+        # subtree bounds, children before parents (breadth-first numbering: children have larger indices)
+        sub_lo = np.zeros((len(nodes), 3)); sub_hi = np.zeros((len(nodes), 3))
+        for i in range(len(nodes) - 1, -1, -1):
+            cell = np.where(f["exp"][i] > 0, np.ldexp(1.0, f["exp"][i].astype(int) - 127), 0.0)
+            lo_all, hi_all = [], []
+            k_int = 0
+            for s in range(8):
+                m = int(f["meta"][i, s])
+                if m == 0:
+                    assert not (f["imask"][i] >> s) & 1
+                    continue
+                blo = f["origin"][i].astype(np.float64) + f["qlo"][i, :, s] * cell
+                bhi = f["origin"][i].astype(np.float64) + f["qhi"][i, :, s] * cell
+                if m & 0x80:
+                    assert (f["imask"][i] >> s) & 1
+                    c = int(f["child_base"][i]) + k_int
+                    k_int += 1
+                    child_seen[c] += 1
+                    clo, chi = sub_lo[c], sub_hi[c]
+                else:
+                    first = int(f["tri_base"][i]) + m - 1
+                    cnt = 1
+                    while not last[first + cnt - 1]:
+                        cnt += 1
+                    assert cnt <= eff
+                    seen[first:first + cnt] += 1
+                    faces = order[first:first + cnt]
+                    clo, chi = tlo[faces].min(axis=0), thi[faces].max(axis=0)
+                assert np.all(blo <= clo) and np.all(bhi >= chi), "quantised child box does not contain its content"
+                lo_all.append(clo); hi_all.append(chi)
+            sub_lo[i] = np.min(lo_all, axis=0); sub_hi[i] = np.max(hi_all, axis=0)
+            assert np.all(f["origin"][i] <= sub_lo[i])
+        assert (seen == 1).all() and (child_seen == 1).all()
+        assert np.array_equal(sub_lo[0].astype(np.float32), bounds[:3]) and np.array_equal(sub_hi[0].astype(np.float32), bounds[3:])
+
+
+def test_wide8_traversal_equals_pair_bvh_and_brute_force(orc, scene_files):
+    rng = np.random.default_rng(8)
+    verts = soup(rng, 3000)
+    verts[:200, [2, 5, 8]] = 0.5                           # a flat sheet
+    S = orc.Scene().add_arrays(verts, np.zeros(3000, np.int32), np.zeros(3000, np.int32), [[.5, .5, .5, 0, 0, 0, 1]])
+    for thresh in (1, 2, 4, 9):
+        S.build_new_bvh(thresh)
+        S.build_wide8(thresh)
+        for any_mode in (0, 1):
+            rays = random_rays(rng, [-12] * 3, [12] * 3, 4000, tmax_any=bool(any_mode))
+            rays[:50, 4:7] = [1, 0, 0]                     # axis-aligned directions: infinite inverse components
+            rays[50:100, 4:7] = [0, 0, -1]
+            t0, f0 = S.trace(rays, which=0, mode=any_mode)
+            t3, f3 = S.trace(rays, which=3, mode=any_mode)
+            t4, f4, st = S.trace(rays, which=4, mode=any_mode, want_stats=True)
+            if any_mode == 0:
+                assert np.array_equal(f4, f3) and np.array_equal(t4.view(np.uint32), t3.view(np.uint32))
+                assert np.array_equal(f4, f0)
+            else:
+                assert np.array_equal(f4 >= 0, f3 >= 0)
+            assert st["max_stack"] < 48
+    # the shipped scenes: fewer than 40 % of the pair-node visits, same hits
+    for name in ("cornell-box", "veach-mis"):
+        S = orc.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+        nodes, order, last, bounds = S.build_new_bvh(2)
+        S.build_wide8(2)
+        rays = random_rays(rng, bounds[:3], bounds[3:], 50000)
+        t0, f0, s0 = S.trace(rays, which=0, mode=0, want_stats=True)
+        t4, f4, s4 = S.trace(rays, which=4, mode=0, want_stats=True)
+        assert np.array_equal(f4, f0) and np.array_equal(t4.view(np.uint32), t0.view(np.uint32))
+        assert s4["inner"] < 0.4 * s0["inner"]
+
+
+def test_wide8_degenerate_inputs_and_render(orc, scene_files):
+    one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    for n in (1, 2, 3, 9):
+        verts = np.repeat(one, n, axis=0) + np.arange(n, dtype=np.float32)[:, None]
+        S = orc.Scene().add_arrays(verts, np.zeros(n, np.int32), np.zeros(n, np.int32), [[.5, .5, .5, 0, 0, 0, 1]])
+        for thresh in (1, 2, 5):
+            nodes, order, last, _ = S.build_wide8(thresh)
+            assert len(nodes) >= 1 and last[-1] == 1 and sorted(order.tolist()) == list(range(n))
+            rays = np.array([[0.2 + (n - 1), 0.2 + (n - 1), -1 + (n - 1), 3e38, 0, 0, 1, 0]], np.float32)
+            t, f = S.trace(rays, which=4)
+            tb, fb = S.trace(rays, which=3)
+            assert f[0] == fb[0] == n - 1 and t[0] == tb[0]
+    same = np.repeat(one, 300, axis=0)                      # identical triangles: a deep chain of duplicate keys
+    S = orc.Scene().add_arrays(same, np.zeros(300, np.int32), np.zeros(300, np.int32), [[.5, .5, .5, 0, 0, 0, 1]])
+    S.build_wide8(2)
+    t, f = S.trace(np.array([[0.2, 0.2, -1, 3e38, 0, 0, 1, 0]], np.float32), which=4)
+    assert f[0] == 0 and t[0] == 1.0
+    S = orc.Scene()
+    nodes, _, _, _ = S.build_wide8(2)                       # empty scene
+    assert len(nodes) == 0
+    # rendering through the wide BVH gives the same fixed-point image
+    name = "veach-mis"
+    S = orc.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    S.build_new_bvh(2); S.build_wide8(2)
+    M = orc.inverse_view_matrix([28.2792, 5.2, 1.23612e-06], [0, 2.8, 0], [0, 1, 0])
+    a0, s0 = S.render([28.2792, 5.2, 1.23612e-06], M, 0.5256, 80, 60, 0, 2, 0.6, 1)
+    a1, s1 = S.render([28.2792, 5.2, 1.23612e-06], M, 0.5256, 80, 60, 0, 2, 0.6, 1, wide=True)
+    assert np.array_equal(a0, a1) and s0["shadow_rays"] == s1["shadow_rays"]
+    assert s1["closest_inner"] < s0["closest_inner"]
