@@ -40,6 +40,7 @@ class Workload:
         import numpy as np
         import cudaraytracing_b200 as crt
         self.name = name
+        self.builder = {"lbvh": 0, "lbvh8": 1}[os.environ.get("CRT_BUILDER", "lbvh")]
         source, W, H, spp, self.desc = WORKLOADS[name]
         self.source = source
         self.tmp = tempfile.mkdtemp(prefix="crt_bench_")
@@ -73,7 +74,7 @@ class Workload:
             scene = crt.Scene().add_obj(self.obj, self.tmp)
         else:
             scene = crt.Scene().add_triangles(*self.arrays())
-        return scene, scene.set_BVH(self.bvh_thresh_n, device=device)
+        return scene, scene.set_BVH(self.bvh_thresh_n, builder=self.builder, device=device)
 
     def build_oracle(self, orc):
         import numpy as np
@@ -522,8 +523,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--builder", default=None, choices=["lbvh", "lbvh8"], help="BVH node layout (default: CRT_BUILDER or lbvh)")
     ap.add_argument("--ref-spp", type=int, default=4, help="reference arm: samples per pixel of the bounded sample (<=0: full)")
     args = ap.parse_args()
+    if args.builder:
+        os.environ["CRT_BUILDER"] = args.builder
     if args.impl == "reference":
         reference(args)
     elif args.workload == "c5":

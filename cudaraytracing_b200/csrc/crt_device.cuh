@@ -175,6 +175,24 @@ CRT_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float h
 
 struct HitRec { float t; int slot; int face; };
 
+// One 64-byte pair node. CRT_LD256 = 1: two 256-bit loads (LDG.E.256, sm_100+) instead of four 128-bit ones -
+// the traversal kernels are bound by L1 data-pipe wavefronts (profiles/r01_s11.md), which are paid per load
+// instruction and distinct line.
+#ifndef CRT_LD256
+#define CRT_LD256 0
+#endif
+CRT_DEV void load_node(const float4* __restrict__ nodes, int cur, float4& n0, float4& n1, float4& n2, float4& n3) {
+    const float4* p = nodes + 4 * (size_t)cur;
+#if CRT_LD256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(p));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w) : "l"(p + 2));
+#else
+    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
+#endif
+}
+
 // MODE 0: closest hit, t > 1e-5, ties -> lower face id (reference DeviceBVH.cuh:128-170 semantics
 //         made BVH-independent). MODE 1: any hit with t > 1e-5 && tmax - t > 1e-5 (the decision of
 //         reference Render.cuh:19-27, with early exit).
@@ -191,10 +209,8 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
     for (;;) {
         if (cur >= 0) {
             if (cur == kEmptyChild) { if (sp == 0) break; cur = stack[--sp]; continue; }
-            const float4 n0 = __ldg(sc.nodes + 4 * (size_t)cur + 0);
-            const float4 n1 = __ldg(sc.nodes + 4 * (size_t)cur + 1);
-            const float4 n2 = __ldg(sc.nodes + 4 * (size_t)cur + 2);
-            const float4 n3 = __ldg(sc.nodes + 4 * (size_t)cur + 3);
+            float4 n0, n1, n2, n3;
+            load_node(sc.nodes, cur, n0, n1, n2, n3);
             const float lim = tlimit * 1.0001f;
             float e0, e1;
             const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);
@@ -304,10 +320,8 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
             while (cur >= 0 && cur != kDone && (STRAT == 0 || first)) {
                 first = false;
                 if (cur == kEmptyChild) { cur = sp ? stack[--sp] : kDone; continue; }   // absent child of a one-leaf scene
-                const float4 n0 = __ldg(sc.nodes + 4 * (size_t)cur + 0);
-                const float4 n1 = __ldg(sc.nodes + 4 * (size_t)cur + 1);
-                const float4 n2 = __ldg(sc.nodes + 4 * (size_t)cur + 2);
-                const float4 n3 = __ldg(sc.nodes + 4 * (size_t)cur + 3);
+                float4 n0, n1, n2, n3;
+                load_node(sc.nodes, cur, n0, n1, n2, n3);
                 const float lim = tlimit * 1.0001f;
                 float e0, e1;
                 const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);
@@ -423,10 +437,8 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                 if (cur == kEmptyChild) {
                     cur = sp ? stack[--sp] : kDone;
                 } else {
-                    const float4 n0 = __ldg(sc.nodes + 4 * (size_t)cur + 0);
-                    const float4 n1 = __ldg(sc.nodes + 4 * (size_t)cur + 1);
-                    const float4 n2 = __ldg(sc.nodes + 4 * (size_t)cur + 2);
-                    const float4 n3 = __ldg(sc.nodes + 4 * (size_t)cur + 3);
+                    float4 n0, n1, n2, n3;
+                    load_node(sc.nodes, cur, n0, n1, n2, n3);
                     const float lim = tlimit * 1.0001f;
                     float e0, e1;
                     const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);

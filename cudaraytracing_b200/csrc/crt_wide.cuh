@@ -21,7 +21,9 @@ namespace crt {
 
 static constexpr int kWideStack = 48;      // one entry per wide-tree level at most; the builder refuses deeper trees
 
-CRT_DEV float wide_byte(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+// byte k of w as a float, exactly: PRMT puts the byte under the exponent of 2^23 and one FADD removes the 2^23
+// (I2F.U8 is a quarter-rate XU instruction; 48 of them per node step made the wide kernels XU-bound).
+CRT_DEV float wide_byte(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)k)) - 8388608.0f; }
 
 struct WideStep {
     uint32_t node_hits, leaf_hits;     // priority space: bit (slot ^ octant), visited in descending order
