@@ -105,6 +105,10 @@ def load_library():
         "crt_render_set_stream": [vp, vp],
         "crt_render_set_stage_timing": [vp, i32],
         "crt_render_run_view": [vp, vp, vp, f32],
+        "crt_render_set_accumulate": [vp, i32],
+        "crt_render_clear_accum": [vp],
+        "crt_render_save_checkpoint": [vp, C.c_char_p, u64],
+        "crt_render_load_checkpoint": [vp, C.c_char_p, C.POINTER(u64), vp, vp, C.POINTER(f32)],
         "crt_render_device_accum": [vp, pp],
         "crt_render_get_accum_i64": [vp, vp],
         "crt_render_get_accum": [vp, vp],
@@ -343,6 +347,23 @@ class Render:
         e = np.ascontiguousarray(eye_pos, np.float32)
         m = np.ascontiguousarray(inv_view_mat, np.float32).reshape(9)
         _check(self.L.crt_render_run_view(self.h, _p(e), _p(m), float(fovY)))
+
+    def set_accumulate(self, on):
+        """Progressive rendering: run_view adds its work range to the accumulation buffer instead of clearing it."""
+        _check(self.L.crt_render_set_accumulate(self.h, 1 if on else 0))
+
+    def clear_accum(self):
+        _check(self.L.crt_render_clear_accum(self.h))
+
+    def save_checkpoint(self, path, work_done):
+        _check(self.L.crt_render_save_checkpoint(self.h, str(path).encode(), int(work_done)))
+
+    def load_checkpoint(self, path):
+        """Returns (work_done, eye, inv_view 3x3, fovy_rad) of the checkpoint; the handle continues to accumulate."""
+        wd, fov = C.c_uint64(), C.c_float()
+        eye, M = np.zeros(3, np.float32), np.zeros(9, np.float32)
+        _check(self.L.crt_render_load_checkpoint(self.h, str(path).encode(), C.byref(wd), _p(eye), _p(M), C.byref(fov)))
+        return wd.value, eye, M.reshape(3, 3), np.float32(fov.value)
 
     def device_accum_ptr(self):
         p = C.c_void_p()

@@ -1,7 +1,9 @@
 // crt_api.cu — the C-ABI of include/crt.h. Thin glue: argument checks, handle state, error slot.
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "crt_gpu.h"
@@ -25,7 +27,34 @@ struct crt_render {
     float* d_linear = nullptr;
     uint8_t* d_rgb8 = nullptr;
     crt_render_stats stats{};
+    // camera of the last run_view (or of the loaded checkpoint): what the accumulation buffer belongs to
+    bool cam_set = false;
+    float cam_eye[3] = {0, 0, 0}, cam_M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, cam_fovy = 0;
 };
+
+// Checkpoint file: this header, then width*height*3 int64 (little endian).
+struct CheckpointHeader {
+    char magic[8];
+    uint32_t width, height, spp, seed, estimator, light_sample_n;
+    float p_rr;
+    uint32_t reserved;
+    uint64_t work_done;
+    float eye[3], M[9], fovy;
+    uint32_t pad;
+    uint64_t payload_bytes, payload_fnv1a;
+};
+static const char kCkptMagic[8] = {'C', 'R', 'T', 'C', 'K', 'P', 'T', '1'};
+static uint64_t fnv1a64(const void* data, size_t n) {
+    // 8 bytes at a time (word-wise FNV-1a variant; n is a multiple of 8 here)
+    const uint64_t* p = (const uint64_t*)data;
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n / 8; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+static bool same_camera(const crt_render* r, const float eye[3], const float M[9], float fovy) {
+    return memcmp(r->cam_eye, eye, sizeof(r->cam_eye)) == 0 && memcmp(r->cam_M, M, sizeof(r->cam_M)) == 0 &&
+           memcmp(&r->cam_fovy, &fovy, sizeof(float)) == 0;
+}
 
 namespace crt {
 int cuda_fail(cudaError_t e, const char* what) {
@@ -327,10 +356,95 @@ int crt_render_set_stage_timing(crt_render* r, int on) {
 int crt_render_run_view(crt_render* r, const float eye[3], const float inv_view[9], float fovy_rad) {
     CHECK_ARG(r && eye && inv_view, "crt_render_run_view: null argument");
     CRT_CUDA(cudaSetDevice(r->scene->dev.device));
+    if (r->rs.accumulate && r->cam_set && !same_camera(r, eye, inv_view, fovy_rad)) {
+        set_error("crt_render_run_view: accumulate is on and the camera differs from the one the accumulation buffer belongs to "
+                  "(crt_render_clear_accum first)");
+        return CRT_ERR_STATE;
+    }
+    memcpy(r->cam_eye, eye, sizeof(r->cam_eye)); memcpy(r->cam_M, inv_view, sizeof(r->cam_M)); r->cam_fovy = fovy_rad;
+    r->cam_set = true;
     float tan_half = tanf(fovy_rad / 2);                          // Render.cuh:338, evaluated on the host
     int rc = wavefront_render(r->wf, r->scene->dev, r->rs, eye, inv_view, tan_half, r->stream, &r->stats);
     r->rendered = rc == CRT_OK;
     return rc;
+}
+
+int crt_render_set_accumulate(crt_render* r, int on) {
+    CHECK_ARG(r, "crt_render_set_accumulate: null handle");
+    r->rs.accumulate = on != 0;
+    return CRT_OK;
+}
+int crt_render_clear_accum(crt_render* r) {
+    CHECK_ARG(r, "crt_render_clear_accum: null handle");
+    CRT_CUDA(cudaSetDevice(r->scene->dev.device));
+    CRT_CUDA(cudaMemsetAsync(wavefront_accum(r->wf), 0, sizeof(int64_t) * 3 * (size_t)r->rs.width * r->rs.height, r->stream));
+    CRT_CUDA(cudaStreamSynchronize(r->stream));
+    r->cam_set = false;
+    return CRT_OK;
+}
+
+int crt_render_save_checkpoint(crt_render* r, const char* path, uint64_t work_done) {
+    CHECK_ARG(r && path, "crt_render_save_checkpoint: null argument");
+    if (!r->cam_set) { set_error("crt_render_save_checkpoint: nothing rendered yet"); return CRT_ERR_STATE; }
+    CRT_CUDA(cudaSetDevice(r->scene->dev.device));
+    const size_t n = 3 * (size_t)r->rs.width * r->rs.height;
+    std::vector<int64_t> buf(n);
+    CRT_CUDA(cudaMemcpy(buf.data(), wavefront_accum(r->wf), sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+    CheckpointHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, kCkptMagic, 8);
+    h.width = r->rs.width; h.height = r->rs.height; h.spp = r->rs.spp; h.seed = r->rs.seed; h.estimator = (uint32_t)r->rs.estimator;
+    h.light_sample_n = r->rs.light_sample_n; h.p_rr = r->rs.p_rr; h.work_done = work_done;
+    memcpy(h.eye, r->cam_eye, sizeof(h.eye)); memcpy(h.M, r->cam_M, sizeof(h.M)); h.fovy = r->cam_fovy;
+    h.payload_bytes = sizeof(int64_t) * n;
+    h.payload_fnv1a = fnv1a64(buf.data(), h.payload_bytes);
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { set_error(std::string("crt_render_save_checkpoint: cannot open ") + tmp); return CRT_ERR_IO; }
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(buf.data(), sizeof(int64_t), n, f) == n;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); set_error(std::string("crt_render_save_checkpoint: write failed: ") + path); return CRT_ERR_IO; }
+    return CRT_OK;
+}
+
+int crt_render_load_checkpoint(crt_render* r, const char* path, uint64_t* work_done, float eye[3], float inv_view[9], float* fovy_rad) {
+    CHECK_ARG(r && path, "crt_render_load_checkpoint: null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error(std::string("crt_render_load_checkpoint: cannot open ") + path); return CRT_ERR_IO; }
+    CheckpointHeader h;
+    const size_t n = 3 * (size_t)r->rs.width * r->rs.height;
+    std::vector<int64_t> buf;
+    int rc = CRT_OK;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kCkptMagic, 8) != 0) {
+        set_error(std::string("crt_render_load_checkpoint: not a checkpoint file: ") + path); rc = CRT_ERR_IO;
+    } else if (h.width != r->rs.width || h.height != r->rs.height || h.spp != r->rs.spp || h.seed != r->rs.seed ||
+               h.estimator != (uint32_t)r->rs.estimator || h.light_sample_n != r->rs.light_sample_n ||
+               memcmp(&h.p_rr, &r->rs.p_rr, sizeof(float)) != 0) {
+        set_error("crt_render_load_checkpoint: the checkpoint was written with different render settings "
+                  "(width, height, spp, seed, estimator, P_RR, light_sample_n must match)");
+        rc = CRT_ERR_STATE;
+    } else if (h.payload_bytes != sizeof(int64_t) * n) {
+        set_error("crt_render_load_checkpoint: payload size does not match the image size"); rc = CRT_ERR_IO;
+    } else {
+        buf.resize(n);
+        char extra;
+        if (fread(buf.data(), sizeof(int64_t), n, f) != n || fread(&extra, 1, 1, f) != 0 || fnv1a64(buf.data(), h.payload_bytes) != h.payload_fnv1a) {
+            set_error(std::string("crt_render_load_checkpoint: truncated or corrupt checkpoint: ") + path); rc = CRT_ERR_IO;
+        }
+    }
+    fclose(f);
+    if (rc != CRT_OK) return rc;
+    CRT_CUDA(cudaSetDevice(r->scene->dev.device));
+    CRT_CUDA(cudaMemcpy(wavefront_accum(r->wf), buf.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice));
+    memcpy(r->cam_eye, h.eye, sizeof(h.eye)); memcpy(r->cam_M, h.M, sizeof(h.M)); r->cam_fovy = h.fovy;
+    r->cam_set = true;
+    r->rs.accumulate = true;
+    r->rendered = true;
+    if (work_done) *work_done = h.work_done;
+    if (eye) memcpy(eye, h.eye, sizeof(h.eye));
+    if (inv_view) memcpy(inv_view, h.M, sizeof(h.M));
+    if (fovy_rad) *fovy_rad = h.fovy;
+    return CRT_OK;
 }
 
 int crt_render_device_accum(crt_render* r, void** d_accum) {

@@ -161,7 +161,7 @@ CRT_DEV bool tri_test(V3 v1, V3 e1, V3 e2, V3 o, V3 d, float* t_out) {
     return 0.0f < alpha && alpha < 1.0f && 0.0f < beta && beta < 1.0f && 0.0f < gamma && gamma < 1.0f;
 }
 
-// Conservative slab test (DESIGN.md "Traversal rule").
+// Conservative slab test (DESIGN.md "Traversal rule"). NaN plane distances drop out of fminf / fmaxf.
 CRT_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, V3 o, V3 inv, float limit,
                   float* enter) {
     float tx0 = (lox - o.x) * inv.x, tx1 = (hix - o.x) * inv.x;
@@ -173,7 +173,18 @@ CRT_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float h
     return tmin <= tmax * 1.0000004f;
 }
 
+// Inverse direction for the box tests: 1/d, and NaN for a component that is exactly zero, so that this axis never
+// culls (every plane distance on it is NaN and drops out of fminf / fmaxf). With 1/0 = inf a ray lying IN a box
+// plane (o.x == plane) gave 0 * inf = NaN on that plane and +-inf on the other, min(NaN, +inf) = +inf emptied the
+// slab, and the traversal dropped boxes whose triangles the Moeller-Trumbore test accepts; the same happens when the
+// origin (a computed hit point) sits one ulp outside a box whose triangle still passes the test. Exact zeros are not
+// rare: sincos_2pi is exact at the quadrants. Found by the wide-node render (profiles/r01_s12_wide_vs_pair.md).
+// Statement: oracle/orc_math.h box_inv.
+CRT_DEV float box_inv(float x) { return x == 0.0f ? __int_as_float(0x7fc00000) : 1.0f / x; }
+CRT_DEV V3 box_inv3(V3 d) { return mk3(box_inv(d.x), box_inv(d.y), box_inv(d.z)); }
+
 struct HitRec { float t; int slot; int face; };
+
 
 // One 64-byte pair node. CRT_LD256 = 1: two 256-bit loads (LDG.E.256, sm_100+) instead of four 128-bit ones -
 // the traversal kernels are bound by L1 data-pipe wavefronts (profiles/r01_s11.md), which are paid per load
@@ -201,7 +212,7 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
     HitRec best;
     best.t = FLT_MAX; best.slot = -1; best.face = -1;
     if (sc.n_nodes == 0) return best;
-    const V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const V3 inv = box_inv3(d);
     float tlimit = MODE == 0 ? FLT_MAX : tmax;
     int stack[kStackSize];
     int sp = 0;
@@ -298,7 +309,7 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
                     if (i < n) {
                         idx = i;
                         const bool live = load(i, o, d, tmax);
-                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        inv = box_inv3(d);
                         tlimit = MODE == 0 ? FLT_MAX : tmax;
                         best.t = FLT_MAX; best.slot = -1; best.face = -1;
                         sp = 0;
@@ -522,7 +533,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                         V3 d;
                         float tmax;
                         const bool live = load(i, o, d, tmax);
-                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        inv = box_inv3(d);
                         tlimit = MODE == 0 ? FLT_MAX : tmax;
                         q.ox[lane] = o.x; q.oy[lane] = o.y; q.oz[lane] = o.z;
                         q.dx[lane] = d.x; q.dy[lane] = d.y; q.dz[lane] = d.z;

@@ -70,6 +70,7 @@ struct RenderSettings {
     unsigned long long work_begin = 0, work_end = 0;
     bool range_set = false;
     bool stage_timing = false;
+    bool accumulate = false;         // run_view adds to the accumulation buffer instead of clearing it (progressive rendering)
 };
 
 struct Wavefront;   // opaque pipeline state (crt_render.cu)

@@ -45,8 +45,9 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 int main(int argc, char** argv) {
     std::string config = "config.json", out = "out.png", root = ".";
-    long spp = -1, seed = -1, width = -1, height = -1;
-    int estimator = -1, device = 0;
+    std::string checkpoint;
+    long spp = -1, seed = -1, width = -1, height = -1, chunk_spp = 64, stop_after = -1;
+    int estimator = -1, device = 0, builder = CRT_BUILDER_LBVH;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -59,9 +60,16 @@ int main(int argc, char** argv) {
         else if (a == "--height") height = atol(next());
         else if (a == "--device") device = atoi(next());
         else if (a == "--estimator") { std::string e = next(); estimator = e == "mis" ? CRT_ESTIMATOR_MIS : CRT_ESTIMATOR_COMPAT; }
+        else if (a == "--builder") { std::string e = next(); builder = e == "lbvh8" ? CRT_BUILDER_LBVH8 : CRT_BUILDER_LBVH; }
+        else if (a == "--checkpoint") checkpoint = next();
+        else if (a == "--chunk-spp") chunk_spp = atol(next());
+        else if (a == "--stop-after") stop_after = atol(next());
         else if (a == "--help" || a == "-h") {
             printf("usage: crt --config config.json [--root DIR] [--out image.png] [--spp N] [--seed S]\n"
-                   "           [--width W --height H] [--estimator compat|mis] [--device D]\n");
+                   "           [--width W --height H] [--estimator compat|mis] [--builder lbvh|lbvh8] [--device D]\n"
+                   "           [--checkpoint FILE [--chunk-spp N] [--stop-after CHUNKS]]\n"
+                   "  --checkpoint: progressive render in chunks of N samples per pixel (default 64); FILE is rewritten after\n"
+                   "                every chunk and, if it exists at start, the render resumes from it (bit-identical image).\n");
             return 0;
         } else { fprintf(stderr, "crt: unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -84,7 +92,7 @@ int main(int argc, char** argv) {
     }
     double t1 = now_ms();
     float build_ms = 0;
-    DIE_IF(crt_scene_build_bvh(scene, cfg.bvh_thresh_n, CRT_BUILDER_LBVH, device, &build_ms), "build_bvh");
+    DIE_IF(crt_scene_build_bvh(scene, cfg.bvh_thresh_n, builder, device, &build_ms), "build_bvh");
     double t2 = now_ms();
     uint64_t n_tris = 0, n_nodes = 0; uint32_t n_mats = 0, n_lights = 0;
     crt_scene_counts(scene, &n_tris, &n_mats, &n_lights, &n_nodes);
@@ -98,19 +106,62 @@ int main(int argc, char** argv) {
     DIE_IF(crt_render_set_estimator(render, (int)cfg.estimator), "set_estimator");
     float M[9];
     crt_inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up, M);
+    const float fovy_rad = cfg.fov_y * (float)M_PI / 180.0f;
     double t3 = now_ms();
-    DIE_IF(crt_render_run_view(render, cfg.eye_pos, M, cfg.fov_y * (float)M_PI / 180.0f), "run_view");   // main.cu:372
+    crt_render_stats st;
+    uint64_t samples_rendered = (uint64_t)cfg.width * cfg.height * cfg.spp, resumed_from = 0;
+    if (checkpoint.empty()) {
+        DIE_IF(crt_render_run_view(render, cfg.eye_pos, M, fovy_rad), "run_view");   // main.cu:372
+        crt_render_get_stats(render, &st);
+    } else {
+        // progressive render with checkpoint / resume: chunks of the sample-major work index space
+        const uint64_t npix = (uint64_t)cfg.width * cfg.height, total = npix * cfg.spp;
+        const uint64_t chunk = npix * (uint64_t)(chunk_spp > 0 ? chunk_spp : 64);
+        uint64_t done = 0;
+        crt_render_set_accumulate(render, 1);
+        if (exists(checkpoint)) {
+            float ce[3], cM[9], cf;
+            DIE_IF(crt_render_load_checkpoint(render, checkpoint.c_str(), &done, ce, cM, &cf), "load_checkpoint");
+            if (memcmp(ce, cfg.eye_pos, sizeof(ce)) || memcmp(cM, M, sizeof(cM)) || memcmp(&cf, &fovy_rad, sizeof(cf))) {
+                fprintf(stderr, "crt: checkpoint %s was rendered with a different camera\n", checkpoint.c_str());
+                return 1;
+            }
+            resumed_from = done;
+        } else {
+            DIE_IF(crt_render_clear_accum(render), "clear_accum");
+        }
+        memset(&st, 0, sizeof(st));
+        long chunks = 0;
+        while (done < total) {
+            const uint64_t end = done + chunk < total ? done + chunk : total;
+            crt_render_set_work_range(render, done, end);
+            DIE_IF(crt_render_run_view(render, cfg.eye_pos, M, fovy_rad), "run_view");
+            crt_render_stats c;
+            crt_render_get_stats(render, &c);
+            st.ms_total += c.ms_total; st.extend_rays += c.extend_rays; st.shadow_rays += c.shadow_rays; st.probe_rays += c.probe_rays;
+            st.iterations += c.iterations; st.kernel_launches += c.kernel_launches; st.samples += c.samples;
+            done = end;
+            DIE_IF(crt_render_save_checkpoint(render, checkpoint.c_str(), done), "save_checkpoint");
+            if (stop_after > 0 && ++chunks >= stop_after) break;
+        }
+        samples_rendered = st.samples;
+        if (done < total) {
+            printf("{\"checkpoint\": \"%s\", \"work_done\": %llu, \"work_total\": %llu, \"resumed_from\": %llu, \"complete\": false}\n",
+                   checkpoint.c_str(), (unsigned long long)done, (unsigned long long)total, (unsigned long long)resumed_from);
+            crt_render_destroy(render);
+            crt_scene_destroy(scene);
+            return 0;
+        }
+    }
     double t4 = now_ms();
     DIE_IF(crt_render_save_png(render, out.c_str()), "save_png");
-    crt_render_stats st;
-    crt_render_get_stats(render, &st);
-    double msamples = (double)cfg.width * cfg.height * cfg.spp / (st.ms_total * 1e3);
+    double msamples = st.ms_total > 0 ? (double)samples_rendered / (st.ms_total * 1e3) : 0.0;
     printf("{\"triangles\": %llu, \"nodes\": %llu, \"materials\": %u, \"lights\": %u, \"load_ms\": %.2f, \"bvh_build_gpu_ms\": %.3f, "
            "\"upload_and_build_ms\": %.2f, \"render_ms\": %.3f, \"render_wall_ms\": %.2f, \"msamples_per_s\": %.2f, "
-           "\"extend_rays\": %llu, \"shadow_rays\": %llu, \"probe_rays\": %llu, \"iterations\": %llu, \"out\": \"%s\"}\n",
+           "\"extend_rays\": %llu, \"shadow_rays\": %llu, \"probe_rays\": %llu, \"iterations\": %llu, \"resumed_from\": %llu, \"out\": \"%s\"}\n",
            (unsigned long long)n_tris, (unsigned long long)n_nodes, n_mats, n_lights, t1 - t0, build_ms, t2 - t1, st.ms_total, t4 - t3,
            msamples, (unsigned long long)st.extend_rays, (unsigned long long)st.shadow_rays, (unsigned long long)st.probe_rays,
-           (unsigned long long)st.iterations, out.c_str());
+           (unsigned long long)st.iterations, (unsigned long long)resumed_from, out.c_str());
     crt_render_destroy(render);
     crt_scene_destroy(scene);
     return 0;

@@ -633,8 +633,11 @@ CRT_DEV void probe_resolve(const SceneView& sc, int probe_slot, V3 w, uint32_t p
 }
 
 // EST: CRT_ESTIMATOR_COMPAT (0) or CRT_ESTIMATOR_MIS (1)
+#ifndef CRT_SHADE_MINB
+#define CRT_SHADE_MINB 1
+#endif
 template <int EST>
-__global__ void __launch_bounds__(128) k_shade(SceneView sc, Counters* c, RenderParamsDev p,
+__global__ void __launch_bounds__(128, CRT_SHADE_MINB) k_shade(SceneView sc, Counters* c, RenderParamsDev p,
                                                       const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                       const float4* __restrict__ q_T, const float* __restrict__ q_pdf,
                                                       float* __restrict__ n_pdf, const float* __restrict__ hit_t,
@@ -906,7 +909,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     w->status_host->done = 0;
     w->status_host->n_cur = 0;
     CRT_CUDA(cudaEventRecord(w->ev_begin, st));
-    CRT_CUDA(cudaMemsetAsync(w->accum, 0, sizeof(long long) * 3 * npix, st));
+    if (!rs.accumulate) CRT_CUDA(cudaMemsetAsync(w->accum, 0, sizeof(long long) * 3 * npix, st));
     CRT_CUDA(cudaMemcpyAsync(w->counters, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     const SceneView sv = ds.view();
     const bool wide = ds.wide;

@@ -25,6 +25,12 @@ static constexpr int kWideStack = 48;      // one entry per wide-tree level at m
 // (I2F.U8 is a quarter-rate XU instruction; 48 of them per node step made the wide kernels XU-bound).
 CRT_DEV float wide_byte(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)k)) - 8388608.0f; }
 
+// 4-bit mask of the non-zero bytes of w (bit k = byte k != 0)
+CRT_DEV uint32_t wide_nonzero_bytes(uint32_t w) {
+    const uint32_t t = (w | ((w & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;      // bit 7 of every non-zero byte
+    return (((t >> 7) * 0x01020408u) >> 24) & 0xfu;                                // bits 0, 8, 16, 24 -> bits 24..27
+}
+
 struct WideStep {
     uint32_t node_hits, leaf_hits;     // priority space: bit (slot ^ octant), visited in descending order
     uint32_t child_base, tri_base, meta_lo, meta_hi, imask;
@@ -51,22 +57,27 @@ CRT_DEV WideStep wide_node_test(const uint4* __restrict__ nodes, uint32_t ni, V3
     const uint32_t ny[2] = {py ? w2.z : w4.x, py ? w2.w : w4.y}, fy[2] = {py ? w4.x : w2.z, py ? w4.y : w2.w};
     const uint32_t nz[2] = {pz ? w3.x : w4.z, pz ? w3.y : w4.w}, fz[2] = {pz ? w4.z : w3.x, pz ? w4.w : w3.y};
     WideStep r;
-    r.node_hits = 0; r.leaf_hits = 0;
     r.child_base = w1.x; r.tri_base = w1.y; r.meta_lo = w1.z; r.meta_hi = w1.w; r.imask = ew >> 24;
+    uint32_t hits = 0;                                     // slot space: bit c = the box of child c is hit
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const int w = c >> 2, k = c & 3;
-        const uint32_t m = ((w ? w1.w : w1.z) >> (8 * k)) & 0xffu;
         const float tnx = fmaf(wide_byte(nx[w], k), bx, ax), tfx = fmaf(wide_byte(fx[w], k), bx, ax);
         const float tny = fmaf(wide_byte(ny[w], k), by, ay), tfy = fmaf(wide_byte(fy[w], k), by, ay);
         const float tnz = fmaf(wide_byte(nz[w], k), bz, az), tfz = fmaf(wide_byte(fz[w], k), bz, az);
         const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
         const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, lim));
-        if (m != 0u && tmin <= fmaf(tmax, 1.0000004f, pad)) {
-            const uint32_t bit = 1u << ((uint32_t)c ^ oinv);
-            if (m & 0x80u) r.node_hits |= bit; else r.leaf_hits |= bit;
-        }
+        if (tmin <= fmaf(tmax, 1.0000004f, pad)) hits |= 1u << c;
     }
+    // children that exist (meta byte != 0), 4 bits per meta word, then node / leaf children from imask
+    hits &= wide_nonzero_bytes(w1.z) | (wide_nonzero_bytes(w1.w) << 4);
+    // slot space -> priority space (bit i -> bit i ^ oinv) for both masks at once: node hits in bits 0-7, leaf hits in 8-15
+    uint32_t both = (hits & r.imask) | ((hits & ~r.imask) << 8);
+    if (oinv & 1u) both = ((both & 0x5555u) << 1) | ((both >> 1) & 0x5555u);
+    if (oinv & 2u) both = ((both & 0x3333u) << 2) | ((both >> 2) & 0x3333u);
+    if (oinv & 4u) both = ((both & 0x0f0fu) << 4) | ((both >> 4) & 0x0f0fu);
+    r.node_hits = both & 0xffu;
+    r.leaf_hits = both >> 8;
     return r;
 }
 
@@ -85,7 +96,7 @@ CRT_DEV HitRec traverse_wide(const SceneView& sc, V3 o, V3 d, float tmax) {
     best.t = FLT_MAX; best.slot = -1; best.face = -1;
     if (sc.n_nodes == 0) return best;
     const uint4* nodes = (const uint4*)sc.nodes;
-    const V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const V3 inv = box_inv3(d);
     const uint32_t oinv = wide_octant(inv);
     float tlimit = MODE == 0 ? FLT_MAX : tmax;
     uint2 stack[kWideStack];
@@ -168,7 +179,7 @@ CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fe
                     if (i < n) {
                         idx = i;
                         const bool live = load(i, o, d, tmax);
-                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        inv = box_inv3(d);
                         oinv = wide_octant(inv);
                         tlimit = MODE == 0 ? FLT_MAX : tmax;
                         best.t = FLT_MAX; best.slot = -1; best.face = -1;
@@ -383,7 +394,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                         V3 d;
                         float tmax;
                         const bool live = load(i, o, d, tmax);
-                        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        inv = box_inv3(d);
                         oinv = wide_octant(inv);
                         tlimit = MODE == 0 ? FLT_MAX : tmax;
                         q.ox[lane] = o.x; q.oy[lane] = o.y; q.oz[lane] = o.z;

@@ -184,6 +184,22 @@ int crt_render_set_stream(crt_render* r, void* cuda_stream);
 /* Render::run_view, include/Render.cuh:435-475 (without the GL PBO). Blocking. Clears the
  * accumulation buffer, renders the sample range, leaves the fixed-point buffer on the device. */
 int crt_render_run_view(crt_render* r, const float eye[3], const float inv_view[9], float fovy_rad);
+/* Progressive rendering (the reference has no accumulation buffer, Render.cuh:342-350):
+ * on != 0 makes run_view ADD its work range to the accumulation buffer instead of clearing it first, so a frame can
+ * be rendered in chunks of the sample-major work index space (crt_render_set_sample_range / set_work_range). The
+ * buffer is integer, so any chunking gives the bit-identical image. crt_render_clear_accum zeroes the buffer. */
+int crt_render_set_accumulate(crt_render* r, int on);
+int crt_render_clear_accum(crt_render* r);
+/* Checkpoint / resume of a progressive render. save: writes the render settings, the camera of the last run_view,
+ * `work_done` (the caller's count of finished work items, w in [0, work_done)) and the int64 accumulation buffer to
+ * `path` (written to path.tmp, then renamed). load: the file's width, height, spp, seed, estimator, P_RR and
+ * light_sample_n must equal the handle's current settings (CRT_ERR_STATE otherwise; CRT_ERR_IO for a truncated or
+ * corrupt file - the payload carries an FNV-1a checksum); fills the accumulation buffer, turns accumulate on and
+ * returns work_done and the camera (any out pointer may be NULL). A later run_view with a different camera fails with
+ * CRT_ERR_STATE until crt_render_clear_accum is called. */
+int crt_render_save_checkpoint(crt_render* r, const char* path, uint64_t work_done);
+int crt_render_load_checkpoint(crt_render* r, const char* path, uint64_t* work_done, float eye[3], float inv_view[9],
+                               float* fovy_rad);
 /* Device pointer of the accumulation buffer: int64[width*height*3], radiance * 2^32 summed over
  * samples. Callers reduce it across GPUs (NCCL sum of int64) before resolving. */
 int crt_render_device_accum(crt_render* r, void** d_accum);

@@ -333,7 +333,7 @@ Hit new_intersect(const Scene& s, const NewBVH& b, const Ray& r, int mode, Trace
     if (st) st->rays++;
     if (b.nodes.empty()) return best;
     V3 o = r.o, d = r.d;
-    V3 inv{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    V3 inv{box_inv(d.x), box_inv(d.y), box_inv(d.z)};
     float tlimit = mode == 0 ? FLT_MAX : r.tmax;
     int stack[128];
     int sp = 0;
@@ -559,7 +559,7 @@ Hit wide8_intersect(const Scene& s, const Wide8BVH& b, const Ray& r, int mode, T
     if (st) st->rays++;
     if (b.nodes.empty()) return best;
     const V3 o = r.o, d = r.d;
-    const V3 inv{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    const V3 inv{box_inv(d.x), box_inv(d.y), box_inv(d.z)};
     const bool negx = inv.x < 0.0f, negy = inv.y < 0.0f, negz = inv.z < 0.0f;
     const uint32_t oinv = (negx ? 0u : 1u) | (negy ? 0u : 2u) | (negz ? 0u : 4u);
     float tlimit = mode == 0 ? FLT_MAX : r.tmax;

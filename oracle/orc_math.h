@@ -13,6 +13,7 @@
 // Under that contract the CPU oracle and the GPU kernels produce bit-identical floats, which is
 // what lets tests/ demand exact equality of hit ids and of the fixed-point accumulation buffer.
 #pragma once
+#include <limits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -44,6 +45,11 @@ static inline V3 normalize(V3 a) {
     return a;
 }
 static inline float length(V3 a) { return sqrtf(dot(a, a)); }
+// Inverse direction for the box tests of the new traversal rules: 1/d, NaN for a component that is exactly zero, so
+// that this axis never culls (NaN plane distances drop out of fminf / fmaxf). With 1/0 = inf a ray lying in a box plane
+// made the pair-node slab empty (min(0 * inf, +inf) = +inf) and boxes were dropped whose triangles pass the triangle
+// test. The reference rule (ref_intersect) keeps the reference's plain 1/d (Ray.cuh:14).
+static inline float box_inv(float x) { return x == 0.0f ? std::numeric_limits<float>::quiet_NaN() : 1.0f / x; }
 static inline V3 vmin(V3 a, V3 b) { return V3{fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)}; }
 static inline V3 vmax(V3 a, V3 b) { return V3{fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}; }
 

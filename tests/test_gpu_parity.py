@@ -298,6 +298,117 @@ def test_mis_estimator_options_and_tail(gpu, orc, monkeypatch, tail):
     assert np.array_equal(total, full)
 
 
+@pytest.mark.parametrize("builder", [0, 1])
+@pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
+def test_rays_lying_in_box_planes(gpu, orc, scene_files, name, builder):
+    """Rays from surface points with one direction component exactly zero (they lie in box planes): the committed
+    regression rays and fresh ones, both node layouts, against the oracle (which equals brute force on them,
+    tests/test_oracle.py::test_rays_lying_in_box_planes_equal_brute_force)."""
+    from conftest import GOLDEN
+    from test_oracle import _surface_rays_with_zero_components
+    cfg = gpu.load_config(scene_files[name]["cfg_path"])
+    a = gpu.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    a.set_BVH(cfg.bvh_thresh_n, builder=builder)
+    b = orc.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    b.build_new_bvh(cfg.bvh_thresh_n)
+    z = np.load(os.path.join(GOLDEN, "axis_planar_rays.npz"))
+    batches = [(z[k], 1 if "_any_" in k else 0) for k in z.files if k.startswith(name)]
+    rng = np.random.default_rng(23)
+    fresh = _surface_rays_with_zero_components(orc, b, cfg, rng, n_max=40000)
+    batches.append((fresh, 0))
+    anyr = fresh.copy()
+    anyr[:, 3] = rng.uniform(0, 900.0 if name == "cornell-box" else 30.0, len(anyr)).astype(np.float32)
+    batches.append((anyr, 1))
+    for rays, mode in batches:
+        t, f, _ = a.trace_rays(rays, mode)
+        if mode == 0:
+            ot, of = b.trace(rays, which=0, mode=0)
+            assert np.array_equal(f, of) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+        else:
+            assert b.check_any_hits(rays, t, f)
+
+
+def test_progressive_chunks_and_checkpoint_resume(gpu, scene_files, tmp_path):
+    """a frame rendered in chunks (accumulate on), interrupted, saved, loaded into a fresh handle and
+    finished equals the frame rendered in one go, bit for bit; mismatching settings / camera / corrupt files are refused."""
+    name = "veach-mis"
+    cfg = gpu.load_config(scene_files[name]["cfg_path"])
+    a = gpu.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    a.set_BVH(cfg.bvh_thresh_n)
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    W, H, spp = 200, 150, 6
+    full = gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n)
+    full.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+    want = full.get_accum_i64()
+    png_full = str(tmp_path / "full.png")
+    full.save_frame_buffer(png_full)
+    npix = W * H
+    ck = str(tmp_path / "render.ckpt")
+    # first process: 2 chunks of ragged size, then "crash"
+    r1 = gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n)
+    r1.set_accumulate(True)
+    r1.clear_accum()
+    done = 0
+    for end in (npix + 777, 3 * npix + 5):
+        r1.set_work_range(done, end)
+        r1.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+        done = end
+        r1.save_checkpoint(ck, done)
+    with pytest.raises(gpu.CrtError) as e:        # accumulate on + another camera
+        r1.run_view(np.asarray(cfg.eye_pos) + 1.0, M, cfg.fovy_rad)
+    assert e.value.code == -5
+    del r1
+    # second process: resume
+    r2 = gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n)
+    wd, eye, Mc, fov = r2.load_checkpoint(ck)
+    assert wd == done and np.array_equal(eye, np.asarray(cfg.eye_pos, np.float32)) and np.array_equal(Mc.reshape(9), np.asarray(M, np.float32).reshape(9))
+    assert np.float32(fov) == np.float32(cfg.fovy_rad)
+    r2.set_work_range(wd, npix * spp)
+    r2.run_view(eye, Mc, fov)
+    assert np.array_equal(r2.get_accum_i64(), want)
+    png2 = str(tmp_path / "resumed.png")
+    r2.save_frame_buffer(png2)
+    assert open(png2, "rb").read() == open(png_full, "rb").read()
+    # refused: other settings, truncated file, flipped payload byte, not a checkpoint
+    r3 = gpu.Render(a, W, H, spp + 1, cfg.P_RR, cfg.light_sample_n)
+    with pytest.raises(gpu.CrtError) as e:
+        r3.load_checkpoint(ck)
+    assert e.value.code == -5
+    data = open(ck, "rb").read()
+    bad = str(tmp_path / "bad.ckpt")
+    for blob in (data[:-9], data[:200] + bytes([data[200] ^ 1]) + data[201:], b"not a checkpoint" * 10, data + b"x"):
+        open(bad, "wb").write(blob)
+        with pytest.raises(gpu.CrtError) as e:
+            gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n).load_checkpoint(bad)
+        assert e.value.code == -2
+    with pytest.raises(gpu.CrtError) as e:
+        gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n).save_checkpoint(ck, 0)      # nothing rendered yet
+    assert e.value.code == -5
+
+
+def test_cli_checkpoint_resume(gpu, scene_files, tmp_path):
+    import json
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "cudaraytracing_b200", "crt")
+    base = [exe, "--config", scene_files["veach-mis"]["cfg_path"], "--width", "160", "--height", "120", "--spp", "7"]
+    one = str(tmp_path / "one.png")
+    r = subprocess.run(base + ["--out", one], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ck, two = str(tmp_path / "c.ckpt"), str(tmp_path / "two.png")
+    r = subprocess.run(base + ["--out", two, "--checkpoint", ck, "--chunk-spp", "2", "--stop-after", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["complete"] is False and info["work_done"] == 4 * 160 * 120 and not os.path.exists(two)
+    r = subprocess.run(base + ["--out", two, "--checkpoint", ck, "--chunk-spp", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["resumed_from"] == 4 * 160 * 120
+    assert open(one, "rb").read() == open(two, "rb").read()
+    r = subprocess.run(base + ["--out", two, "--checkpoint", ck, "--seed", "5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "different render settings" in r.stderr
+
+
 def test_save_png_and_cli(gpu, scene_files, tmp_path):
     import subprocess
     import struct

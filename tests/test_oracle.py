@@ -113,6 +113,55 @@ def test_new_traversal_equals_brute_force(orc):
                 assert np.array_equal(f0 >= 0, f3 >= 0)       # the blocker found may differ, the decision may not
 
 
+def _surface_rays_with_zero_components(orc, S, cfg, rng, n_max=3000):
+    """Rays that start ON surfaces (primary hit points) with one direction component exactly zero - the case in which
+    a ray lies in a box plane: rays from the back wall with d.z == 0, from the ceiling with d.y == 0, ..."""
+    M = orc.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    rays = orc.primary_rays(cfg.eye_pos, M, float(cfg.fovy_rad), 200, 150)
+    t, f = S.trace(rays, which=0, mode=0)
+    hit = f >= 0
+    pos = (rays[hit, 0:3] + t[hit, None] * rays[hit, 4:7])[:n_max]
+    out = []
+    for axis in range(3):
+        d = rng.normal(size=(len(pos), 3)).astype(np.float32)
+        d[:, axis] = 0.0
+        d /= np.sqrt((d * d).sum(axis=1, keepdims=True)).astype(np.float32)
+        r = np.zeros((len(pos), 8), np.float32)
+        r[:, 0:3] = pos
+        r[:, 4:7] = d
+        r[:, 3] = np.finfo(np.float32).max
+        out.append(r)
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
+def test_rays_lying_in_box_planes_equal_brute_force(orc, crt, scene_files, name):
+    """Regression (found on the B200 by the wide-node render): with inv = 1/0 = inf a ray lying in a box plane made the
+    pair-node slab empty and the traversal missed triangles that brute force hits. Zero direction components now give a
+    NaN inverse (that axis never culls). Committed rays (tests/golden/axis_planar_rays.npz) + fresh ones."""
+    cfg = crt.load_config(scene_files[name]["cfg_path"])
+    S = orc.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    S.build_new_bvh(cfg.bvh_thresh_n)
+    S.build_wide8(cfg.bvh_thresh_n)
+    z = np.load(os.path.join(GOLDEN, "axis_planar_rays.npz"))
+    batches = [(k, z[k], 1 if "_any_" in k else 0) for k in z.files if k.startswith(name)]
+    rng = np.random.default_rng(11)
+    fresh = _surface_rays_with_zero_components(orc, S, cfg, rng)
+    batches.append(("fresh_closest", fresh, 0))
+    anyr = fresh.copy()
+    anyr[:, 3] = rng.uniform(0, 900.0 if name == "cornell-box" else 30.0, len(anyr)).astype(np.float32)
+    batches.append(("fresh_any", anyr, 1))
+    for key, rays, mode in batches:
+        tb, fb = S.trace(rays, which=3, mode=mode)
+        for which in (0, 4):
+            t, f = S.trace(rays, which=which, mode=mode)
+            if mode == 0:
+                assert np.array_equal(f, fb) and np.array_equal(t.view(np.uint32), tb.view(np.uint32)), (key, which)
+            else:
+                assert np.array_equal(f >= 0, fb >= 0), (key, which)
+    assert (S.trace(fresh, which=3, mode=0)[1] >= 0).mean() > 0.3       # the batch does exercise hits
+
+
 def test_new_bvh_structure(orc):
     rng = np.random.default_rng(3)
     n = 2000

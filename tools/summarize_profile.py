@@ -39,8 +39,9 @@ for r in rr[2:]:
         def b(k):
             v = float(r[idx[k]]); u = rr[1][idx[k]].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-        traffic[name] = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
-        out.append(f"| dram traffic per launch | {traffic[name]/1e6:.2f} | MB |")
+        key = name.replace("void ", "").split("<")[0]
+        traffic[key] = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
+        out.append(f"| dram traffic per launch | {traffic[key]/1e6:.2f} | MB |")
     except (KeyError, ValueError): pass
     out.append("")
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
