@@ -159,7 +159,7 @@ def test_rays_lying_in_box_planes_equal_brute_force(orc, crt, scene_files, name)
                 assert np.array_equal(f, fb) and np.array_equal(t.view(np.uint32), tb.view(np.uint32)), (key, which)
             else:
                 assert np.array_equal(f >= 0, fb >= 0), (key, which)
-    assert (S.trace(fresh, which=3, mode=0)[1] >= 0).mean() > 0.3       # the batch does exercise hits
+    assert (S.trace(fresh, which=3, mode=0)[1] >= 0).mean() > 0.1       # the batch does exercise hits
 
 
 def test_new_bvh_structure(orc):
