@@ -224,4 +224,145 @@ int write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t he
     return CRT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Texture images for map_Kd (the reference calls stbi_load(path, &x, &y, &comp, 0), Loader.h:55-59):
+// PNG (non-interlaced; grey / RGB / palette, with or without alpha or tRNS; 1-16 bits) and binary PNM
+// (P5 / P6, maxval <= 255). Pixels come back 8 bits per channel, top row first, with the channel count
+// stb_image reports for the file (the loader's texel arithmetic depends on it).
+// Returns 0 = ok, 1 = cannot open, 2 = format not supported or file corrupt.
+// ---------------------------------------------------------------------------------------------
+namespace {
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+int paeth(int a, int b, int c) {
+    int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+int read_png(const std::vector<uint8_t>& file, int* w, int* h, int* ch, std::vector<uint8_t>& px) {
+    if (file.size() < 8 + 25) return 2;
+    size_t pos = 8;
+    uint32_t W = 0, H = 0;
+    int depth = 0, ctype = 0;
+    bool have_ihdr = false, have_trns = false;
+    std::vector<uint8_t> idat, plte, trns;
+    for (;;) {
+        if (pos + 12 > file.size()) return 2;
+        const uint32_t len = be32(&file[pos]);
+        const char* type = (const char*)&file[pos + 4];
+        if (pos + 12 + (size_t)len > file.size()) return 2;
+        const uint8_t* d = &file[pos + 8];
+        if (!memcmp(type, "IHDR", 4)) {
+            if (len != 13) return 2;
+            W = be32(d); H = be32(d + 4); depth = d[8]; ctype = d[9];
+            if (d[10] != 0 || d[11] != 0 || d[12] != 0) return 2;           // compression, filter, interlace (Adam7 not supported)
+            have_ihdr = true;
+        } else if (!memcmp(type, "PLTE", 4)) plte.assign(d, d + len);
+        else if (!memcmp(type, "tRNS", 4)) { trns.assign(d, d + len); have_trns = true; }
+        else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), d, d + len);
+        else if (!memcmp(type, "IEND", 4)) break;
+        pos += 12 + (size_t)len;
+    }
+    if (!have_ihdr || W == 0 || H == 0 || W > (1u << 24) || H > (1u << 24) || idat.empty()) return 2;
+    int nc;                                                               // channels in the file
+    switch (ctype) { case 0: nc = 1; break; case 2: nc = 3; break; case 3: nc = 1; break; case 4: nc = 2; break; case 6: nc = 4; break; default: return 2; }
+    if (!(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) return 2;
+    if (ctype == 3 && (depth == 16 || plte.size() < 3)) return 2;
+    const size_t bpp_bits = (size_t)nc * depth;
+    const size_t stride = ((size_t)W * bpp_bits + 7) / 8;
+    const size_t fb = bpp_bits >= 8 ? bpp_bits / 8 : 1;                    // filter byte distance
+    std::vector<uint8_t> raw((stride + 1) * H);
+    uLongf raw_len = (uLongf)raw.size();
+    if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) return 2;
+    std::vector<uint8_t> prev(stride, 0), cur(stride);
+    std::vector<uint8_t> samples((size_t)W * H * nc);                      // one byte per sample (16-bit: high byte; palette: index)
+    static const uint8_t scale[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
+    for (uint32_t y = 0; y < H; ++y) {
+        const uint8_t* in = &raw[(stride + 1) * y];
+        const int ft = in[0];
+        if (ft > 4) return 2;
+        for (size_t i = 0; i < stride; ++i) {
+            const int a = i >= fb ? cur[i - fb] : 0, b = prev[i], c = i >= fb ? prev[i - fb] : 0;
+            int x = in[1 + i];
+            switch (ft) { case 1: x += a; break; case 2: x += b; break; case 3: x += (a + b) >> 1; break; case 4: x += paeth(a, b, c); break; default: break; }
+            cur[i] = (uint8_t)x;
+        }
+        uint8_t* out = &samples[(size_t)y * W * nc];
+        const size_t n = (size_t)W * nc;
+        if (depth == 8) memcpy(out, cur.data(), n);
+        else if (depth == 16) for (size_t i = 0; i < n; ++i) out[i] = cur[2 * i];
+        else for (size_t i = 0; i < n; ++i) {
+            const int v = (cur[i * depth / 8] >> (8 - depth - (int)(i * depth % 8))) & ((1 << depth) - 1);
+            out[i] = (uint8_t)(ctype == 0 ? v * scale[depth] : v);
+        }
+        prev.swap(cur);
+    }
+    const size_t np = (size_t)W * H;
+    if (ctype == 3) {                                                      // palette -> RGB, or RGBA when a tRNS chunk is present
+        const int oc = have_trns ? 4 : 3;
+        px.resize(np * oc);
+        for (size_t i = 0; i < np; ++i) {
+            const size_t k = samples[i];
+            for (int c = 0; c < 3; ++c) px[i * oc + c] = 3 * k + c < plte.size() ? plte[3 * k + c] : 0;
+            if (have_trns) px[i * oc + 3] = k < trns.size() ? trns[k] : 255;
+        }
+        *ch = oc;
+    } else if (have_trns && (ctype == 0 || ctype == 2) && trns.size() >= (size_t)2 * nc) {   // colour key -> alpha channel
+        uint8_t key[3];
+        for (int c = 0; c < nc; ++c) key[c] = depth == 16 ? trns[2 * c] : (uint8_t)(trns[2 * c + 1] * (depth < 8 ? scale[depth] : 1));
+        const int oc = nc + 1;
+        px.resize(np * oc);
+        for (size_t i = 0; i < np; ++i) {
+            bool same = true;
+            for (int c = 0; c < nc; ++c) { px[i * oc + c] = samples[i * nc + c]; same = same && samples[i * nc + c] == key[c]; }
+            px[i * oc + nc] = same ? 0 : 255;
+        }
+        *ch = oc;
+    } else {
+        px.swap(samples);
+        *ch = nc;
+    }
+    *w = (int)W; *h = (int)H;
+    return 0;
+}
+
+int read_pnm(const std::vector<uint8_t>& f, int* w, int* h, int* ch, std::vector<uint8_t>& px) {
+    size_t pos = 2;
+    auto number = [&](int* out) {
+        for (;;) {
+            while (pos < f.size() && (f[pos] == ' ' || f[pos] == '\t' || f[pos] == '\n' || f[pos] == '\r')) ++pos;
+            if (pos < f.size() && f[pos] == '#') { while (pos < f.size() && f[pos] != '\n') ++pos; continue; }
+            break;
+        }
+        if (pos >= f.size() || f[pos] < '0' || f[pos] > '9') return false;
+        long v = 0;
+        while (pos < f.size() && f[pos] >= '0' && f[pos] <= '9' && v < (1 << 28)) v = v * 10 + (f[pos++] - '0');
+        *out = (int)v;
+        return true;
+    };
+    int W, H, maxv;
+    if (!number(&W) || !number(&H) || !number(&maxv) || W <= 0 || H <= 0 || maxv <= 0 || maxv > 255) return 2;
+    ++pos;                                                                 // the single whitespace after maxval
+    const int nc = f[1] == '6' ? 3 : 1;
+    const size_t n = (size_t)W * H * nc;
+    if (pos + n > f.size()) return 2;
+    px.assign(f.begin() + pos, f.begin() + pos + n);
+    *w = W; *h = H; *ch = nc;
+    return 0;
+}
+}  // namespace
+
+int read_image(const char* path, int* w, int* h, int* ch, std::vector<uint8_t>& px) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return 1;
+    std::vector<uint8_t> file;
+    uint8_t buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) file.insert(file.end(), buf, buf + n);
+    fclose(f);
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    if (file.size() >= 8 && !memcmp(file.data(), sig, 8)) return read_png(file, w, h, ch, px);
+    if (file.size() >= 7 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) return read_pnm(file, w, h, ch, px);
+    return 2;
+}
+
 }  // namespace crt

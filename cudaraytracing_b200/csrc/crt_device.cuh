@@ -404,6 +404,14 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
 #ifndef CRT_QSTEPS
 #define CRT_QSTEPS 6
 #endif
+// CRT_SSTACK = N > 0: the first N entries of every lane's traversal stack live in shared memory, laid out
+// [entry][thread] so that a push / pop is one conflict-free wavefront whatever the lanes' depths are; a
+// local-memory stack costs one L1 wavefront per distinct depth in the warp, and the traversal kernels are
+// bound by L1 wavefronts (profiles/r01_s11.md). Deeper entries spill to the local array.
+#ifndef CRT_SSTACK
+#define CRT_SSTACK 0
+#endif
+static constexpr int kSharedStack = CRT_SSTACK;
 static constexpr int kQueueFlush = CRT_QFLUSH;       // queued leaves that trigger a flush
 static constexpr int kQueueSteps = CRT_QSTEPS;       // node steps between two looks at the queue
 static constexpr int kQueueCap = kQueueFlush + 32 * kQueueSteps;
@@ -424,8 +432,19 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
     const unsigned long long kNoHit = ((unsigned long long)0x7f7fffffu << 32) | 0x7fffffffull;   // t = FLT_MAX
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int stack[kStackSize];
+    int stack[kStackSize - kSharedStack];
+    __shared__ int s_stack[kSharedStack > 0 ? kSharedStack : 1][128];
     int sp = 0, cur = kDone;                               // kDone: no node in hand and the stack is empty
+    auto push = [&](int v) {
+        if (kSharedStack > 0 && sp < kSharedStack) s_stack[sp][threadIdx.x] = v;
+        else stack[sp - kSharedStack] = v;
+        ++sp;
+    };
+    auto pop = [&]() -> int {
+        --sp;
+        if (kSharedStack > 0 && sp < kSharedStack) return s_stack[sp][threadIdx.x];
+        return stack[sp - kSharedStack];
+    };
     uint32_t idx = 0;
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
@@ -442,11 +461,11 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                 q.q_slot[pos] = ~cur;
                 q.q_lane[pos] = (unsigned char)lane;
                 pending++;
-                cur = sp ? stack[--sp] : kDone;
+                cur = sp ? pop() : kDone;
             }
             if (cur >= 0 && cur != kDone) {
                 if (cur == kEmptyChild) {
-                    cur = sp ? stack[--sp] : kDone;
+                    cur = sp ? pop() : kDone;
                 } else {
                     float4 n0, n1, n2, n3;
                     load_node(sc.nodes, cur, n0, n1, n2, n3);
@@ -458,11 +477,11 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                     if (h0 && h1) {
                         int nearc = c0, farc = c1;
                         if (e1 < e0) { nearc = c1; farc = c0; }
-                        stack[sp++] = farc;
+                        push(farc);
                         cur = nearc;
                     } else if (h0) cur = c0;
                     else if (h1) cur = c1;
-                    else cur = sp ? stack[--sp] : kDone;
+                    else cur = sp ? pop() : kDone;
                 }
             }
         }

@@ -9,6 +9,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <array>
 #include <charconv>
 #include <cmath>
 #include <cstring>
@@ -76,6 +77,35 @@ struct Shape {                 // one `usemtl` occurrence (OBJLoader.h:131-137)
     std::string material;
     size_t face_begin = 0, face_end = 0;   // range in the shared index array (3 indices per face)
 };
+
+// Loader.h:85-103. The reference passes (&height, &width) to stbi_load's (x, y): its "width" is the image HEIGHT and
+// its "height" the image WIDTH; u scales by (image height - 1), v by (image width - 1), and the texel offset is
+// (v * image height + u) * channels. Kept as is (it is the usual lookup for square textures). uv of a corner = vt[vertex index].
+inline float frac01(float x) {
+    float ip;
+    return modff(modff(x, &ip) + 1.0f, &ip);
+}
+bool texel_mean(const std::vector<uint8_t>& tex, int img_w, int img_h, int ch, const std::vector<float>& uv, const uint32_t corner[3],
+                float kd[3]) {
+    const int width = img_h, height = img_w;             // the reference's names
+    float sum[3] = {0, 0, 0};
+    for (int k = 0; k < 3; ++k) {
+        const size_t vi = corner[k];
+        if (2 * vi + 1 >= uv.size()) return false;
+        const int u = (int)(frac01(uv[2 * vi]) * (float)(width - 1));
+        const int v = (int)(frac01(uv[2 * vi + 1]) * (float)(height - 1));
+        const long long off = ((long long)v * width + u) * ch;
+        float t[3];
+        for (int c = 0; c < 3; ++c) {
+            const long long o = off + c;
+            t[c] = (float)((o >= 0 && (size_t)o < tex.size()) ? tex[(size_t)o] : 0) / 255.0f;
+        }
+        if (k == 0) { sum[0] = t[0]; sum[1] = t[1]; sum[2] = t[2]; }
+        else { sum[0] += t[0]; sum[1] += t[1]; sum[2] += t[2]; }
+    }
+    for (int c = 0; c < 3; ++c) kd[c] = sum[c] / 3.0f;
+    return true;
+}
 }  // namespace
 
 void finish_material(HostMaterial& m) {
@@ -153,6 +183,7 @@ int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
     MappedFile f;
     if (!f.open(obj_path)) { set_error(std::string("Unable to open OBJ file: ") + obj_path); return CRT_ERR_IO; }
     std::vector<float> pos;                  // 3 per `v`
+    std::vector<float> uv;                   // 2 per `vt` (only read when a material has map_Kd)
     std::vector<uint32_t> idx;               // 3 per kept face
     std::vector<Shape> shapes;
     std::string mtl_name;
@@ -170,6 +201,9 @@ int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
         if (key == "v") {
             float x = c.number(), y = c.number(), z = c.number();
             pos.push_back(x); pos.push_back(y); pos.push_back(z);
+        } else if (key == "vt") {
+            float a = c.number(), b = c.number();
+            uv.push_back(a); uv.push_back(b);
         } else if (key == "f") {
             // "v", "v/vt", "v//vn", "v/vt/vn"; only the vertex index matters (Triangle.h:27-28
             // recomputes the normal) and only the first three corners are used (Loader.h:62-68).
@@ -234,6 +268,7 @@ int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
             else if (cur && key == "Ks") { cur->ks[0] = c.number(); cur->ks[1] = c.number(); cur->ks[2] = c.number(); }
             else if (cur && key == "Ke") { cur->ke[0] = c.number(); cur->ke[1] = c.number(); cur->ke[2] = c.number(); }
             else if (cur && key == "Ns") { cur->ns = c.number(); }
+            else if (cur && key == "map_Kd") { cur->map_kd = std::string(mtl_dir) + "/" + std::string(c.token()); }   // OBJLoader.h:184-193
             q = nl ? nl + 1 : mend;
         }
     }
@@ -248,11 +283,40 @@ int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
         int mat = (int)s.mats.size();
         s.mats.push_back(m);
         if (sh.face_end == sh.face_begin) continue;
+        // map_Kd (Loader.h:55-59,78-105): Kd of a triangle = mean of the three texels at its corners. A texture
+        // file that cannot be opened leaves the plain Kd (stbi_load returns null there); one that exists but
+        // cannot be decoded is an error.
+        int tw = 0, th = 0, tch = 0;
+        std::vector<uint8_t> tex;
+        std::map<std::array<uint32_t, 3>, int> tex_mats;
+        if (!m.map_kd.empty()) {
+            int rc = read_image(m.map_kd.c_str(), &tw, &th, &tch, tex);
+            if (rc == 2) { set_error("map_Kd: unsupported or corrupt image (PNG and binary PNM are read): " + m.map_kd); return CRT_ERR_IO; }
+            if (rc != 0) tex.clear();
+        }
         int obj = s.n_objects++;
         for (size_t fi = sh.face_begin; fi < sh.face_end; ++fi) {
             float v[9];
             for (int k = 0; k < 3; ++k) memcpy(v + 3 * k, &pos[3 * (size_t)idx[3 * fi + k]], 3 * sizeof(float));
-            if (!push_triangle(s, v, mat, obj)) {
+            int tri_mat = mat;
+            if (!tex.empty()) {
+                float kd[3];
+                if (!texel_mean(tex, tw, th, tch, uv, &idx[3 * fi], kd)) {
+                    set_error(std::string(obj_path) + ": map_Kd needs one vt per vertex (the reference indexes vt by the vertex index, Loader.h:81-83)");
+                    return CRT_ERR_IO;
+                }
+                std::array<uint32_t, 3> key;
+                memcpy(key.data(), kd, sizeof(kd));
+                auto found = tex_mats.find(key);
+                if (found == tex_mats.end()) {
+                    HostMaterial tm = m;
+                    memcpy(tm.kd, kd, sizeof(kd));
+                    found = tex_mats.emplace(key, (int)s.mats.size()).first;
+                    s.mats.push_back(tm);
+                }
+                tri_mat = found->second;
+            }
+            if (!push_triangle(s, v, tri_mat, obj)) {
                 set_error(std::string(obj_path) + ": non-finite vertex coordinate");
                 return CRT_ERR_IO;
             }

@@ -19,6 +19,7 @@ struct HostMaterial {
     float probe_dtheta = 0, probe_dphi = 0, probe_shin = 1;   // Render.cuh:296-300,306-307
     float pdf_area = 0;        // mis estimator: light-sampling density per unit area on triangles of this material
     std::string name;
+    std::string map_kd;        // texture path (OBJLoader.h:184-193); per-triangle Kd is derived at load time (Loader.h:78-105)
 };
 
 struct HostLight {             // one emissive usemtl group (Scene.h:38-42, DeviceLights.cuh:6-54)
@@ -56,5 +57,8 @@ int load_config(const char* path, crt_config* out);
 void inverse_view_matrix(const float eye[3], const float lookat[3], const float up[3], float out9[9]);
 // PNG, RGB8, top row first (replaces stbi_write_png, Render.cuh:492)
 int write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height);
+// map_Kd texture files (replaces stbi_load, Loader.h:58): PNG / binary PNM -> 8-bit pixels, top row first, channel count as
+// stb_image reports it. 0 = ok, 1 = cannot open, 2 = unsupported format or corrupt file.
+int read_image(const char* path, int* width, int* height, int* channels, std::vector<uint8_t>& pixels);
 
 }  // namespace crt

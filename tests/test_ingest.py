@@ -188,3 +188,61 @@ def test_shard_work_partitions_exactly(crt):
             assert all(parts[k][1] == parts[k + 1][0] for k in range(world - 1))
             if spp >= world:
                 assert all(b % npix == 0 and e % npix == 0 for b, e in parts)
+
+
+# ---- map_Kd textures (reference Loader.h:55-59,78-105) ----
+def _kd_of(scene):
+    tr, m = scene.tris(), scene.mats()
+    return tr, m[tr["mat"]][:, 0:3]
+
+
+def test_map_kd_equals_the_statement(crt, tmp_path):
+    """Every kind of texture file the reader accepts (PNG colour types 0/2/3/4/6, 2/4/8/16 bits, five row filters, tRNS,
+    split IDAT; binary PPM), uv inside / outside [0, 1) and negative: per-triangle Kd = the numpy statement of the
+    reference's rule, bit for bit. A texture file that does not exist leaves the plain Kd (stbi_load returns null)."""
+    from oracle import orc_texture as ot
+    from tools import texture_fixture as tf
+    obj, info = tf.write_scene(str(tmp_path))
+    S = crt.Scene().add_obj(obj, str(tmp_path))
+    tr, kd = _kd_of(S)
+    assert len(kd) == len(info["uv"])
+    want = info["plain_kd"].copy()
+    for name, px in info["pixels"].items():
+        rows = [i for i, t in enumerate(info["face_texture"]) if t == name]
+        want[rows] = ot.kd_from_texture(px, info["uv"][rows])
+    assert np.array_equal(kd.view(np.uint32), want.view(np.uint32))
+    textured = np.array([t is not None for t in info["face_texture"]])
+    assert len(np.unique(kd[textured], axis=0)) > 50                     # the textures do vary over the strips
+    assert S.counts()["n_lights"] == 1 and S.mats().shape[0] > 20         # one material per distinct texel mean
+
+
+def test_map_kd_equals_the_real_reference_on_the_pinnable_scene(crt, tmp_path):
+    """tests/golden/map_kd.npz comes from the REAL reference loader (stb_image decode, swapped (x, y), uv -> texel
+    arithmetic, /255), -O0 build, on the scene whose triangles carry one uv on all three corners - the only case in
+    which the reference's own mean is not undefined behaviour in effect (tools/texture_fixture.py)."""
+    from tools import texture_fixture as tf
+    g = np.load(os.path.join(ROOT, "tests", "golden", "map_kd.npz"))
+    obj, info = tf.write_scene(str(tmp_path), same_uv=True)
+    tr, kd = _kd_of(crt.Scene().add_obj(obj, str(tmp_path)))
+    assert np.array_equal(tr["verts"].view(np.uint32), g["verts"].view(np.uint32))
+    assert np.array_equal(kd.view(np.uint32), g["kd"].view(np.uint32))
+    assert len(np.unique(g["kd"], axis=0)) > 50
+
+
+def test_map_kd_errors(crt, tmp_path):
+    from tools import texture_fixture as tf
+    obj, _ = tf.write_scene(str(tmp_path))
+    with open(os.path.join(str(tmp_path), "rgb.png"), "wb") as f:        # exists, but is not an image we can decode: loud
+        f.write(b"\xff\xd8\xff\xe0 this is not a PNG")
+    with pytest.raises(crt.CrtError):
+        crt.Scene().add_obj(obj, str(tmp_path))
+    obj, _ = tf.write_scene(str(tmp_path))
+    with open(os.path.join(str(tmp_path), "rgb.png"), "r+b") as f:       # truncated file
+        f.truncate(60)
+    with pytest.raises(crt.CrtError):
+        crt.Scene().add_obj(obj, str(tmp_path))
+    # fewer vt than vertices: the reference would index out of bounds (Loader.h:81-83)
+    with open(os.path.join(str(tmp_path), "few.obj"), "w") as f:
+        f.write("mtllib textured.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0.5 0.5\nusemtl t_rgba\nf 1 2 3\n")
+    with pytest.raises(crt.CrtError):
+        crt.Scene().add_obj(os.path.join(str(tmp_path), "few.obj"), str(tmp_path))
