@@ -33,6 +33,9 @@ WORKLOADS = {
 }
 
 
+BUILDERS = {"lbvh": 0, "lbvh8": 1, "ploc": 2, "ploc8": 3}     # include/crt.h crt_builder
+
+
 class Workload:
     """Camera + render settings + how to build the scene (product and oracle side)."""
 
@@ -40,7 +43,7 @@ class Workload:
         import numpy as np
         import cudaraytracing_b200 as crt
         self.name = name
-        self.builder = {"lbvh": 0, "lbvh8": 1}[os.environ.get("CRT_BUILDER", "lbvh")]
+        self.builder = BUILDERS[os.environ.get("CRT_BUILDER", "lbvh")]
         source, W, H, spp, self.desc = WORKLOADS[name]
         self.source = source
         self.tmp = tempfile.mkdtemp(prefix="crt_bench_")
@@ -83,7 +86,9 @@ class Workload:
         else:
             v, m, o, mats = self.arrays()
             S = orc.Scene().add_arrays(v, m.astype(np.int32), o.astype(np.int32), mats)
-        S.build_new_bvh(self.bvh_thresh_n)
+        S.build_new_bvh(self.bvh_thresh_n, self.builder & 2)          # same topology as the product
+        if self.builder & 1:
+            S.build_wide8(self.bvh_thresh_n, self.builder)
         return S
 
 
@@ -93,7 +98,7 @@ DATA_NOTE = {
     "synthetic": "procedural scene generated from a seed at run time (tools/synthetic.py), Philox seed 0",
 }
 
-S_NODE, S_TRI, S_RAY_IO_CLOSEST, S_RAY_IO_ANY = 64, 48, 32 + 8, 48 + 0   # bytes, DESIGN.md "Algorithmic bytes"
+S_NODE, S_NODE_WIDE, S_TRI, S_RAY_IO_CLOSEST, S_RAY_IO_ANY = 64, 80, 48, 32 + 8, 48 + 0   # bytes, DESIGN.md "Algorithmic bytes"
 
 
 def load_peaks():
@@ -177,7 +182,8 @@ def cpu_baseline_leg(cfg, budget_samples=float(os.environ.get("CRT_CPU_BUDGET", 
     spp = max(1, min(cfg.spp, int(budget_samples // (w * h))))
     threads = os.cpu_count() or orc.max_threads()          # torchrun exports OMP_NUM_THREADS=1; use every host core
     t0 = time.time()
-    _, st = S.render(cfg.eye, M, float(cfg.fovy_rad), w, h, 0, spp, cfg.P_RR, cfg.light_sample_n, threads=threads)
+    _, st = S.render(cfg.eye, M, float(cfg.fovy_rad), w, h, 0, spp, cfg.P_RR, cfg.light_sample_n, threads=threads,
+                      wide=bool(cfg.builder & 1))
     dt = time.time() - t0
     per_ray = {
         "closest_inner": st["closest_inner"] / max(st["closest_rays"], 1), "closest_tris": st["closest_tris"] / max(st["closest_rays"], 1),
@@ -285,8 +291,9 @@ def ours(args):
         st = render.stats()
         render.set_stage_timing(False)
         render.set_spp(cfg.spp)
-        b_closest = per_ray["closest_inner"] * S_NODE + per_ray["closest_tris"] * S_TRI + S_RAY_IO_CLOSEST
-        b_any = per_ray["any_inner"] * S_NODE + per_ray["any_tris"] * S_TRI + S_RAY_IO_ANY
+        s_node = S_NODE_WIDE if cfg.builder & 1 else S_NODE
+        b_closest = per_ray["closest_inner"] * s_node + per_ray["closest_tris"] * S_TRI + S_RAY_IO_CLOSEST
+        b_any = per_ray["any_inner"] * s_node + per_ray["any_tris"] * S_TRI + S_RAY_IO_ANY
         kernels = {
             "k_extend": {"ms": st["ms_extend"], "rays": st["extend_rays"] + st["probe_rays"], "bytes_per_ray": b_closest},
             "k_shadow": {"ms": st["ms_shadow"], "rays": st["shadow_rays"], "bytes_per_ray": b_any},
@@ -302,7 +309,7 @@ def ours(args):
                 traffic = json.load(f).get(args.workload, {}).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(kernels[dom]["achieved_gbs"], 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(kernels[dom]["achieved_gbs"] / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_kind": peak_kind,
-                "note": "algorithmic bytes = oracle-counted node (64 B) and triangle (48 B) visits + ray I/O per ray x rays per launch; "
+                "note": "algorithmic bytes = oracle-counted node (%d B) and triangle (48 B) visits + ray I/O per ray x rays per launch; " % s_node +
                         "the BVH is L2-resident on this workload, so this is L2/latency-bound work measured against the HBM copy peak",
                 "launches": int(st["iterations"]), "avg_launch_ms": round(kernels[dom]["ms"] / max(st["iterations"], 1), 4),
                 "stage_ms": {"generate": round(st["ms_generate"], 3), "extend": round(st["ms_extend"], 3), "shade": round(st["ms_shade"], 3),
@@ -319,6 +326,7 @@ def ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE[cfg.source if cfg.source == "synthetic" else "fixture"],
             "config": {"workload": desc, "width": cfg.width, "height": cfg.height, "spp": cfg.spp, "light_sample_n": cfg.light_sample_n,
                        "P_RR": round(float(cfg.P_RR), 4), "bvh_thresh_n": cfg.bvh_thresh_n, "estimator": "compat",
+                       "builder": [k for k, v in BUILDERS.items() if v == cfg.builder][0],
                        "parallelism": "samples sharded over %d GPU(s), one int64 NCCL reduce" % world,
                        "l2": "256 MiB buffer written before each timed region (L2 flush); per-step path/shadow queues exceed L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 13 * 4, "d2h_bytes_per_step": npix * 3,
@@ -477,11 +485,12 @@ def ours_c5(args):
         from oracle import orc
         O = cfg.build_oracle(orc)
         sample = rays[:200000].cpu().numpy()
-        _, _, st = O.trace(sample, which=0, mode=0, want_stats=True, threads=os.cpu_count())
+        which = 4 if cfg.builder & 1 else 0
+        _, _, st = O.trace(sample, which=which, mode=0, want_stats=True, threads=os.cpu_count())
         t0 = time.time()
-        O.trace(sample, which=0, mode=0, threads=os.cpu_count())
+        O.trace(sample, which=which, mode=0, threads=os.cpu_count())
         cpu_dt = time.time() - t0
-        bpr = st["inner"] / st["rays"] * S_NODE + st["tris"] / st["rays"] * S_TRI + S_RAY_IO_CLOSEST
+        bpr = st["inner"] / st["rays"] * (S_NODE_WIDE if cfg.builder & 1 else S_NODE) + st["tris"] / st["rays"] * S_TRI + S_RAY_IO_CLOSEST
         ach = res["closest"]["mrays"] * 1e6 * bpr / 1e9
         print(json.dumps({
             "metric": "Mrays/s (closest-hit)", "value": round(res["closest"]["mrays"], 1), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -523,7 +532,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--builder", default=None, choices=["lbvh", "lbvh8"], help="BVH node layout (default: CRT_BUILDER or lbvh)")
+    ap.add_argument("--builder", default=None, choices=sorted(BUILDERS), help="BVH node layout (default: CRT_BUILDER or lbvh)")
     ap.add_argument("--ref-spp", type=int, default=4, help="reference arm: samples per pixel of the bounded sample (<=0: full)")
     args = ap.parse_args()
     if args.builder:

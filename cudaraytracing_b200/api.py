@@ -17,7 +17,7 @@ _LIB = None
 
 ESTIMATOR_COMPAT, ESTIMATOR_MIS = 0, 1
 RAY_CLOSEST, RAY_ANY = 0, 1
-BUILDER_LBVH, BUILDER_LBVH8 = 0, 1
+BUILDER_LBVH, BUILDER_LBVH8, BUILDER_PLOC, BUILDER_PLOC8 = 0, 1, 2, 3     # bit 0: 8-wide nodes, bit 1: PLOC topology
 MAX_OBJ_PATHS, PATH_LEN = 16, 1024
 
 
@@ -261,7 +261,7 @@ class Scene:
     def export_bvh(self):
         """nodes (BVH_NODE, or BVH8_NODE for a scene built with BUILDER_LBVH8), order, last, bounds."""
         c = self.counts()
-        wide = self.bvh_kind() == BUILDER_LBVH8
+        wide = bool(self.bvh_kind() & 1)
         nodes = np.zeros(c["n_nodes"], BVH8_NODE if wide else BVH_NODE)
         order = np.zeros(c["n_tris"], np.int32)
         last = np.zeros(c["n_tris"], np.uint8)

@@ -139,7 +139,7 @@ int crt_scene_add_triangles(crt_scene* s, const float* verts, const uint32_t* ma
 
 int crt_scene_build_bvh(crt_scene* s, uint32_t thresh_n, int builder, int device, float* build_ms) {
     CHECK_ARG(s, "crt_scene_build_bvh: null scene");
-    CHECK_ARG(builder == CRT_BUILDER_LBVH || builder == CRT_BUILDER_LBVH8, "crt_scene_build_bvh: unknown builder");
+    CHECK_ARG(builder >= CRT_BUILDER_LBVH && builder <= CRT_BUILDER_PLOC8, "crt_scene_build_bvh: unknown builder");
     int n = crt_device_count();
     if (n <= 0) { set_error("crt_scene_build_bvh: no CUDA device (there is no CPU fallback)"); return CRT_ERR_CUDA; }
     CHECK_ARG(device >= 0 && device < n, "crt_scene_build_bvh: device out of range");
@@ -223,7 +223,7 @@ int crt_scene_export_bvh8(crt_scene* s, crt_bvh8_node* nodes, int32_t* tri_order
 int crt_scene_bvh_kind(crt_scene* s, int* builder) {
     CHECK_ARG(s && builder, "crt_scene_bvh_kind: null argument");
     if (!s->built) { set_error("crt_scene_bvh_kind: BVH not built"); return CRT_ERR_STATE; }
-    *builder = s->dev.wide ? CRT_BUILDER_LBVH8 : CRT_BUILDER_LBVH;
+    *builder = s->dev.builder;
     return CRT_OK;
 }
 

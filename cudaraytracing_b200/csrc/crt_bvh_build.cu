@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <vector>
 
 namespace crt {
 
@@ -313,6 +314,126 @@ __global__ void k_refit(int n, const uint32_t* __restrict__ order, const float4*
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// PLOC topology (builders CRT_BUILDER_PLOC / PLOC8): bottom-up agglomeration over the Morton order instead of
+// the Karras tree. Specification and CPU statement: oracle/orc_bvh.cpp build_ploc_tree (every array must come
+// out bit-identical). One round = k_ploc_nn -> k_ploc_lower + scan -> k_ploc_merge; the host reads the number
+// of clusters left after each round. k_ploc_finalize then walks the rounds in reverse (parents before
+// children) to hand every node its slot range and writes the same arrays the Karras path produces
+// (left/right/first/last/blo/bhi + the depth-first triangle order), so the leaf rule, the pair-node emitter
+// and the 8-wide collapse run unchanged on either topology.
+// A cluster is two float4: (box lo, ref bits) (box hi, triangle count); ref < 0: ~Morton position of a single
+// triangle, else the creation index of the merge that made it.
+// ------------------------------------------------------------------------------------------
+static constexpr int kPlocRadius = 8;
+
+__global__ void k_ploc_init(uint32_t n, const uint32_t* __restrict__ morton, const float4* __restrict__ tlo,
+                            const float4* __restrict__ thi, float4* __restrict__ clo, float4* __restrict__ chi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t f = morton[i];
+    float4 lo = tlo[f], hi = thi[f];
+    lo.w = __int_as_float(~(int)i);
+    hi.w = __int_as_float(1);
+    clo[i] = lo; chi[i] = hi;
+}
+
+// nearest neighbour by union-box area inside the window [k-R, k+R]; buddy k^1 first, then ascending j, strictly smaller wins
+__global__ void __launch_bounds__(256) k_ploc_nn(int m, const float4* __restrict__ clo, const float4* __restrict__ chi,
+                                                 int* __restrict__ nn) {
+    __shared__ float4 slo[256 + 2 * kPlocRadius], shi[256 + 2 * kPlocRadius];
+    const int base = (int)(blockIdx.x * 256) - kPlocRadius;
+    for (int t = threadIdx.x; t < 256 + 2 * kPlocRadius; t += 256) {
+        const int g = base + t;
+        if (g >= 0 && g < m) { slo[t] = clo[g]; shi[t] = chi[g]; }
+    }
+    __syncthreads();
+    const int k = (int)(blockIdx.x * 256 + threadIdx.x);
+    if (k >= m) return;
+    const float4 alo = slo[threadIdx.x + kPlocRadius], ahi = shi[threadIdx.x + kPlocRadius];
+    auto area = [&](int dl) {
+        const float4 b0 = slo[threadIdx.x + kPlocRadius + dl], b1 = shi[threadIdx.x + kPlocRadius + dl];
+        const float ex = fmaxf(ahi.x, b1.x) - fminf(alo.x, b0.x);
+        const float ey = fmaxf(ahi.y, b1.y) - fminf(alo.y, b0.y);
+        const float ez = fmaxf(ahi.z, b1.z) - fminf(alo.z, b0.z);
+        return (ex * ey + ey * ez) + ez * ex;
+    };
+    float best = FLT_MAX;
+    int bj = -1;
+    const int buddy = k ^ 1;                             // examined first: wins ties (oracle build_ploc_tree)
+    if (buddy < m) { best = area(buddy - k); bj = buddy; }
+#pragma unroll
+    for (int dl = -kPlocRadius; dl <= kPlocRadius; ++dl) {
+        const int j = k + dl;
+        if (dl == 0 || j == buddy || j < 0 || j >= m) continue;
+        const float a = area(dl);
+        if (bj < 0 || a < best) { best = a; bj = j; }
+    }
+    nn[k] = bj;
+}
+
+// 1 for the lower member of every mutual pair (it becomes the merged cluster)
+__global__ void k_ploc_lower(int m, const int* __restrict__ nn, uint32_t* __restrict__ lower) {
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= m) return;
+    const int j = nn[k];
+    lower[k] = (k < j && nn[j] == k) ? 1u : 0u;
+}
+
+__global__ void k_ploc_merge(int m, uint32_t created_base, const float4* __restrict__ clo, const float4* __restrict__ chi,
+                             const int* __restrict__ nn, const uint32_t* __restrict__ lower_rank, float4* __restrict__ out_lo,
+                             float4* __restrict__ out_hi, int* __restrict__ cl, int* __restrict__ cr, float4* __restrict__ nlo,
+                             float4* __restrict__ nhi) {
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= m) return;
+    const int j = nn[k];
+    const bool mutual = nn[j] == k;
+    if (mutual && k > j) return;                         // the upper member's place is dropped
+    // places dropped before k = upper members before k = lower members before k - pairs still open at k
+    int open = 0;
+    for (int l = max(0, k - kPlocRadius); l < k; ++l) {
+        const int jl = nn[l];
+        if (jl >= k && nn[jl] == l) ++open;
+    }
+    const uint32_t lr = lower_rank[k];
+    const int pos = k - ((int)lr - open);
+    float4 lo = clo[k], hi = chi[k];
+    if (mutual) {
+        const float4 lo2 = clo[j], hi2 = chi[j];
+        const int id = (int)(created_base + lr);
+        const int cnt = __float_as_int(hi.w) + __float_as_int(hi2.w);
+        cl[id] = __float_as_int(lo.w);
+        cr[id] = __float_as_int(lo2.w);
+        lo = make_float4(fminf(lo.x, lo2.x), fminf(lo.y, lo2.y), fminf(lo.z, lo2.z), __int_as_float(id));
+        hi = make_float4(fmaxf(hi.x, hi2.x), fmaxf(hi.y, hi2.y), fmaxf(hi.z, hi2.z), __int_as_float(cnt));
+        nlo[id] = lo; nhi[id] = hi;
+    }
+    out_lo[pos] = lo; out_hi[pos] = hi;
+}
+
+// merges [c_begin, c_end) of one round; node id = ni - 1 - creation index; the slot range of a node was written
+// by its parent in an earlier launch (later round), the root's by k_ploc_root
+__global__ void k_ploc_root(int n, int* __restrict__ first, int* __restrict__ last) { first[0] = 0; last[0] = n - 1; }
+__global__ void k_ploc_finalize(uint32_t c_begin, uint32_t c_end, int ni, const int* __restrict__ cl, const int* __restrict__ cr,
+                                const float4* __restrict__ nlo, const float4* __restrict__ nhi, const uint32_t* __restrict__ morton,
+                                int* __restrict__ left, int* __restrict__ right, int* __restrict__ first, int* __restrict__ last,
+                                float4* __restrict__ blo, float4* __restrict__ bhi, uint32_t* __restrict__ order) {
+    const uint32_t c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_end) return;
+    const int nd = ni - 1 - (int)c;
+    const int f = first[nd], l = last[nd];
+    float4 lo = nlo[c], hi = nhi[c];
+    lo.w = 0.0f; hi.w = 0.0f;
+    blo[nd] = lo; bhi[nd] = hi;
+    const int a = cl[c], b = cr[c];
+    const int lcount = a < 0 ? 1 : __float_as_int(nhi[a].w);
+    if (a < 0) { left[nd] = ~f; order[f] = morton[~a]; }
+    else { const int ch = ni - 1 - a; left[nd] = ch; first[ch] = f; last[ch] = f + lcount - 1; }
+    const int g = f + lcount;
+    if (b < 0) { right[nd] = ~g; order[g] = morton[~b]; }
+    else { const int ch = ni - 1 - b; right[nd] = ch; first[ch] = g; last[ch] = l; }
+}
+
 __global__ void k_keep_flags(int n_internal, const int* __restrict__ first, const int* __restrict__ last, uint32_t thresh,
                              uint32_t* __restrict__ keep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -581,13 +702,17 @@ __global__ void k_wide_emit(WideBuildView v, uint32_t n_level, uint32_t level_st
 int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face_shade, uint32_t n, uint32_t thresh_n,
                      int builder, cudaStream_t st, float* build_ms) {
     int rc = CRT_OK;
-    const bool wide = builder == CRT_BUILDER_LBVH8;
+    const bool wide = (builder & 1) != 0;               // bit 0: 8-wide node layout, bit 1: PLOC topology
+    const bool ploc = (builder & 2) != 0;
     if (thresh_n < 1) thresh_n = 1;
     if (wide && thresh_n > 15) thresh_n = 15;            // 7-bit leaf offsets inside a wide node
     uint4* wnodes = nullptr;
     int *work0 = nullptr, *work1 = nullptr, *tmp_ref = nullptr, *tmp_cnt = nullptr;
     uint32_t *cnt_int = nullptr, *cnt_tri = nullptr, *off_int = nullptr, *off_tri = nullptr, *order8 = nullptr, *d_tot2 = nullptr;
     uint8_t* last8 = nullptr;
+    float4 *pc_lo[2] = {nullptr, nullptr}, *pc_hi[2] = {nullptr, nullptr}, *pn_lo = nullptr, *pn_hi = nullptr;
+    int *p_nn = nullptr, *p_cl = nullptr, *p_cr = nullptr;
+    uint32_t *p_lower = nullptr, *p_rank = nullptr, *p_order = nullptr;
     const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
     const int nb = (int)((n + 255) / 256);
     float4 *tlo = nullptr, *thi = nullptr, *blo = nullptr, *bhi = nullptr;
@@ -603,6 +728,7 @@ int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face
     ds.n_tris = n;
     ds.n_nodes = 0;
     ds.wide = wide;
+    ds.builder = builder;
     if (n == 0) { if (build_ms) *build_ms = 0; return CRT_OK; }
 
     BUILD_CHECK(cudaEventCreate(&ev0));
@@ -664,9 +790,53 @@ int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face
         BUILD_CHECK(cudaMalloc(&flags, sizeof(uint32_t) * ni));
         BUILD_CHECK(cudaMalloc(&keep, sizeof(uint32_t) * ni));
         BUILD_CHECK(cudaMalloc(&rank, sizeof(uint32_t) * ni));
-        BUILD_CHECK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * ni, st));
-        k_radix_tree<<<nbi, 256, 0, st>>>(keys0, (int)n, left, right, first, last, pnode, pleaf);
-        k_refit<<<nb, 256, 0, st>>>((int)n, ds.order, tlo, thi, left, right, pnode, pleaf, blo, bhi, flags);
+        if (!ploc) {
+            BUILD_CHECK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * ni, st));
+            k_radix_tree<<<nbi, 256, 0, st>>>(keys0, (int)n, left, right, first, last, pnode, pleaf);
+            k_refit<<<nb, 256, 0, st>>>((int)n, ds.order, tlo, thi, left, right, pnode, pleaf, blo, bhi, flags);
+        } else {
+            for (int b = 0; b < 2; ++b) {
+                BUILD_CHECK(cudaMalloc(&pc_lo[b], sizeof(float4) * n));
+                BUILD_CHECK(cudaMalloc(&pc_hi[b], sizeof(float4) * n));
+            }
+            BUILD_CHECK(cudaMalloc(&pn_lo, sizeof(float4) * ni));
+            BUILD_CHECK(cudaMalloc(&pn_hi, sizeof(float4) * ni));
+            BUILD_CHECK(cudaMalloc(&p_nn, sizeof(int) * n));
+            BUILD_CHECK(cudaMalloc(&p_cl, sizeof(int) * ni));
+            BUILD_CHECK(cudaMalloc(&p_cr, sizeof(int) * ni));
+            BUILD_CHECK(cudaMalloc(&p_lower, sizeof(uint32_t) * n));
+            BUILD_CHECK(cudaMalloc(&p_rank, sizeof(uint32_t) * n));
+            BUILD_CHECK(cudaMalloc(&p_order, sizeof(uint32_t) * n));
+            k_ploc_init<<<nb, 256, 0, st>>>(n, ds.order, tlo, thi, pc_lo[0], pc_hi[0]);
+            std::vector<uint32_t> round_start;            // creation index at which every round begins
+            uint32_t m = n, created = 0;
+            int cur = 0;
+            while (m > 1) {
+                const int nbm = (int)((m + 255) / 256);
+                k_ploc_nn<<<nbm, 256, 0, st>>>((int)m, pc_lo[cur], pc_hi[cur], p_nn);
+                k_ploc_lower<<<nbm, 256, 0, st>>>((int)m, p_nn, p_lower);
+                BUILD_CHECK(exclusive_scan_u32(p_lower, p_rank, m, scratch, d_total, st));
+                k_ploc_merge<<<nbm, 256, 0, st>>>((int)m, created, pc_lo[cur], pc_hi[cur], p_nn, p_rank, pc_lo[cur ^ 1], pc_hi[cur ^ 1],
+                                                  p_cl, p_cr, pn_lo, pn_hi);
+                uint32_t merged = 0;
+                BUILD_CHECK(cudaMemcpyAsync(&merged, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                BUILD_CHECK(cudaStreamSynchronize(st));
+                if (merged == 0 || merged > m / 2) { set_error("PLOC: a round merged nothing"); rc = CRT_ERR_STATE; goto done; }
+                round_start.push_back(created);
+                created += merged;
+                m -= merged;
+                cur ^= 1;
+            }
+            if (created != ni) { set_error("PLOC: merge count mismatch"); rc = CRT_ERR_STATE; goto done; }
+            round_start.push_back(created);
+            k_ploc_root<<<1, 1, 0, st>>>((int)n, first, last);
+            for (size_t r = round_start.size() - 1; r-- > 0;) {
+                const uint32_t c0 = round_start[r], c1 = round_start[r + 1];
+                k_ploc_finalize<<<(int)((c1 - c0 + 255) / 256), 256, 0, st>>>(c0, c1, (int)ni, p_cl, p_cr, pn_lo, pn_hi, ds.order, left, right,
+                                                                               first, last, blo, bhi, p_order);
+            }
+            std::swap(ds.order, p_order);                 // depth-first order replaces the Morton order
+        }
         k_keep_flags<<<nbi, 256, 0, st>>>((int)ni, first, last, thresh_n, keep);
         BUILD_CHECK(exclusive_scan_u32(keep, rank, ni, scratch, d_total, st));
         BUILD_CHECK(cudaMemcpyAsync(&n_kept, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -741,6 +911,8 @@ done:
     cudaFree(left); cudaFree(right); cudaFree(first); cudaFree(last); cudaFree(pnode); cudaFree(pleaf);
     cudaFree(wnodes); cudaFree(work0); cudaFree(work1); cudaFree(tmp_ref); cudaFree(tmp_cnt); cudaFree(cnt_int); cudaFree(cnt_tri);
     cudaFree(off_int); cudaFree(off_tri); cudaFree(order8); cudaFree(last8); cudaFree(d_tot2);
+    for (int b = 0; b < 2; ++b) { cudaFree(pc_lo[b]); cudaFree(pc_hi[b]); }
+    cudaFree(pn_lo); cudaFree(pn_hi); cudaFree(p_nn); cudaFree(p_cl); cudaFree(p_cr); cudaFree(p_lower); cudaFree(p_rank); cudaFree(p_order);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     return rc;

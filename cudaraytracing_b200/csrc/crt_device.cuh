@@ -15,6 +15,12 @@ namespace crt {
 
 #define CRT_DEV __device__ __forceinline__
 
+// Slack of the box tests: a child is entered iff tmin <= tmax * kSlabSlack, kSlabSlack = 1 + 2^-17 (64 ulp). The
+// slab distances carry ~3 roundings each, but the margin has to cover the *triangle test's* error too: Moeller-
+// Trumbore accepts points a few 1e-6 (relative to the distance) outside a small, far triangle, so a ray through a
+// box corner (a light sample AT a vertex, veach-mis) was accepted by the triangle test and rejected by a 4-ulp box
+// test - found as a one-pixel difference between the pair-node and the 8-wide render (profiles/r01_s15.md).
+static constexpr float kSlabSlack = 1.00000762939453125f;
 static constexpr float kEps = 0.00001f;                 // EPSILON, reference Global.h:11
 static constexpr float kPi = 3.14159265358979323846f;
 static constexpr float kTwoPi = 6.2831853071795864769f; // get_cuda_sphere_sample_inv_pdf(), Global.h:96-99
@@ -162,15 +168,32 @@ CRT_DEV bool tri_test(V3 v1, V3 e1, V3 e2, V3 o, V3 d, float* t_out) {
 }
 
 // Conservative slab test (DESIGN.md "Traversal rule"). NaN plane distances drop out of fminf / fmaxf.
+// Axis the ray is parallel to (direction component exactly 0, inverse = NaN - box_inv below): its plane distances
+// drop out of the min/max of the slab test, and the axis is tested here instead: o must lie in [lo, hi] widened by
+// 2^-17 * (|o| + exit distance + summed box extent). Statement and rationale: oracle/orc_bvh.cpp parallel_ok.
+CRT_DEV bool parallel_ok(float lo, float hi, float o, float texit, float ext) {
+    const float dlt = ((fabsf(o) + texit) + ext) * 7.62939453125e-06f;
+    return lo - o <= dlt && o - hi <= dlt;
+}
+CRT_DEV bool has_parallel_axis(V3 inv) { return inv.x != inv.x || inv.y != inv.y || inv.z != inv.z; }
+
+// zray: the ray has a parallel axis (rare; hoisted so that the common path pays one predicate)
 CRT_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, V3 o, V3 inv, float limit,
-                  float* enter) {
+                  float* enter, bool zray) {
     float tx0 = (lox - o.x) * inv.x, tx1 = (hix - o.x) * inv.x;
     float ty0 = (loy - o.y) * inv.y, ty1 = (hiy - o.y) * inv.y;
     float tz0 = (loz - o.z) * inv.z, tz1 = (hiz - o.z) * inv.z;
     float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
     float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), limit));
     *enter = tmin;
-    return tmin <= tmax * 1.0000004f;
+    bool hit = tmin <= tmax * kSlabSlack;
+    if (zray && hit) {
+        const float ext = ((hix - lox) + (hiy - loy)) + (hiz - loz);
+        if (inv.x != inv.x) hit = parallel_ok(lox, hix, o.x, tmax, ext);
+        if (hit && inv.y != inv.y) hit = parallel_ok(loy, hiy, o.y, tmax, ext);
+        if (hit && inv.z != inv.z) hit = parallel_ok(loz, hiz, o.z, tmax, ext);
+    }
+    return hit;
 }
 
 // Inverse direction for the box tests: 1/d, and NaN for a component that is exactly zero, so that this axis never
@@ -213,6 +236,7 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
     best.t = FLT_MAX; best.slot = -1; best.face = -1;
     if (sc.n_nodes == 0) return best;
     const V3 inv = box_inv3(d);
+    const bool zray = has_parallel_axis(inv);
     float tlimit = MODE == 0 ? FLT_MAX : tmax;
     int stack[kStackSize];
     int sp = 0;
@@ -224,8 +248,8 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
             load_node(sc.nodes, cur, n0, n1, n2, n3);
             const float lim = tlimit * 1.0001f;
             float e0, e1;
-            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);
-            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1);
+            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0, zray);
+            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1, zray);
             const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
             if (h0 && h1) {
                 int nearc = c0, farc = c1;
@@ -294,7 +318,7 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
     float tmax = 0.0f, tlimit = 0.0f;
     HitRec best;
     best.t = FLT_MAX; best.slot = -1; best.face = -1;
-    bool have = false, exhausted = false;
+    bool have = false, exhausted = false, zray = false;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
         if (idle) {
@@ -310,6 +334,7 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
                         idx = i;
                         const bool live = load(i, o, d, tmax);
                         inv = box_inv3(d);
+                        zray = has_parallel_axis(inv);
                         tlimit = MODE == 0 ? FLT_MAX : tmax;
                         best.t = FLT_MAX; best.slot = -1; best.face = -1;
                         sp = 0;
@@ -335,8 +360,8 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
                 load_node(sc.nodes, cur, n0, n1, n2, n3);
                 const float lim = tlimit * 1.0001f;
                 float e0, e1;
-                const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);
-                const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1);
+                const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0, zray);
+                const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1, zray);
                 const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
                 if (h0 && h1) {
                     int nearc = c0, farc = c1;
@@ -449,7 +474,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
     int pending = 0;
-    bool have = false, exhausted = false;
+    bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
     for (;;) {
@@ -471,8 +496,8 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                     load_node(sc.nodes, cur, n0, n1, n2, n3);
                     const float lim = tlimit * 1.0001f;
                     float e0, e1;
-                    const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0);
-                    const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1);
+                    const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0, zray);
+                    const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1, zray);
                     const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
                     if (h0 && h1) {
                         int nearc = c0, farc = c1;
@@ -553,6 +578,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                         float tmax;
                         const bool live = load(i, o, d, tmax);
                         inv = box_inv3(d);
+                        zray = has_parallel_axis(inv);
                         tlimit = MODE == 0 ? FLT_MAX : tmax;
                         q.ox[lane] = o.x; q.oy[lane] = o.y; q.oz[lane] = o.z;
                         q.dx[lane] = d.x; q.dy[lane] = d.y; q.dz[lane] = d.z;

@@ -23,6 +23,7 @@ int cuda_fail(cudaError_t e, const char* what);
 struct DeviceScene {
     int device = 0;
     uint32_t n_tris = 0, n_nodes = 0, n_mats = 0, n_lights = 0, n_light_tris = 0;
+    int builder = 0;                // crt_builder the scene was built with
     bool wide = false;              // nodes are 80-byte 8-wide compressed nodes (5 x 16 B) instead of 64-byte pairs
     float4* nodes = nullptr;        // n_nodes * 4 (pairs) or n_nodes * 5 (wide)
     float4* tri_geom = nullptr;     // n_tris * 3, BVH slot order

@@ -60,13 +60,13 @@ int main(int argc, char** argv) {
         else if (a == "--height") height = atol(next());
         else if (a == "--device") device = atoi(next());
         else if (a == "--estimator") { std::string e = next(); estimator = e == "mis" ? CRT_ESTIMATOR_MIS : CRT_ESTIMATOR_COMPAT; }
-        else if (a == "--builder") { std::string e = next(); builder = e == "lbvh8" ? CRT_BUILDER_LBVH8 : CRT_BUILDER_LBVH; }
+        else if (a == "--builder") { std::string e = next(); builder = e == "lbvh8" ? CRT_BUILDER_LBVH8 : e == "ploc" ? CRT_BUILDER_PLOC : e == "ploc8" ? CRT_BUILDER_PLOC8 : CRT_BUILDER_LBVH; }
         else if (a == "--checkpoint") checkpoint = next();
         else if (a == "--chunk-spp") chunk_spp = atol(next());
         else if (a == "--stop-after") stop_after = atol(next());
         else if (a == "--help" || a == "-h") {
             printf("usage: crt --config config.json [--root DIR] [--out image.png] [--spp N] [--seed S]\n"
-                   "           [--width W --height H] [--estimator compat|mis] [--builder lbvh|lbvh8] [--device D]\n"
+                   "           [--width W --height H] [--estimator compat|mis] [--builder lbvh|lbvh8|ploc|ploc8] [--device D]\n"
                    "           [--checkpoint FILE [--chunk-spp N] [--stop-after CHUNKS]]\n"
                    "  --checkpoint: progressive render in chunks of N samples per pixel (default 64); FILE is rewritten after\n"
                    "                every chunk and, if it exists at start, the render resumes from it (bit-identical image).\n");

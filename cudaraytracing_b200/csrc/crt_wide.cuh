@@ -37,7 +37,7 @@ struct WideStep {
 };
 
 // Box tests of the 8 children of node ni against the ray (o, inv); lim = 1.0001 * current t limit.
-CRT_DEV WideStep wide_node_test(const uint4* __restrict__ nodes, uint32_t ni, V3 o, V3 inv, uint32_t oinv, float lim) {
+CRT_DEV WideStep wide_node_test(const uint4* __restrict__ nodes, uint32_t ni, V3 o, V3 inv, uint32_t oinv, float lim, bool zray) {
     const uint4* p = nodes + 5 * (size_t)ni;
     const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
     const uint32_t ew = w0.w;
@@ -67,7 +67,16 @@ CRT_DEV WideStep wide_node_test(const uint4* __restrict__ nodes, uint32_t ni, V3
         const float tnz = fmaf(wide_byte(nz[w], k), bz, az), tfz = fmaf(wide_byte(fz[w], k), bz, az);
         const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
         const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, lim));
-        if (tmin <= fmaf(tmax, 1.0000004f, pad)) hits |= 1u << c;
+        bool hit = tmin <= fmaf(tmax, kSlabSlack, pad);
+        if (zray && hit) {                                   // parallel axes: near = lo bytes, far = hi bytes (oinv bit set)
+            const float qnx = wide_byte(nx[w], k), qfx = wide_byte(fx[w], k), qny = wide_byte(ny[w], k), qfy = wide_byte(fy[w], k),
+                        qnz = wide_byte(nz[w], k), qfz = wide_byte(fz[w], k);
+            const float ext = (fabsf(qfx - qnx) * sx + fabsf(qfy - qny) * sy) + fabsf(qfz - qnz) * sz;
+            if (inv.x != inv.x) hit = parallel_ok(fmaf(qnx, sx, __uint_as_float(w0.x)), fmaf(qfx, sx, __uint_as_float(w0.x)), o.x, tmax, ext);
+            if (hit && inv.y != inv.y) hit = parallel_ok(fmaf(qny, sy, __uint_as_float(w0.y)), fmaf(qfy, sy, __uint_as_float(w0.y)), o.y, tmax, ext);
+            if (hit && inv.z != inv.z) hit = parallel_ok(fmaf(qnz, sz, __uint_as_float(w0.z)), fmaf(qfz, sz, __uint_as_float(w0.z)), o.z, tmax, ext);
+        }
+        if (hit) hits |= 1u << c;
     }
     // children that exist (meta byte != 0), 4 bits per meta word, then node / leaf children from imask
     hits &= wide_nonzero_bytes(w1.z) | (wide_nonzero_bytes(w1.w) << 4);
@@ -98,6 +107,7 @@ CRT_DEV HitRec traverse_wide(const SceneView& sc, V3 o, V3 d, float tmax) {
     const uint4* nodes = (const uint4*)sc.nodes;
     const V3 inv = box_inv3(d);
     const uint32_t oinv = wide_octant(inv);
+    const bool zray = has_parallel_axis(inv);
     float tlimit = MODE == 0 ? FLT_MAX : tmax;
     uint2 stack[kWideStack];
     int sp = 0;
@@ -112,7 +122,7 @@ CRT_DEV HitRec traverse_wide(const SceneView& sc, V3 o, V3 d, float tmax) {
         g_bits &= ~(1u << pr);
         const uint32_t sl = (uint32_t)pr ^ oinv;
         const uint32_t ni = g_base + (uint32_t)__popc((g_bits >> 8) & ((1u << sl) - 1u));
-        WideStep s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f);
+        WideStep s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f, zray);
         while (s.leaf_hits) {
             const int lp = 31 - __clz((int)s.leaf_hits);
             s.leaf_hits &= ~(1u << lp);
@@ -164,7 +174,7 @@ CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fe
     best.t = FLT_MAX; best.slot = -1; best.face = -1;
     WideStep s;
     s.node_hits = s.leaf_hits = s.child_base = s.tri_base = s.meta_lo = s.meta_hi = s.imask = 0;
-    bool have = false, exhausted = false;
+    bool have = false, exhausted = false, zray = false;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
         if (idle) {
@@ -181,6 +191,7 @@ CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fe
                         const bool live = load(i, o, d, tmax);
                         inv = box_inv3(d);
                         oinv = wide_octant(inv);
+                        zray = has_parallel_axis(inv);
                         tlimit = MODE == 0 ? FLT_MAX : tmax;
                         best.t = FLT_MAX; best.slot = -1; best.face = -1;
                         sp = 0;
@@ -208,7 +219,7 @@ CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fe
                 g_bits &= ~(1u << pr);
                 const uint32_t sl = (uint32_t)pr ^ oinv;
                 const uint32_t ni = g_base + (uint32_t)__popc((g_bits >> 8) & ((1u << sl) - 1u));
-                s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f);
+                s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f, zray);
                 if (s.node_hits) {
                     if (g_bits & 0xffu) stack[sp++] = make_uint2(g_base, g_bits);
                     g_base = s.child_base;
@@ -291,7 +302,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
     int pending = 0;
-    bool have = false, exhausted = false;
+    bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
     for (;;) {
@@ -307,7 +318,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                 g_bits &= ~(1u << pr);
                 const uint32_t sl = (uint32_t)pr ^ oinv;
                 const uint32_t ni = g_base + (uint32_t)__popc((g_bits >> 8) & ((1u << sl) - 1u));
-                WideStep s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f);
+                WideStep s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f, zray);
                 if (s.leaf_hits) {
                     const int cnt = __popc(s.leaf_hits);
                     int pos = atomicAdd(&q.count, cnt);
@@ -396,6 +407,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                         const bool live = load(i, o, d, tmax);
                         inv = box_inv3(d);
                         oinv = wide_octant(inv);
+                        zray = has_parallel_axis(inv);
                         tlimit = MODE == 0 ? FLT_MAX : tmax;
                         q.ox[lane] = o.x; q.oy[lane] = o.y; q.oz[lane] = o.z;
                         q.dx[lane] = d.x; q.dy[lane] = d.y; q.dz[lane] = d.z;

@@ -65,7 +65,11 @@ typedef enum crt_estimator { CRT_ESTIMATOR_COMPAT = 0, CRT_ESTIMATOR_MIS = 1 } c
 /* CRT_BUILDER_LBVH: Morton-sorted binary radix tree emitted as 64-byte child-pair nodes (crt_bvh_node).
  * CRT_BUILDER_LBVH8: the same radix tree collapsed into 80-byte 8-wide nodes with 8-bit quantised child
  * boxes (crt_bvh8_node); bvh_thresh_n is clamped to 15. Hits and images do not depend on the builder. */
-typedef enum crt_builder { CRT_BUILDER_LBVH = 0, CRT_BUILDER_LBVH8 = 1 } crt_builder;
+/* Bit 1 selects the tree topology: CRT_BUILDER_PLOC / CRT_BUILDER_PLOC8 agglomerate the Morton-ordered triangles
+ * bottom-up by union-box area (parallel locally-ordered clustering, search radius 8) instead of splitting by key
+ * prefix; the tree costs a few more build kernels and needs about a third fewer node visits per ray
+ * (DESIGN.md "BVH build"). Node layouts, leaf rule and exports are those of LBVH / LBVH8. */
+typedef enum crt_builder { CRT_BUILDER_LBVH = 0, CRT_BUILDER_LBVH8 = 1, CRT_BUILDER_PLOC = 2, CRT_BUILDER_PLOC8 = 3 } crt_builder;
 typedef enum crt_ray_mode { CRT_RAY_CLOSEST = 0, CRT_RAY_ANY = 1 } crt_ray_mode;
 
 /* 64-byte BVH node as exported by crt_scene_export_bvh (DESIGN.md "Layout"). */

@@ -61,6 +61,7 @@ def lib():
     L.orc_render.argtypes = [vp, f32p, f32p, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_float,
                              C.c_int, C.c_uint32, C.c_int, C.c_int, i64p, vp, C.c_int]
     L.orc_wide8_build.argtypes = [vp, C.c_uint]
+    L.orc_wide8_build2.argtypes = [vp, C.c_uint, C.c_int]
     L.orc_wide8_get.argtypes = [vp, vp, vp, vp, vp]
     L.orc_resolve.argtypes = [i64p, C.c_int, C.c_uint32, vp, vp]
     L.orc_philox.argtypes = [u32p, u32p, u32p]
@@ -167,6 +168,7 @@ class Scene:
         return nodes, order, self.L.orc_refbvh_root(self.h)
 
     def build_new_bvh(self, thresh_n, builder=0):
+        """64-byte pair nodes. builder: 0 = Karras radix tree (LBVH), 2 = PLOC topology."""
         n = self.L.orc_newbvh_build(self.h, thresh_n, builder)
         nodes = np.zeros(n, PAIR_NODE)
         order = np.zeros(self.n_tris, np.int32)
@@ -213,9 +215,10 @@ class Scene:
         assert np.all(t[b] > eps) and np.all(rays[b, 3] - t[b] > eps)
         return True
 
-    def build_wide8(self, thresh_n):
-        """8-wide compressed BVH (80-byte nodes): returns nodes (n x 20 uint32), order, last, bounds."""
-        n = self.L.orc_wide8_build(self.h, thresh_n)
+    def build_wide8(self, thresh_n, builder=1):
+        """8-wide compressed BVH (80-byte nodes): returns nodes (n x 20 uint32), order, last, bounds.
+        builder: 1 = collapse of the Karras tree (LBVH8), 3 = collapse of the PLOC tree (PLOC8)."""
+        n = self.L.orc_wide8_build2(self.h, thresh_n, builder)
         nodes = np.zeros((n, 20), np.uint32)
         order = np.zeros(self.n_tris, np.int32)
         last = np.zeros(self.n_tris, np.uint8)

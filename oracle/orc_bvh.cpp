@@ -80,6 +80,11 @@ bool tri_test(const Tri& tr, V3 o, V3 d, float* t_out) {
 }
 
 static const float kEps = 0.00001f;     // Global.h:11
+// Slack of the new box tests: tmin <= tmax * (1 + 2^-17). It has to cover the triangle test's error, not only the
+// slab arithmetic: Moeller-Trumbore accepts points a few 1e-6 (relative to the distance) outside a small, far
+// triangle, so a shadow ray aimed AT a light-triangle vertex (veach-mis) passed the triangle test and failed a
+// 4-ulp box test of the pair-node tree, while the looser quantised boxes of the 8-wide tree let it through.
+static const float kSlabSlack = 1.00000762939453125f;
 
 // DeviceBVH.cuh:87-126, literally (including the NaN behaviour of the ?: min/max).
 static inline bool ref_hit_aabb(const RefNode& n, V3 o, V3 d, V3 inv) {
@@ -187,13 +192,14 @@ struct RadixTree {
     std::vector<V3> blo, bhi;                // boxes of the internal nodes
 };
 
-static void build_radix_tree(const Scene& s, RadixTree& rt) {
+// Steps 1-3: scene box, Morton keys, stable sort. Returns the sorted keys (empty when n == 0).
+static std::vector<uint64_t> morton_sort(const Scene& s, RadixTree& rt) {
     const int n = (int)s.tris.size();
     rt.n = n;
     rt.lo = V3{FLT_MAX, FLT_MAX, FLT_MAX};
     rt.hi = V3{-FLT_MAX, -FLT_MAX, -FLT_MAX};
     rt.order.clear(); rt.left.clear(); rt.right.clear(); rt.first.clear(); rt.last.clear(); rt.blo.clear(); rt.bhi.clear();
-    if (n == 0) return;
+    if (n == 0) return {};
     for (const Tri& t : s.tris) { rt.lo = vmin(rt.lo, t.lo); rt.hi = vmax(rt.hi, t.hi); }
     V3 ext = rt.hi - rt.lo;
     V3 scale{ext.x > 0 ? 2097152.0f / ext.x : 0.0f, ext.y > 0 ? 2097152.0f / ext.y : 0.0f,
@@ -209,9 +215,15 @@ static void build_radix_tree(const Scene& s, RadixTree& rt) {
     rt.order.resize(n);
     std::iota(rt.order.begin(), rt.order.end(), 0);
     std::stable_sort(rt.order.begin(), rt.order.end(), [&](int a, int b) { return key[a] < key[b]; });
-    if (n < 2) return;
     std::vector<uint64_t> skey(n);
     for (int i = 0; i < n; ++i) skey[i] = key[rt.order[i]];
+    return skey;
+}
+
+static void build_radix_tree(const Scene& s, RadixTree& rt) {
+    std::vector<uint64_t> skey = morton_sort(s, rt);
+    const int n = rt.n;
+    if (n < 2) return;
     // Karras radix tree: internal nodes 0..n-2
     Radix rx{skey, n};
     rt.left.resize(n - 1); rt.right.resize(n - 1); rt.first.resize(n - 1); rt.last.resize(n - 1);
@@ -259,13 +271,110 @@ static void build_radix_tree(const Scene& s, RadixTree& rt) {
     }
 }
 
+// =============================================================================================
+// PLOC topology (builders BUILDER_PLOC / PLOC8) - parallel locally-ordered clustering (Meister & Bittner
+// 2018), stated sequentially. It replaces step 4 (the Karras tree) by bottom-up agglomeration, which looks
+// at box areas instead of key prefixes and so copes with the large wall triangles next to dense meshes that
+// a Morton split handles badly. Specification (the CUDA builder reproduces every array bit for bit):
+//   * clusters start as the single triangles in Morton order (steps 1-3 unchanged);
+//   * one round: every cluster k finds nn(k) = the cluster j in [k-R, k+R], j != k, that minimises
+//     A(k, j) = half area of the union box, (ex*ey + ey*ez) + ez*ex with one rounding per operation;
+//     the "buddy" k ^ 1 is examined first, then the window by ascending j, and only a strictly smaller
+//     area replaces the choice - so among equal areas the buddy wins, and runs of identical or regularly
+//     tessellated triangles pair up (k, k ^ 1) instead of forming one long chain with a single mutual pair
+//     per round (257 copies of one triangle: 9 rounds instead of 256);
+//     k and j = nn(k) merge iff nn(j) == k; the new cluster takes the place of min(k, j), the other
+//     place is dropped, order otherwise kept; rounds repeat until one cluster is left;
+//   * merges are numbered in creation order (round by round, by position inside a round); node id =
+//     (n - 2) - creation index, so the root is node 0 and every child id is larger than its parent's;
+//     left child = the cluster that stood at the lower position;
+//   * triangle slots are the depth-first order of the finished tree (left before right), so every node
+//     again owns a contiguous slot range [first, last] - what the leaf rule and the wide collapse need.
+// =============================================================================================
+static const int kPlocRadius = 8;
+
+static void build_ploc_tree(const Scene& s, RadixTree& rt) {
+    morton_sort(s, rt);
+    const int n = rt.n;
+    if (n < 2) return;
+    const std::vector<int> morton = rt.order;            // Morton position -> face id
+    struct Cl { int ref; int count; V3 lo, hi; };         // ref < 0: ~Morton position of a triangle; else creation index
+    std::vector<Cl> cur(n), nxt;
+    for (int i = 0; i < n; ++i) cur[i] = Cl{~i, 1, s.tris[morton[i]].lo, s.tris[morton[i]].hi};
+    std::vector<int> cl(n - 1), cr(n - 1), ccount(n - 1);  // by creation index
+    std::vector<V3> clo(n - 1), chi(n - 1);
+    int created = 0, rounds = 0;
+    std::vector<int> nn;
+    while (cur.size() > 1) {
+        const int m = (int)cur.size();
+        nn.assign(m, -1);
+        for (int k = 0; k < m; ++k) {
+            auto area = [&](int j) {
+                V3 lo = vmin(cur[k].lo, cur[j].lo), hi = vmax(cur[k].hi, cur[j].hi);
+                float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+                return (ex * ey + ey * ez) + ez * ex;
+            };
+            float best = FLT_MAX;
+            int bj = -1;
+            const int buddy = k ^ 1;
+            if (buddy < m) { best = area(buddy); bj = buddy; }
+            for (int j = std::max(0, k - kPlocRadius); j <= std::min(m - 1, k + kPlocRadius); ++j) {
+                if (j == k || j == buddy) continue;
+                float a = area(j);
+                if (bj < 0 || a < best) { best = a; bj = j; }
+            }
+            nn[k] = bj;
+        }
+        nxt.clear();
+        for (int k = 0; k < m; ++k) {
+            const int j = nn[k];
+            if (nn[j] == k) {
+                if (k < j) {
+                    const int id = created++;
+                    cl[id] = cur[k].ref; cr[id] = cur[j].ref;
+                    ccount[id] = cur[k].count + cur[j].count;
+                    clo[id] = vmin(cur[k].lo, cur[j].lo); chi[id] = vmax(cur[k].hi, cur[j].hi);
+                    nxt.push_back(Cl{id, ccount[id], clo[id], chi[id]});
+                }                                       // k > j: dropped
+            } else nxt.push_back(cur[k]);
+        }
+        cur.swap(nxt);
+        ++rounds;
+    }
+    if (getenv("ORC_PLOC_DEBUG")) fprintf(stderr, "ploc: n=%d rounds=%d\n", n, rounds);
+    // node ids, slot ranges (top-down: a parent's id is smaller than its children's), final order
+    const int ni = n - 1;
+    rt.left.resize(ni); rt.right.resize(ni); rt.first.resize(ni); rt.last.resize(ni); rt.blo.resize(ni); rt.bhi.resize(ni);
+    auto node_of = [&](int creation) { return ni - 1 - creation; };
+    rt.first[0] = 0; rt.last[0] = n - 1;
+    std::vector<int> order(n);
+    for (int nd = 0; nd < ni; ++nd) {
+        const int c = ni - 1 - nd;
+        rt.blo[nd] = clo[c]; rt.bhi[nd] = chi[c];
+        const int f = rt.first[nd];
+        const int lcount = cl[c] < 0 ? 1 : ccount[cl[c]];
+        if (cl[c] < 0) { rt.left[nd] = ~f; order[f] = morton[~cl[c]]; }
+        else { const int ch = node_of(cl[c]); rt.left[nd] = ch; rt.first[ch] = f; rt.last[ch] = f + lcount - 1; }
+        const int g = f + lcount;
+        if (cr[c] < 0) { rt.right[nd] = ~g; order[g] = morton[~cr[c]]; }
+        else { const int ch = node_of(cr[c]); rt.right[nd] = ch; rt.first[ch] = g; rt.last[ch] = rt.last[nd]; }
+    }
+    rt.order = order;
+}
+
+// Topology stage of a builder id (bit 0 of the product's crt_builder is the node layout, bit 1 the topology).
+static void build_tree(const Scene& s, int builder, RadixTree& rt) {
+    if (builder & 2) build_ploc_tree(s, rt);
+    else build_radix_tree(s, rt);
+}
+
 void build_new_bvh(const Scene& s, unsigned thresh_n, int builder, NewBVH& out) {
     const int n = (int)s.tris.size();
     out.nodes.clear(); out.order.clear(); out.last.clear();
     out.builder = builder;
     if (thresh_n < 1) thresh_n = 1;
     RadixTree rt;
-    build_radix_tree(s, rt);
+    build_tree(s, builder, rt);
     out.lo = rt.lo; out.hi = rt.hi;
     if (n == 0) return;
     out.order = rt.order;
@@ -317,6 +426,20 @@ void build_new_bvh(const Scene& s, unsigned thresh_n, int builder, NewBVH& out) 
 // New traversal rule (DESIGN.md §"Traversal rule"): conservative slabs, near child first,
 // far child pushed, leaves postponed on the stack; t-culling against 1.0001 * current limit.
 // =============================================================================================
+// A direction component that is exactly zero has a NaN inverse (orc_math.h box_inv), so its plane distances drop out
+// of the min/max above; the axis is tested here instead: the ray stays at o on it, so o must lie inside [lo, hi],
+// widened by 2^-17 * (|o| + exit distance + box extent summed over the axes) - the same relative slack as kSlabSlack,
+// applied sideways: o is a computed hit point (a few ulp off its surface) and the triangle test's acceptance band scales
+// with the distance AND with the triangle's size (a ray 3e-5 outside the 556-unit ceiling triangle of cornell-box is
+// accepted; tests/golden/axis_planar_rays.npz). The extent is monotone up the tree, so an ancestor never culls what a
+// descendant accepts.
+// Without this test an axis-parallel ray (a hemisphere sample exactly along the normal of a wall, a few per frame)
+// is culled on one axis only and walks most of the tree: 35 ms for ONE ray of a 1.8 ms launch (profiles/r01_s15.md).
+static inline bool parallel_ok(float lo, float hi, float o, float texit, float ext) {
+    const float dlt = ((fabsf(o) + texit) + ext) * 7.62939453125e-06f;
+    return lo - o <= dlt && o - hi <= dlt;
+}
+
 static inline bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, V3 o, V3 inv,
                         float limit, float* enter) {
     float tx0 = (lox - o.x) * inv.x, tx1 = (hix - o.x) * inv.x;
@@ -325,7 +448,15 @@ static inline bool slab(float lox, float hix, float loy, float hiy, float loz, f
     float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
     float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), limit));
     *enter = tmin;
-    return tmin <= tmax * 1.0000004f;
+    if (!(tmin <= tmax * kSlabSlack)) return false;
+    // axes the ray is parallel to (inverse = NaN, see box_inv): the origin coordinate must lie in the box's interval
+    if (inv.x != inv.x || inv.y != inv.y || inv.z != inv.z) {
+        const float ext = ((hix - lox) + (hiy - loy)) + (hiz - loz);
+        if (inv.x != inv.x && !parallel_ok(lox, hix, o.x, tmax, ext)) return false;
+        if (inv.y != inv.y && !parallel_ok(loy, hiy, o.y, tmax, ext)) return false;
+        if (inv.z != inv.z && !parallel_ok(loz, hiz, o.z, tmax, ext)) return false;
+    }
+    return true;
 }
 
 Hit new_intersect(const Scene& s, const NewBVH& b, const Ray& r, int mode, TraceStats* st) {
@@ -409,13 +540,13 @@ static inline int exp_of_double(double v) {          // floor(log2 v) for a posi
 }
 }  // namespace
 
-void build_wide8_bvh(const Scene& s, unsigned thresh_n, Wide8BVH& out) {
+void build_wide8_bvh(const Scene& s, unsigned thresh_n, Wide8BVH& out, int builder) {
     const int n = (int)s.tris.size();
     out.nodes.clear(); out.order.clear(); out.last.clear();
     if (thresh_n < 1) thresh_n = 1;
     if (thresh_n > kWideMaxLeaf) thresh_n = kWideMaxLeaf;
     RadixTree rt;
-    build_radix_tree(s, rt);
+    build_tree(s, builder, rt);
     out.lo = rt.lo; out.hi = rt.hi;
     if (n == 0) return;
     out.order.assign(n, -1);
@@ -605,7 +736,15 @@ Hit wide8_intersect(const Scene& s, const Wide8BVH& b, const Ray& r, int mode, T
             const float tnz = fmaf((float)qnz[c], bz, az), tfz = fmaf((float)qfz[c], bz, az);
             const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, lim));
-            if (tmin <= fmaf(tmax, 1.0000004f, pad)) {
+            if (tmin <= fmaf(tmax, kSlabSlack, pad)) {
+                // parallel axes (NaN inverse: near = lo, far = hi bytes), same rule as the pair nodes
+                if (inv.x != inv.x || inv.y != inv.y || inv.z != inv.z) {
+                    const float ext = (fabsf((float)qfx[c] - (float)qnx[c]) * sx + fabsf((float)qfy[c] - (float)qny[c]) * sy) +
+                                      fabsf((float)qfz[c] - (float)qnz[c]) * sz;
+                    if (inv.x != inv.x && !parallel_ok(fmaf((float)qnx[c], sx, px), fmaf((float)qfx[c], sx, px), o.x, tmax, ext)) continue;
+                    if (inv.y != inv.y && !parallel_ok(fmaf((float)qny[c], sy, py), fmaf((float)qfy[c], sy, py), o.y, tmax, ext)) continue;
+                    if (inv.z != inv.z && !parallel_ok(fmaf((float)qnz[c], sz, pz), fmaf((float)qfz[c], sz, pz), o.z, tmax, ext)) continue;
+                }
                 if (meta[c] & 0x80) node_hits |= 1u << (c ^ oinv); else leaf_hits |= 1u << (c ^ oinv);
             }
         }

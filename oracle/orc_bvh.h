@@ -54,7 +54,8 @@ struct NewBVH {
     V3 lo, hi;                        // scene bounds
     int builder = 0;
 };
-enum Builder { BUILDER_LBVH = 0 };
+// same numbering as the product's crt_builder: bit 0 = 8-wide node layout, bit 1 = PLOC topology
+enum Builder { BUILDER_LBVH = 0, BUILDER_LBVH8 = 1, BUILDER_PLOC = 2, BUILDER_PLOC8 = 3 };
 void build_new_bvh(const Scene& s, unsigned thresh_n, int builder, NewBVH& out);
 
 // mode 0: closest hit (t > 1e-5, ties -> lower face id); mode 1: any hit with
@@ -78,7 +79,7 @@ struct Wide8BVH {
     V3 lo, hi;
 };
 static const unsigned kWideMaxLeaf = 15;      // a leaf holds at most this many triangles (7-bit offsets)
-void build_wide8_bvh(const Scene& s, unsigned thresh_n, Wide8BVH& out);
+void build_wide8_bvh(const Scene& s, unsigned thresh_n, Wide8BVH& out, int builder = BUILDER_LBVH8);
 Hit wide8_intersect(const Scene& s, const Wide8BVH& b, const Ray& r, int mode, TraceStats* st);
 
 }  // namespace orc

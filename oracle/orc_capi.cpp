@@ -119,6 +119,11 @@ void orc_newbvh_get(orc_scene* h, void* nodes64, int* order, uint8_t* last, floa
 }
 
 // ---- 8-wide BVH
+int orc_wide8_build2(orc_scene* h, unsigned thresh_n, int builder) {
+    build_wide8_bvh(h->s, thresh_n, h->wb, builder);
+    h->has_wide = true;
+    return (int)h->wb.nodes.size();
+}
 int orc_wide8_build(orc_scene* h, unsigned thresh_n) {
     build_wide8_bvh(h->s, thresh_n, h->wb);
     h->has_wide = true;

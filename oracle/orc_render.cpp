@@ -100,6 +100,13 @@ struct Ctx {
     const Wide8BVH* wide;          // when set, rays go through the 8-wide BVH (same hits, other visit counts)
 };
 static inline Hit trace(const Ctx& c, const Ray& r, int mode, TraceStats* st) {
+    if (getenv("ORC_DEBUG_XCHECK") && c.wide) {                 // development aid: report rays on which the two BVHs disagree
+        Hit a = wide8_intersect(c.s, *c.wide, r, mode, nullptr), b = new_intersect(c.s, c.b, r, mode, nullptr), e = brute_intersect(c.s, r, mode);
+        bool bad = mode == 0 ? (a.face != b.face || a.t != b.t) : ((a.face >= 0) != (b.face >= 0));
+        if (bad)
+            fprintf(stderr, "XCHECK mode %d ray o %.9g %.9g %.9g d %.9g %.9g %.9g tmax %.9g | wide %d %.9g pair %d %.9g brute %d %.9g\n", mode, r.o.x, r.o.y,
+                    r.o.z, r.d.x, r.d.y, r.d.z, r.tmax, a.face, a.t, b.face, b.t, e.face, e.t);
+    }
     return c.wide ? wide8_intersect(c.s, *c.wide, r, mode, st) : new_intersect(c.s, c.b, r, mode, st);
 }
 }  // namespace

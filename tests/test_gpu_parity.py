@@ -298,7 +298,7 @@ def test_mis_estimator_options_and_tail(gpu, orc, monkeypatch, tail):
     assert np.array_equal(total, full)
 
 
-@pytest.mark.parametrize("builder", [0, 1])
+@pytest.mark.parametrize("builder", [0, 1, 2, 3])
 @pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])
 def test_rays_lying_in_box_planes(gpu, orc, scene_files, name, builder):
     """Rays from surface points with one direction component exactly zero (they lie in box planes): the committed
@@ -319,6 +319,22 @@ def test_rays_lying_in_box_planes(gpu, orc, scene_files, name, builder):
     anyr = fresh.copy()
     anyr[:, 3] = rng.uniform(0, 900.0 if name == "cornell-box" else 30.0, len(anyr)).astype(np.float32)
     batches.append((anyr, 1))
+    # rays exactly along a coordinate axis (two zero components): must be culled on both parallel axes - the kernel time
+    # bound below fails when such rays walk the whole tree (35 ms per ray on cornell-box, profiles/r01_s15.md)
+    lo, hi = b.build_new_bvh(cfg.bvh_thresh_n)[3][:3], b.build_new_bvh(cfg.bvh_thresh_n)[3][3:]
+    n = 100000
+    ax = np.zeros((n, 8), np.float32)
+    ax[:, 0:3] = rng.uniform(lo, hi, (n, 3))
+    ax[np.arange(n), 4 + rng.integers(0, 3, n)] = rng.choice([-1.0, 1.0], n)
+    ax[:, 3] = FLT_MAX
+    t, f, ms = a.trace_rays(ax, 0)
+    ot, of = b.trace(ax, which=0, mode=0)
+    assert np.array_equal(f, of) and np.array_equal(t.view(np.uint32), ot.view(np.uint32))
+    assert ms < 20.0, "axis-parallel rays took %.1f ms" % ms
+    if name == "veach-mis":      # the shadow ray through a box corner (tests/test_oracle.py::test_shadow_ray_through_a_box_corner)
+        corner = np.array([[-5, 1.35669553, 2.52801561, 8.02512932, 0.570246458, 0.669184923, -0.476456344, 0]], np.float32)
+        t, f, _ = a.trace_rays(corner, 1)
+        assert f[0] == 2022
     for rays, mode in batches:
         t, f, _ = a.trace_rays(rays, mode)
         if mode == 0:

@@ -417,3 +417,48 @@ def test_wide8_degenerate_inputs_and_render(orc, scene_files):
     a1, s1 = S.render([28.2792, 5.2, 1.23612e-06], M, 0.5256, 80, 60, 0, 2, 0.6, 1, wide=True)
     assert np.array_equal(a0, a1) and s0["shadow_rays"] == s1["shadow_rays"]
     assert s1["closest_inner"] < s0["closest_inner"]
+
+
+def test_axis_parallel_rays_are_culled_on_their_parallel_axes(orc, crt, scene_files):
+    """A direction component that is exactly 0 has a NaN inverse, so the slab arithmetic ignores that axis; the axis is
+    tested by containment of the origin instead (oracle parallel_ok). Without that test a ray exactly along a wall normal
+    (sincos_2pi is exact at the quadrants, so hemisphere samples produce a few per frame) was culled on ONE axis only
+    and walked most of the tree: 35 ms for one ray inside a 1.8 ms k_extend launch (profiles/r01_s15.md)."""
+    name = "cornell-box"
+    cfg = crt.load_config(scene_files[name]["cfg_path"])
+    S = orc.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    S.build_new_bvh(cfg.bvh_thresh_n)
+    S.build_wide8(cfg.bvh_thresh_n)
+    rng = np.random.default_rng(2)
+    n = 2000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform([5, 5, 5], [550, 540, 550], (n, 3))
+    axis = rng.integers(0, 3, n)
+    rays[np.arange(n), 4 + axis] = rng.choice([-1.0, 1.0], n)       # two zero components
+    rays[:, 3] = np.finfo(np.float32).max
+    planar = _surface_rays_with_zero_components(orc, S, cfg, rng)    # one zero component, origins on surfaces
+    for batch, bound in ((rays, 80), (planar, 120)):
+        tb, fb = S.trace(batch, which=3, mode=0)
+        for which in (0, 4):
+            t, f, st = S.trace(batch, which=which, mode=0, want_stats=True)
+            assert np.array_equal(f, fb) and np.array_equal(t.view(np.uint32), tb.view(np.uint32))
+            assert st["inner"] / st["rays"] < bound, (which, st)
+
+
+def test_shadow_ray_through_a_box_corner(orc, crt, scene_files):
+    """veach-mis, C2 pixel 332442: a shadow ray aimed at a light-triangle vertex. Moeller-Trumbore accepts the light's own
+    triangle 1e-5 in front of the sample point (the reference's self-occlusion E8), but the ray enters that triangle's
+    leaf box through its corner, where the 4-ulp slab test of the pair nodes saw an empty interval while the 8-wide
+    tree's looser boxes did not. The box slack is 2^-17 now (kSlabSlack); every BVH kind reports the blocker."""
+    name = "veach-mis"
+    cfg = crt.load_config(scene_files[name]["cfg_path"])
+    S = orc.Scene().add_obj(scene_files[name]["obj"], scene_files[name]["dir"])
+    ray = np.array([[-5, 1.35669553, 2.52801561, 8.02512932, 0.570246458, 0.669184923, -0.476456344, 0]], np.float32)
+    tb, fb = S.trace(ray, which=3, mode=1)
+    assert fb[0] == 2022
+    for topo in (0, 2):
+        S.build_new_bvh(cfg.bvh_thresh_n, topo)
+        S.build_wide8(cfg.bvh_thresh_n, topo | 1)
+        for which in (0, 4):
+            t, f = S.trace(ray, which=which, mode=1)
+            assert f[0] == 2022 and t[0] == tb[0], (topo, which)

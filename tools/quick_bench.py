@@ -8,7 +8,8 @@ from tools import scene_fixture as sf
 
 def main():
     tmp = tempfile.mkdtemp()
-    builders = [a for a in sys.argv[1:] if a in ("lbvh", "lbvh8")] or ["lbvh"]
+    B = {"lbvh": 0, "lbvh8": 1, "ploc": 2, "ploc8": 3}
+    builders = [a for a in sys.argv[1:] if a in B] or ["lbvh"]
     W, H, spp = 1920, 1080, 16
     for name in ("cornell-box", "veach-mis"):
         cfg_path = sf.unpack(sf.fixture(name), os.path.join(tmp, name))
@@ -16,7 +17,7 @@ def main():
         d = os.path.dirname(cfg_path)
         for b in builders:
             S = crt.Scene().add_obj(os.path.join(d, cfg.OBJ_paths[0][0]), d)
-            S.set_BVH(cfg.bvh_thresh_n, builder={"lbvh": 0, "lbvh8": 1}[b])
+            S.set_BVH(cfg.bvh_thresh_n, builder=B[b])
             M = crt.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
             for est in (0, 1):
                 R = crt.Render(S, W, H, spp, cfg.P_RR, cfg.light_sample_n)
