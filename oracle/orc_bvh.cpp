@@ -363,8 +363,10 @@ static void build_ploc_tree(const Scene& s, RadixTree& rt) {
 }
 
 // Topology stage of a builder id (bit 0 of the product's crt_builder is the node layout, bit 1 the topology).
-static void build_tree(const Scene& s, int builder, RadixTree& rt) {
-    if (builder & 2) build_ploc_tree(s, rt);
+// A scene of at most thresh_n triangles is ONE leaf: no topology is needed and its slots keep the Morton order,
+// whatever the builder (the GPU builder skips the PLOC rounds in that case, crt_bvh_build.cu build_bvh_device).
+static void build_tree(const Scene& s, int builder, unsigned thresh_n, RadixTree& rt) {
+    if ((builder & 2) && s.tris.size() > (size_t)thresh_n) build_ploc_tree(s, rt);
     else build_radix_tree(s, rt);
 }
 
@@ -374,7 +376,7 @@ void build_new_bvh(const Scene& s, unsigned thresh_n, int builder, NewBVH& out) 
     out.builder = builder;
     if (thresh_n < 1) thresh_n = 1;
     RadixTree rt;
-    build_tree(s, builder, rt);
+    build_tree(s, builder, thresh_n, rt);
     out.lo = rt.lo; out.hi = rt.hi;
     if (n == 0) return;
     out.order = rt.order;
@@ -546,7 +548,7 @@ void build_wide8_bvh(const Scene& s, unsigned thresh_n, Wide8BVH& out, int build
     if (thresh_n < 1) thresh_n = 1;
     if (thresh_n > kWideMaxLeaf) thresh_n = kWideMaxLeaf;
     RadixTree rt;
-    build_tree(s, builder, rt);
+    build_tree(s, builder, thresh_n, rt);
     out.lo = rt.lo; out.hi = rt.hi;
     if (n == 0) return;
     out.order.assign(n, -1);

@@ -110,6 +110,19 @@ def test_ploc_needs_fewer_node_visits_on_the_shipped_scenes(orc, crt, scene_file
     assert np.array_equal(acc, res[0][0])
 
 
+def test_ploc_single_leaf_scene_keeps_the_morton_order(orc):
+    """n <= thresh_n: the scene is one leaf, no topology is built, and every builder emits the Morton order
+    (first GPU run of the PLOC builder, session 16: the oracle permuted the slots of a 5-triangle leaf)."""
+    rng = np.random.default_rng(5 * 13 + 8)
+    verts = soup(rng, 5, extent=20.0, size=0.7)
+    S = _scene(orc, verts)
+    ref = S.build_new_bvh(8, 0)
+    for b in (PLOC, PLOC8):
+        got = S.build_wide8(8, b) if b & 1 else S.build_new_bvh(8, b)
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    assert ref[0].tobytes() == S.build_new_bvh(8, PLOC)[0].tobytes()
+
+
 def test_ploc_degenerate_inputs(orc):
     one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
     for n in (1, 2, 3, 9):
