@@ -215,6 +215,9 @@ struct HitRec { float t; int slot; int face; };
 #ifndef CRT_LD256
 #define CRT_LD256 0
 #endif
+#ifndef CRT_N3_64
+#define CRT_N3_64 0
+#endif
 CRT_DEV void load_node(const float4* __restrict__ nodes, int cur, float4& n0, float4& n1, float4& n2, float4& n3) {
     const float4* p = nodes + 4 * (size_t)cur;
 #if CRT_LD256
@@ -223,8 +226,32 @@ CRT_DEV void load_node(const float4* __restrict__ nodes, int cur, float4& n0, fl
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w) : "l"(p + 2));
 #else
-    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
+    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2);
+#if CRT_N3_64
+    { const float2 ch = __ldg((const float2*)(p + 3)); n3 = make_float4(ch.x, ch.y, 0.0f, 0.0f); }   // children only: 56 of the 64 bytes
+#else
+    n3 = __ldg(p + 3);
 #endif
+#endif
+}
+
+// One triangle record (48-byte stride). CRT_TRI40 = 1: the record is (v1, face|last) (e1, e2.x) (e2.y, e2.z, mat, 0) and the
+// test reads 40 bytes (LDG.128, LDG.128, LDG.64) instead of 48 - the traversal kernels are bound by the L1 data pipe
+// (profiles/r01_s17.md), which moves what the lanes ask for, used or not.
+#ifndef CRT_TRI40
+#define CRT_TRI40 0
+#endif
+CRT_DEV uint32_t load_tri(const float4* __restrict__ tri_geom, int slot, V3& v1, V3& e1, V3& e2) {
+    const float4* p = tri_geom + 3 * (size_t)slot;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    v1 = mk3(a); e1 = mk3(b);
+#if CRT_TRI40
+    const float2 c = __ldg((const float2*)(p + 2));
+    e2 = mk3(b.w, c.x, c.y);
+#else
+    e2 = mk3(__ldg(p + 2));
+#endif
+    return __float_as_uint(a.w);
 }
 
 // MODE 0: closest hit, t > 1e-5, ties -> lower face id (reference DeviceBVH.cuh:128-170 semantics
@@ -262,13 +289,11 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
         } else {
             int slot = ~cur;
             for (;; ++slot) {
-                const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
-                const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
-                const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
-                const uint32_t fw = __float_as_uint(a.w);
+                V3 tv1, te1, te2;
+                const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
                 const int face = (int)(fw & ~kLastBit);
                 float t;
-                if (tri_test(mk3(a), mk3(b), mk3(c), o, d, &t) && t > kEps) {
+                if (tri_test(tv1, te1, te2, o, d, &t) && t > kEps) {
                     if (MODE == 0) {
                         if (t < best.t || (t == best.t && face < best.face)) {
                             best.t = t; best.slot = slot; best.face = face;
@@ -379,13 +404,11 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
                 int slot = ~cur;
                 bool stop = false;
                 for (;; ++slot) {
-                    const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
-                    const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
-                    const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
-                    const uint32_t fw = __float_as_uint(a.w);
+                    V3 tv1, te1, te2;
+                    const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
                     const int face = (int)(fw & ~kLastBit);
                     float t;
-                    if (tri_test(mk3(a), mk3(b), mk3(c), o, d, &t) && t > kEps) {
+                    if (tri_test(tv1, te1, te2, o, d, &t) && t > kEps) {
                         if (MODE == 0) {
                             if (t < best.t || (t == best.t && face < best.face)) {
                                 best.t = t; best.slot = slot; best.face = face;
@@ -428,6 +451,9 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
 #endif
 #ifndef CRT_QSTEPS
 #define CRT_QSTEPS 6
+#endif
+#ifndef CRT_QBALLOT
+#define CRT_QBALLOT 0
 #endif
 // CRT_SSTACK = N > 0: the first N entries of every lane's traversal stack live in shared memory, laid out
 // [entry][thread] so that a push / pop is one conflict-free wavefront whatever the lanes' depths are; a
@@ -474,6 +500,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
     int pending = 0;
+    int qn = 0;                                            // CRT_QBALLOT: queued leaves, the same value in every lane
     bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
@@ -481,6 +508,20 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
         // A. node steps; a leaf in hand goes to the queue and the lane takes the next entry of its stack
 #pragma unroll
         for (int r = 0; r < kQueueSteps; ++r) {
+#if CRT_QBALLOT
+            {   // the queue belongs to this warp and every lane is here: positions from a ballot, no shared atomic
+                const bool leaf = cur < 0;
+                const unsigned lm = __ballot_sync(kFull, leaf);
+                if (leaf) {
+                    const int pos = qn + __popc(lm & lt_mask);
+                    q.q_slot[pos] = ~cur;
+                    q.q_lane[pos] = (unsigned char)lane;
+                    pending++;
+                    cur = sp ? pop() : kDone;
+                }
+                qn += __popc(lm);
+            }
+#else
             if (cur < 0) {
                 const int pos = atomicAdd(&q.count, 1);
                 q.q_slot[pos] = ~cur;
@@ -488,6 +529,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                 pending++;
                 cur = sp ? pop() : kDone;
             }
+#endif
             if (cur >= 0 && cur != kDone) {
                 if (cur == kEmptyChild) {
                     cur = sp ? pop() : kDone;
@@ -513,7 +555,11 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
         // B. flush the leaf queue when it is full enough, or when no lane has a node or leaf in hand
         const unsigned walking = __ballot_sync(kFull, cur != kDone);
         __syncwarp();
+#if CRT_QBALLOT
+        const int q_count = qn;
+#else
         const int q_count = q.count;
+#endif
         if (q_count >= kQueueFlush || (walking == 0 && q_count > 0)) {
             for (int base = 0; base < q_count; base += 32) {
                 const int k = base + lane;
@@ -525,12 +571,10 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                     const V3 ro = mk3(q.ox[owner], q.oy[owner], q.oz[owner]), rd = mk3(q.dx[owner], q.dy[owner], q.dz[owner]);
                     const float rtmax = q.tmax[owner];
                     for (;; ++slot) {
-                        const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
-                        const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
-                        const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
-                        const uint32_t fw = __float_as_uint(a.w);
+                        V3 tv1, te1, te2;
+                        const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
                         float t;
-                        if (tri_test(mk3(a), mk3(b), mk3(c), ro, rd, &t) && t > kEps && (MODE == 0 || rtmax - t > kEps)) {
+                        if (tri_test(tv1, te1, te2, ro, rd, &t) && t > kEps && (MODE == 0 || rtmax - t > kEps)) {
                             const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (fw & ~kLastBit);
                             if (key < mykey) { mykey = key; myslot = slot; }
                         }
@@ -542,7 +586,11 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                 if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
                 __syncwarp();
             }
+#if CRT_QBALLOT
+            qn = 0;
+#else
             if (lane == 0) q.count = 0;
+#endif
             pending = 0;
             if (have) {
                 const unsigned long long b = q.best[lane];

@@ -128,13 +128,11 @@ CRT_DEV HitRec traverse_wide(const SceneView& sc, V3 o, V3 d, float tmax) {
             s.leaf_hits &= ~(1u << lp);
             int slot = wide_leaf_slot(s, lp, oinv);
             for (;; ++slot) {
-                const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
-                const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
-                const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
-                const uint32_t fw = __float_as_uint(a.w);
+                V3 tv1, te1, te2;
+                const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
                 const int face = (int)(fw & ~kLastBit);
                 float t;
-                if (tri_test(mk3(a), mk3(b), mk3(c), o, d, &t) && t > kEps) {
+                if (tri_test(tv1, te1, te2, o, d, &t) && t > kEps) {
                     if (MODE == 0) {
                         if (t < best.t || (t == best.t && face < best.face)) {
                             best.t = t; best.slot = slot; best.face = face;
@@ -232,13 +230,11 @@ CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fe
                 s.leaf_hits &= ~(1u << lp);
                 int slot = wide_leaf_slot(s, lp, oinv);
                 for (;; ++slot) {
-                    const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
-                    const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
-                    const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
-                    const uint32_t fw = __float_as_uint(a.w);
+                    V3 tv1, te1, te2;
+                    const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
                     const int face = (int)(fw & ~kLastBit);
                     float t;
-                    if (tri_test(mk3(a), mk3(b), mk3(c), o, d, &t) && t > kEps) {
+                    if (tri_test(tv1, te1, te2, o, d, &t) && t > kEps) {
                         if (MODE == 0) {
                             if (t < best.t || (t == best.t && face < best.face)) {
                                 best.t = t; best.slot = slot; best.face = face;
@@ -302,6 +298,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
     int pending = 0;
+    int qn = 0;                                            // CRT_QBALLOT: queued leaves, the same value in every lane
     bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
@@ -313,12 +310,23 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                 const uint2 e = stack[--sp];
                 g_base = e.x; g_bits = e.y;
             }
+#if CRT_QBALLOT
+            int cnt = 0;
+            uint32_t leaf_bits = 0;
+            WideStep lstep;
+            lstep.tri_base = lstep.meta_lo = lstep.meta_hi = 0;
+#endif
             if (g_bits & 0xffu) {
                 const int pr = 31 - __clz((int)(g_bits & 0xffu));
                 g_bits &= ~(1u << pr);
                 const uint32_t sl = (uint32_t)pr ^ oinv;
                 const uint32_t ni = g_base + (uint32_t)__popc((g_bits >> 8) & ((1u << sl) - 1u));
                 WideStep s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f, zray);
+#if CRT_QBALLOT
+                cnt = __popc(s.leaf_hits);
+                leaf_bits = s.leaf_hits;
+                lstep = s;
+#else
                 if (s.leaf_hits) {
                     const int cnt = __popc(s.leaf_hits);
                     int pos = atomicAdd(&q.count, cnt);
@@ -331,17 +339,39 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                         ++pos;
                     }
                 }
+#endif
                 if (s.node_hits) {
                     if (g_bits & 0xffu) stack[sp++] = make_uint2(g_base, g_bits);
                     g_base = s.child_base;
                     g_bits = (s.imask << 8) | s.node_hits;
                 }
             }
+#if CRT_QBALLOT
+            {   // the queue belongs to this warp and every lane is here: exclusive prefix of cnt (<= 8, four bits) from four
+                // ballots instead of a shared atomic that serialises the lanes
+                const unsigned b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2),
+                               b2 = __ballot_sync(kFull, cnt & 4), b3 = __ballot_sync(kFull, cnt & 8);
+                int pos = qn + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask) + 8 * __popc(b3 & lt_mask);
+                qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+                pending += cnt;
+                while (leaf_bits) {
+                    const int lp = 31 - __clz((int)leaf_bits);
+                    leaf_bits &= ~(1u << lp);
+                    q.q_slot[pos] = wide_leaf_slot(lstep, lp, oinv);
+                    q.q_lane[pos] = (unsigned char)lane;
+                    ++pos;
+                }
+            }
+#endif
         }
         // B. flush the leaf queue when it is full enough, or when no lane has a node in hand
         const unsigned walking = __ballot_sync(kFull, (g_bits & 0xffu) != 0u || sp > 0);
         __syncwarp();
+#if CRT_QBALLOT
+        const int q_count = qn;
+#else
         const int q_count = q.count;
+#endif
         if (q_count >= kWQFlush || (walking == 0 && q_count > 0)) {
             for (int base = 0; base < q_count; base += 32) {
                 const int k = base + lane;
@@ -353,12 +383,10 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                     const V3 ro = mk3(q.ox[owner], q.oy[owner], q.oz[owner]), rd = mk3(q.dx[owner], q.dy[owner], q.dz[owner]);
                     const float rtmax = q.tmax[owner];
                     for (;; ++slot) {
-                        const float4 a = __ldg(sc.tri_geom + 3 * (size_t)slot + 0);
-                        const float4 b = __ldg(sc.tri_geom + 3 * (size_t)slot + 1);
-                        const float4 c = __ldg(sc.tri_geom + 3 * (size_t)slot + 2);
-                        const uint32_t fw = __float_as_uint(a.w);
+                        V3 tv1, te1, te2;
+                        const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
                         float t;
-                        if (tri_test(mk3(a), mk3(b), mk3(c), ro, rd, &t) && t > kEps && (MODE == 0 || rtmax - t > kEps)) {
+                        if (tri_test(tv1, te1, te2, ro, rd, &t) && t > kEps && (MODE == 0 || rtmax - t > kEps)) {
                             const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (fw & ~kLastBit);
                             if (key < mykey) { mykey = key; myslot = slot; }
                         }
@@ -370,7 +398,11 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                 if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
                 __syncwarp();
             }
+#if CRT_QBALLOT
+            qn = 0;
+#else
             if (lane == 0) q.count = 0;
+#endif
             pending = 0;
             if (have) {
                 const unsigned long long b = q.best[lane];
