@@ -43,7 +43,7 @@ class Workload:
         import numpy as np
         import cudaraytracing_b200 as crt
         self.name = name
-        self.builder = BUILDERS[os.environ.get("CRT_BUILDER", "ploc")]
+        self.builder = BUILDERS[os.environ.get("CRT_BUILDER", "ploc8")]
         source, W, H, spp, self.desc = WORKLOADS[name]
         self.source = source
         self.tmp = tempfile.mkdtemp(prefix="crt_bench_")
@@ -534,7 +534,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--builder", default=None, choices=sorted(BUILDERS), help="BVH topology + node layout (default: CRT_BUILDER or ploc)")
+    ap.add_argument("--builder", default=None, choices=sorted(BUILDERS), help="BVH topology + node layout (default: CRT_BUILDER or ploc8)")
     ap.add_argument("--ref-spp", type=int, default=4, help="reference arm: samples per pixel of the bounded sample (<=0: full)")
     args = ap.parse_args()
     if args.builder:

@@ -213,7 +213,7 @@ struct HitRec { float t; int slot; int face; };
 // the traversal kernels are bound by L1 data-pipe wavefronts (profiles/r01_s11.md), which are paid per load
 // instruction and distinct line.
 #ifndef CRT_LD256
-#define CRT_LD256 0
+#define CRT_LD256 1
 #endif
 #ifndef CRT_N3_64
 #define CRT_N3_64 0
@@ -453,14 +453,14 @@ CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, 
 #define CRT_QSTEPS 6
 #endif
 #ifndef CRT_QBALLOT
-#define CRT_QBALLOT 0
+#define CRT_QBALLOT 1      // queue positions from one ballot instead of a shared atomicAdd that serialises the lanes (+2 %, r01_s18)
 #endif
 // CRT_SSTACK = N > 0: the first N entries of every lane's traversal stack live in shared memory, laid out
 // [entry][thread] so that a push / pop is one conflict-free wavefront whatever the lanes' depths are; a
 // local-memory stack costs one L1 wavefront per distinct depth in the warp, and the traversal kernels are
 // bound by L1 wavefronts (profiles/r01_s11.md). Deeper entries spill to the local array.
 #ifndef CRT_SSTACK
-#define CRT_SSTACK 0
+#define CRT_SSTACK 8       // with CRT_LD256 and CRT_QBALLOT: +7 % on cornell-box, +3 % on veach-mis (profiles/r01_s18.md)
 #endif
 static constexpr int kSharedStack = CRT_SSTACK;
 static constexpr int kQueueFlush = CRT_QFLUSH;       // queued leaves that trigger a flush

@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
     std::string config = "config.json", out = "out.png", root = ".";
     std::string checkpoint;
     long spp = -1, seed = -1, width = -1, height = -1, chunk_spp = 64, stop_after = -1;
-    int estimator = -1, device = 0, builder = CRT_BUILDER_PLOC;
+    int estimator = -1, device = 0, builder = CRT_BUILDER_PLOC8;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };

@@ -633,11 +633,19 @@ CRT_DEV void probe_resolve(const SceneView& sc, int probe_slot, V3 w, uint32_t p
 }
 
 // EST: CRT_ESTIMATOR_COMPAT (0) or CRT_ESTIMATOR_MIS (1)
+// Resident blocks per SM asked of the compiler. The compat vertex is a long dependent chain of IEEE divisions and square
+// roots behind three levels of dependent loads (queue -> triangle -> material / light): at 108 registers only 16 warps
+// per SM hide it (warps active 24 %, profiles/r01_s17.md). Capping registers at 64 (a few spilled words) takes the
+// stage from 14.7 to 10.3 ms on veach-mis and from 4.70 to 4.14 ms on cornell-box (1080p spp 16, r01_s18.md); the
+// mis vertex (fewer live values, one light sample) gets slower under the same cap and keeps the compiler's choice.
 #ifndef CRT_SHADE_MINB
-#define CRT_SHADE_MINB 1
+#define CRT_SHADE_MINB 8
+#endif
+#ifndef CRT_SHADE_MINB_MIS
+#define CRT_SHADE_MINB_MIS 1
 #endif
 template <int EST>
-__global__ void __launch_bounds__(128, CRT_SHADE_MINB) k_shade(SceneView sc, Counters* c, RenderParamsDev p,
+__global__ void __launch_bounds__(128, EST == CRT_ESTIMATOR_COMPAT ? CRT_SHADE_MINB : CRT_SHADE_MINB_MIS) k_shade(SceneView sc, Counters* c, RenderParamsDev p,
                                                       const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                       const float4* __restrict__ q_T, const float* __restrict__ q_pdf,
                                                       float* __restrict__ n_pdf, const float* __restrict__ hit_t,

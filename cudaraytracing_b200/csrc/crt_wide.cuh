@@ -265,10 +265,15 @@ CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fe
 // has a node left) the whole warp tests them, one entry per lane; owners' best hits are combined with a
 // 64-bit shared atomicMin on (t bits, face id). Lanes walk with the t-limit of the last flush.
 #ifndef CRT_WQFLUSH
-#define CRT_WQFLUSH 24
+#define CRT_WQFLUSH 16
 #endif
 #ifndef CRT_WQSTEPS
 #define CRT_WQSTEPS 2
+#endif
+// 1: queue positions from four bit-sliced ballots instead of the shared atomicAdd. Measured slower here (-1 %, B200,
+// profiles/r01_s18.md): the wide kernels are bound by ALU issue, not by the L1 data pipe, unlike the pair-node kernels.
+#ifndef CRT_WQBALLOT
+#define CRT_WQBALLOT 0
 #endif
 static constexpr int kWQFlush = CRT_WQFLUSH;
 static constexpr int kWQSteps = CRT_WQSTEPS;
@@ -298,7 +303,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
     int pending = 0;
-    int qn = 0;                                            // CRT_QBALLOT: queued leaves, the same value in every lane
+    int qn = 0;                                            // CRT_WQBALLOT: queued leaves, the same value in every lane
     bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
@@ -310,7 +315,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                 const uint2 e = stack[--sp];
                 g_base = e.x; g_bits = e.y;
             }
-#if CRT_QBALLOT
+#if CRT_WQBALLOT
             int cnt = 0;
             uint32_t leaf_bits = 0;
             WideStep lstep;
@@ -322,7 +327,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                 const uint32_t sl = (uint32_t)pr ^ oinv;
                 const uint32_t ni = g_base + (uint32_t)__popc((g_bits >> 8) & ((1u << sl) - 1u));
                 WideStep s = wide_node_test(nodes, ni, o, inv, oinv, tlimit * 1.0001f, zray);
-#if CRT_QBALLOT
+#if CRT_WQBALLOT
                 cnt = __popc(s.leaf_hits);
                 leaf_bits = s.leaf_hits;
                 lstep = s;
@@ -346,7 +351,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                     g_bits = (s.imask << 8) | s.node_hits;
                 }
             }
-#if CRT_QBALLOT
+#if CRT_WQBALLOT
             {   // the queue belongs to this warp and every lane is here: exclusive prefix of cnt (<= 8, four bits) from four
                 // ballots instead of a shared atomic that serialises the lanes
                 const unsigned b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2),
@@ -367,7 +372,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
         // B. flush the leaf queue when it is full enough, or when no lane has a node in hand
         const unsigned walking = __ballot_sync(kFull, (g_bits & 0xffu) != 0u || sp > 0);
         __syncwarp();
-#if CRT_QBALLOT
+#if CRT_WQBALLOT
         const int q_count = qn;
 #else
         const int q_count = q.count;
@@ -398,7 +403,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                 if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
                 __syncwarp();
             }
-#if CRT_QBALLOT
+#if CRT_WQBALLOT
             qn = 0;
 #else
             if (lane == 0) q.count = 0;
