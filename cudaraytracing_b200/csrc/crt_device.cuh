@@ -322,6 +322,60 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
 //   * "while-while" phases (Aila & Laine 2009): all lanes walk inner nodes until each holds a leaf, then
 //     all lanes intersect their leaf, which keeps lanes on the same instructions.
 // load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result.
+// ---- ray-index reservation of a persistent warp -------------------------------------------------
+// CRT_CHUNK = 0: every refill does one global atomicAdd for exactly the idle lanes and waits for it (6 % of k_shadow's
+// stall samples, profiles/r01_s20.md), then waits again for the ray data of those indices to come from DRAM (8 %).
+// CRT_CHUNK = N >= 32: a warp reserves N indices at a time and keeps one reservation ahead ([nxt, nxt_end)), whose ray
+// data it prefetches (pre functor) when it makes the reservation; refills hand out indices from [cur, cur_end) without
+// touching global memory. Small launches shrink the chunk so that every warp still gets rays. Which ray a lane
+// traces changes, the per-ray result does not (done() is keyed by the ray index).
+#ifndef CRT_CHUNK
+#define CRT_CHUNK 0
+#endif
+struct NoPrefetch { CRT_DEV void operator()(int, uint32_t, uint32_t) const {} };
+CRT_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+struct RayFetch {                 // every member holds the same value in all lanes of the warp
+    uint32_t cur, cur_end, nxt, nxt_end, chunk;
+    bool drained;
+    CRT_DEV void init(uint32_t n) {
+        cur = cur_end = nxt = nxt_end = 0;
+        drained = false;
+        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+        uint32_t c = n / (warps * 4u);
+        chunk = c < 32u ? 32u : (c > (uint32_t)CRT_CHUNK ? (uint32_t)CRT_CHUNK : c);
+    }
+    template <typename Pre>
+    CRT_DEV void reserve(uint32_t n, uint32_t* fetch, int lane, Pre& pre) {
+        if (drained) { nxt = nxt_end = 0; return; }
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetch, chunk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        nxt = base < n ? base : n;
+        nxt_end = base + chunk < n ? base + chunk : n;
+        if (base + chunk >= n) drained = true;
+        if (nxt < nxt_end) pre(lane, nxt, nxt_end - nxt);
+    }
+    // index for the idle lane of rank `rank` among n_idle idle lanes, or 0xffffffff when the queue is empty
+    template <typename Pre>
+    CRT_DEV uint32_t take(uint32_t n, uint32_t* fetch, int lane, int rank, int n_idle, Pre& pre) {
+        uint32_t my = 0xffffffffu;
+        const uint32_t a = min(cur_end - cur, (uint32_t)n_idle);
+        if ((uint32_t)rank < a) my = cur + (uint32_t)rank;
+        cur += a;
+        const uint32_t rest = (uint32_t)n_idle - a;
+        if (rest > 0u) {
+            cur = nxt; cur_end = nxt_end;
+            reserve(n, fetch, lane, pre);
+            const uint32_t b = min(cur_end - cur, rest);
+            if ((uint32_t)rank >= a && (uint32_t)rank < a + b) my = cur + ((uint32_t)rank - a);
+            cur += b;
+        }
+        return my;
+    }
+    CRT_DEV bool exhausted() const { return drained && cur == cur_end && nxt == nxt_end; }
+};
+
 static constexpr int kDone = 0x7ffffffe;
 #ifndef CRT_REFILL_LANES
 #define CRT_REFILL_LANES 12
@@ -475,8 +529,8 @@ struct WarpLeafQueue {
     int count;
 };
 
-template <int MODE, typename Load, typename Done>
-CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+template <int MODE, typename Load, typename Done, typename Pre>
+CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
     __shared__ WarpLeafQueue s_wq[4];                      // launched with 128 threads per block
     WarpLeafQueue& q = s_wq[threadIdx.x >> 5];
     const unsigned kFull = 0xffffffffu;
@@ -504,6 +558,11 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
     bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
+#if CRT_CHUNK
+    RayFetch rf;
+    rf.init(n);
+    rf.reserve(n, fetch, lane, pre);
+#endif
     for (;;) {
         // A. node steps; a leaf in hand goes to the queue and the lane takes the next entry of its stack
 #pragma unroll
@@ -580,7 +639,10 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                         }
                         if (fw & kLastBit) break;
                     }
-                    if (myslot >= 0) atomicMin(&q.best[owner], mykey);
+                    if (myslot >= 0) {
+                        if (MODE == 0) atomicMin(&q.best[owner], mykey);
+                        else q.best[owner] = mykey;                 // any blocker will do: one of the writers wins (64-bit store)
+                    }
                 }
                 __syncwarp();
                 if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
@@ -614,12 +676,17 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
         if (idle) {
             const int n_idle = __popc(idle);
             if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
+#if CRT_CHUNK
+                const uint32_t my_i = rf.take(n, fetch, lane, __popc(idle & lt_mask), n_idle, pre);
+#else
                 const int leader = __ffs(idle) - 1;
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
                 base = __shfl_sync(kFull, base, leader);
+                const uint32_t my_i = base + __popc(idle & lt_mask);
+#endif
                 if (!have) {
-                    const uint32_t i = base + __popc(idle & lt_mask);
+                    const uint32_t i = my_i;
                     if (i < n) {
                         idx = i;
                         V3 d;
@@ -639,7 +706,11 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                         have = true;
                     }
                 }
+#if CRT_CHUNK
+                exhausted = rf.exhausted();
+#else
                 if (base + (uint32_t)n_idle >= n) exhausted = true;
+#endif
                 __syncwarp();
             }
             if (idle == kFull && !__any_sync(kFull, have)) {
@@ -649,9 +720,9 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
     }
 }
 
-template <int MODE, int STRAT, typename Load, typename Done>
-CRT_DEV void trace_rays_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    if (STRAT == 2) trace_persistent_queue<MODE>(sc, n, fetch, load, done);
+template <int MODE, int STRAT, typename Load, typename Done, typename Pre>
+CRT_DEV void trace_rays_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
+    if (STRAT == 2) trace_persistent_queue<MODE>(sc, n, fetch, load, done, pre);
     else trace_persistent<MODE, STRAT>(sc, n, fetch, load, done);
 }
 

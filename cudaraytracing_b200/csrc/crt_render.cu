@@ -21,6 +21,9 @@
 #define CRT_WSTRAT 2
 #endif
 
+#ifndef CRT_SHADOW_SCRATCH
+#define CRT_SHADOW_SCRATCH 1
+#endif
 #ifndef CRT_MINB
 #define CRT_MINB 1     // __launch_bounds__ min blocks/SM of the traversal kernels (register cap experiment)
 #endif
@@ -126,10 +129,19 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device
 // =============================================================================================
 // node-layout dispatch: WIDE = false: 64-byte child-pair nodes, true: 80-byte 8-wide compressed nodes
 // =============================================================================================
+template <int MODE, bool WIDE, typename Load, typename Done, typename Pre>
+CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
+    if (WIDE) trace_rays_persistent_wide<MODE, CRT_WSTRAT>(sc, n, fetch, load, done, pre);
+    else trace_rays_persistent<MODE, CRT_STRAT>(sc, n, fetch, load, done, pre);
+}
 template <int MODE, bool WIDE, typename Load, typename Done>
 CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    if (WIDE) trace_rays_persistent_wide<MODE, CRT_WSTRAT>(sc, n, fetch, load, done);
-    else trace_rays_persistent<MODE, CRT_STRAT>(sc, n, fetch, load, done);
+    trace_queue<MODE, WIDE>(sc, n, fetch, load, done, NoPrefetch());
+}
+// Prefetch of rays [first, first + count) of a float4-per-ray array into L2: one 128-byte line holds 8 rays, lane L takes
+// lines L, L + 32, ... of the range (RayFetch::reserve calls this one reservation ahead of use).
+CRT_DEV void prefetch_rays16(const float4* __restrict__ a, int lane, uint32_t first, uint32_t count) {
+    for (uint32_t k = 8u * (uint32_t)lane; k < count; k += 256u) prefetch_l2(a + first + k);
 }
 template <int MODE, bool WIDE>
 CRT_DEV HitRec trace_one(const SceneView& sc, V3 o, V3 d, float tmax) {
@@ -154,6 +166,9 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_trace_batch(SceneView sc, con
         [&](uint32_t i, const HitRec& h) {
             if (t_out) t_out[i] = h.t;
             if (face_out) face_out[i] = h.face;
+        },
+        [&](int lane, uint32_t first, uint32_t count) {
+            for (uint32_t k = 4u * (uint32_t)lane; k < count; k += 128u) prefetch_l2(rays + 2 * (size_t)(first + k));
         });
 }
 
@@ -354,7 +369,8 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_extend(SceneView sc, Counters
     trace_queue<0, WIDE>(
         sc, c->n_cur, &c->fetch_extend,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
-        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });
+        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; },
+        [&](int lane, uint32_t first, uint32_t count) { prefetch_rays16(q_o, lane, first, count); prefetch_rays16(q_d, lane, first, count); });
 }
 
 // SPECULAR probe rays (reference Render.cuh:303): traced only when the continuation ray hit.
@@ -763,12 +779,33 @@ template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
                                                 const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
                                                 long long* __restrict__ accum) {
+#if CRT_SHADOW_SCRATCH
+    // the contribution and pixel of the ray a lane owns wait in shared memory (loaded with the ray, one DRAM round trip
+    // instead of a second one when the ray finishes: 3.7 % of this kernel's stall samples, profiles/r01_s20.md)
+    __shared__ float4 s_contrib[128];
+    trace_queue<1, WIDE>(
+        sc, c->n_shadow, &c->fetch_shadow,
+        [&](uint32_t i, V3& o, V3& d, float& tmax) {
+            const float4 a = sh_o[i], b = sh_d[i], cc = sh_c[i];
+            o = mk3(a); tmax = a.w; d = mk3(b);
+            s_contrib[threadIdx.x] = make_float4(cc.x, cc.y, cc.z, b.w);
+            return true;
+        },
+        [&](uint32_t i, const HitRec& h) {
+            if (h.slot < 0) { const float4 cc = s_contrib[threadIdx.x]; accum_add(accum, __float_as_uint(cc.w), mk3(cc)); }
+        },
+        [&](int lane, uint32_t first, uint32_t count) {
+            prefetch_rays16(sh_o, lane, first, count); prefetch_rays16(sh_d, lane, first, count); prefetch_rays16(sh_c, lane, first, count);
+        });
+#else
     trace_queue<1, WIDE>(
         sc, c->n_shadow, &c->fetch_shadow,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { const float4 a = sh_o[i]; o = mk3(a); tmax = a.w; d = mk3(sh_d[i]); return true; },
         [&](uint32_t i, const HitRec& h) {
             if (h.slot < 0) accum_add(accum, __float_as_uint(sh_d[i].w), mk3(sh_c[i]));
-        });
+        },
+        [&](int lane, uint32_t first, uint32_t count) { prefetch_rays16(sh_o, lane, first, count); prefetch_rays16(sh_d, lane, first, count); });
+#endif
 }
 
 // E11 (reference Render.cuh:348,350): mean over spp, clamp, pow 0.6, *255, truncate.

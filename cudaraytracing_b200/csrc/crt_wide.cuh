@@ -265,7 +265,7 @@ CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fe
 // has a node left) the whole warp tests them, one entry per lane; owners' best hits are combined with a
 // 64-bit shared atomicMin on (t bits, face id). Lanes walk with the t-limit of the last flush.
 #ifndef CRT_WQFLUSH
-#define CRT_WQFLUSH 16
+#define CRT_WQFLUSH 12
 #endif
 #ifndef CRT_WQSTEPS
 #define CRT_WQSTEPS 2
@@ -287,8 +287,8 @@ struct WarpLeafQueueW {
     int count;
 };
 
-template <int MODE, typename Load, typename Done>
-CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+template <int MODE, typename Load, typename Done, typename Pre>
+CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
     __shared__ WarpLeafQueueW s_wq[4];                     // launched with 128 threads per block
     WarpLeafQueueW& q = s_wq[threadIdx.x >> 5];
     const uint4* nodes = (const uint4*)sc.nodes;
@@ -307,6 +307,11 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
+#if CRT_CHUNK
+    RayFetch rf;
+    rf.init(n);
+    rf.reserve(n, fetch, lane, pre);
+#endif
     for (;;) {
         // A. node steps; leaf children go to the queue
 #pragma unroll
@@ -397,7 +402,10 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                         }
                         if (fw & kLastBit) break;
                     }
-                    if (myslot >= 0) atomicMin(&q.best[owner], mykey);
+                    if (myslot >= 0) {
+                        if (MODE == 0) atomicMin(&q.best[owner], mykey);
+                        else q.best[owner] = mykey;                 // any blocker will do: one of the writers wins (64-bit store)
+                    }
                 }
                 __syncwarp();
                 if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
@@ -431,12 +439,17 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
         if (idle) {
             const int n_idle = __popc(idle);
             if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
+#if CRT_CHUNK
+                const uint32_t my_i = rf.take(n, fetch, lane, __popc(idle & lt_mask), n_idle, pre);
+#else
                 const int leader = __ffs(idle) - 1;
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
                 base = __shfl_sync(kFull, base, leader);
+                const uint32_t my_i = base + __popc(idle & lt_mask);
+#endif
                 if (!have) {
-                    const uint32_t i = base + __popc(idle & lt_mask);
+                    const uint32_t i = my_i;
                     if (i < n) {
                         idx = i;
                         V3 d;
@@ -458,7 +471,11 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                         have = true;
                     }
                 }
+#if CRT_CHUNK
+                exhausted = rf.exhausted();
+#else
                 if (base + (uint32_t)n_idle >= n) exhausted = true;
+#endif
                 __syncwarp();
             }
             if (idle == kFull && !__any_sync(kFull, have)) {
@@ -468,9 +485,9 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     }
 }
 
-template <int MODE, int STRAT, typename Load, typename Done>
-CRT_DEV void trace_rays_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    if (STRAT == 2) trace_persistent_wide_queue<MODE>(sc, n, fetch, load, done);
+template <int MODE, int STRAT, typename Load, typename Done, typename Pre>
+CRT_DEV void trace_rays_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
+    if (STRAT == 2) trace_persistent_wide_queue<MODE>(sc, n, fetch, load, done, pre);
     else trace_persistent_wide<MODE>(sc, n, fetch, load, done);
 }
 

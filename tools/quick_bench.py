@@ -10,8 +10,8 @@ def main():
     tmp = tempfile.mkdtemp()
     B = {"lbvh": 0, "lbvh8": 1, "ploc": 2, "ploc8": 3}
     builders = [a for a in sys.argv[1:] if a in B] or ["lbvh"]
-    W, H, spp = 1920, 1080, 16
-    for name in ("cornell-box", "veach-mis"):
+    W, H, spp = int(os.environ.get("QB_W", "1920")), int(os.environ.get("QB_H", "1080")), int(os.environ.get("QB_SPP", "16"))
+    for name in os.environ.get("QB_SCENES", "cornell-box,veach-mis").split(","):
         cfg_path = sf.unpack(sf.fixture(name), os.path.join(tmp, name))
         cfg = crt.load_config(cfg_path)
         d = os.path.dirname(cfg_path)
@@ -31,6 +31,8 @@ def main():
                     name, b, est, min(ms), W * H * spp / min(ms) / 1e3, s2["ms_generate"], s2["ms_extend"], s2["ms_shade"], s2["ms_shadow"],
                     s2["extend_rays"], s2["shadow_rays"], s2["probe_rays"]), flush=True)
                 del R
+            if os.environ.get("QB_NO_BATCH"):
+                continue
             # incoherent batch on this scene (L2-resident BVH)
             lo, hi = S.export_bvh()[3][:3], S.export_bvh()[3][3:]
             rng = np.random.default_rng(5)
