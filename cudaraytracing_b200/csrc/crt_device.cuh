@@ -322,59 +322,12 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
 //   * "while-while" phases (Aila & Laine 2009): all lanes walk inner nodes until each holds a leaf, then
 //     all lanes intersect their leaf, which keeps lanes on the same instructions.
 // load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result.
-// ---- ray-index reservation of a persistent warp -------------------------------------------------
-// CRT_CHUNK = 0: every refill does one global atomicAdd for exactly the idle lanes and waits for it (6 % of k_shadow's
-// stall samples, profiles/r01_s20.md), then waits again for the ray data of those indices to come from DRAM (8 %).
-// CRT_CHUNK = N >= 32: a warp reserves N indices at a time and keeps one reservation ahead ([nxt, nxt_end)), whose ray
-// data it prefetches (pre functor) when it makes the reservation; refills hand out indices from [cur, cur_end) without
-// touching global memory. Small launches shrink the chunk so that every warp still gets rays. Which ray a lane
-// traces changes, the per-ray result does not (done() is keyed by the ray index).
-#ifndef CRT_CHUNK
-#define CRT_CHUNK 0
-#endif
+// Prefetch functor slot of the persistent kernels (kept as a no-op). Measured and removed (B200, profiles/r01_s21.md): a warp
+// reserving 32-128 ray indices at a time with one reservation of lookahead + L2 prefetch of those rays is 8-12 % SLOWER
+// than one global atomicAdd per refill, on short frames and at steady state alike: with per-refill fetches all warps
+// of an SM work on neighbouring queue entries and share nodes / triangles in L1; private chunks pull them apart.
 struct NoPrefetch { CRT_DEV void operator()(int, uint32_t, uint32_t) const {} };
-CRT_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-struct RayFetch {                 // every member holds the same value in all lanes of the warp
-    uint32_t cur, cur_end, nxt, nxt_end, chunk;
-    bool drained;
-    CRT_DEV void init(uint32_t n) {
-        cur = cur_end = nxt = nxt_end = 0;
-        drained = false;
-        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-        uint32_t c = n / (warps * 4u);
-        chunk = c < 32u ? 32u : (c > (uint32_t)CRT_CHUNK ? (uint32_t)CRT_CHUNK : c);
-    }
-    template <typename Pre>
-    CRT_DEV void reserve(uint32_t n, uint32_t* fetch, int lane, Pre& pre) {
-        if (drained) { nxt = nxt_end = 0; return; }
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch, chunk);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        nxt = base < n ? base : n;
-        nxt_end = base + chunk < n ? base + chunk : n;
-        if (base + chunk >= n) drained = true;
-        if (nxt < nxt_end) pre(lane, nxt, nxt_end - nxt);
-    }
-    // index for the idle lane of rank `rank` among n_idle idle lanes, or 0xffffffff when the queue is empty
-    template <typename Pre>
-    CRT_DEV uint32_t take(uint32_t n, uint32_t* fetch, int lane, int rank, int n_idle, Pre& pre) {
-        uint32_t my = 0xffffffffu;
-        const uint32_t a = min(cur_end - cur, (uint32_t)n_idle);
-        if ((uint32_t)rank < a) my = cur + (uint32_t)rank;
-        cur += a;
-        const uint32_t rest = (uint32_t)n_idle - a;
-        if (rest > 0u) {
-            cur = nxt; cur_end = nxt_end;
-            reserve(n, fetch, lane, pre);
-            const uint32_t b = min(cur_end - cur, rest);
-            if ((uint32_t)rank >= a && (uint32_t)rank < a + b) my = cur + ((uint32_t)rank - a);
-            cur += b;
-        }
-        return my;
-    }
-    CRT_DEV bool exhausted() const { return drained && cur == cur_end && nxt == nxt_end; }
-};
+CRT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 static constexpr int kDone = 0x7ffffffe;
 #ifndef CRT_REFILL_LANES
@@ -558,11 +511,6 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
     bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
-#if CRT_CHUNK
-    RayFetch rf;
-    rf.init(n);
-    rf.reserve(n, fetch, lane, pre);
-#endif
     for (;;) {
         // A. node steps; a leaf in hand goes to the queue and the lane takes the next entry of its stack
 #pragma unroll
@@ -676,15 +624,11 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
         if (idle) {
             const int n_idle = __popc(idle);
             if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
-#if CRT_CHUNK
-                const uint32_t my_i = rf.take(n, fetch, lane, __popc(idle & lt_mask), n_idle, pre);
-#else
                 const int leader = __ffs(idle) - 1;
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
                 base = __shfl_sync(kFull, base, leader);
                 const uint32_t my_i = base + __popc(idle & lt_mask);
-#endif
                 if (!have) {
                     const uint32_t i = my_i;
                     if (i < n) {
@@ -706,11 +650,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                         have = true;
                     }
                 }
-#if CRT_CHUNK
-                exhausted = rf.exhausted();
-#else
                 if (base + (uint32_t)n_idle >= n) exhausted = true;
-#endif
                 __syncwarp();
             }
             if (idle == kFull && !__any_sync(kFull, have)) {

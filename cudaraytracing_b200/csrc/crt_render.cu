@@ -138,11 +138,6 @@ template <int MODE, bool WIDE, typename Load, typename Done>
 CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
     trace_queue<MODE, WIDE>(sc, n, fetch, load, done, NoPrefetch());
 }
-// Prefetch of rays [first, first + count) of a float4-per-ray array into L2: one 128-byte line holds 8 rays, lane L takes
-// lines L, L + 32, ... of the range (RayFetch::reserve calls this one reservation ahead of use).
-CRT_DEV void prefetch_rays16(const float4* __restrict__ a, int lane, uint32_t first, uint32_t count) {
-    for (uint32_t k = 8u * (uint32_t)lane; k < count; k += 256u) prefetch_l2(a + first + k);
-}
 template <int MODE, bool WIDE>
 CRT_DEV HitRec trace_one(const SceneView& sc, V3 o, V3 d, float tmax) {
     if (WIDE) return traverse_wide<MODE>(sc, o, d, tmax);
@@ -166,9 +161,6 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_trace_batch(SceneView sc, con
         [&](uint32_t i, const HitRec& h) {
             if (t_out) t_out[i] = h.t;
             if (face_out) face_out[i] = h.face;
-        },
-        [&](int lane, uint32_t first, uint32_t count) {
-            for (uint32_t k = 4u * (uint32_t)lane; k < count; k += 128u) prefetch_l2(rays + 2 * (size_t)(first + k));
         });
 }
 
@@ -344,6 +336,8 @@ __global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c
     const unsigned long long w0 = c->gen_work0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
         unsigned long long w = w0 + k;
+        // (an 8x4-tile order of the pixels inside a sample, alone or in blocks of 4-16 tiles, changes nothing measurable:
+        //  profiles/r01_s21.md - the camera rays are a third of the extend rays and the cheapest ones)
         uint32_t pixel = (uint32_t)(w % p.n_pixels);
         uint32_t sample = p.s_begin + (uint32_t)(w / p.n_pixels);
         uint32_t i = pixel % p.width, j = pixel / p.width;
@@ -369,8 +363,7 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_extend(SceneView sc, Counters
     trace_queue<0, WIDE>(
         sc, c->n_cur, &c->fetch_extend,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
-        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; },
-        [&](int lane, uint32_t first, uint32_t count) { prefetch_rays16(q_o, lane, first, count); prefetch_rays16(q_d, lane, first, count); });
+        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });
 }
 
 // SPECULAR probe rays (reference Render.cuh:303): traced only when the continuation ray hit.
@@ -793,9 +786,6 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters
         },
         [&](uint32_t i, const HitRec& h) {
             if (h.slot < 0) { const float4 cc = s_contrib[threadIdx.x]; accum_add(accum, __float_as_uint(cc.w), mk3(cc)); }
-        },
-        [&](int lane, uint32_t first, uint32_t count) {
-            prefetch_rays16(sh_o, lane, first, count); prefetch_rays16(sh_d, lane, first, count); prefetch_rays16(sh_c, lane, first, count);
         });
 #else
     trace_queue<1, WIDE>(
@@ -803,8 +793,7 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters
         [&](uint32_t i, V3& o, V3& d, float& tmax) { const float4 a = sh_o[i]; o = mk3(a); tmax = a.w; d = mk3(sh_d[i]); return true; },
         [&](uint32_t i, const HitRec& h) {
             if (h.slot < 0) accum_add(accum, __float_as_uint(sh_d[i].w), mk3(sh_c[i]));
-        },
-        [&](int lane, uint32_t first, uint32_t count) { prefetch_rays16(sh_o, lane, first, count); prefetch_rays16(sh_d, lane, first, count); });
+        });
 #endif
 }
 

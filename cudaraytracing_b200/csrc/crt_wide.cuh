@@ -275,6 +275,10 @@ CRT_DEV void trace_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fe
 #ifndef CRT_WQBALLOT
 #define CRT_WQBALLOT 0
 #endif
+#ifndef CRT_WSSTACK
+#define CRT_WSSTACK 4
+#endif
+// Measured and removed: prefetch.global.L1 of a leaf's triangles when it is queued, -5 % (profiles/r01_s21.md).
 static constexpr int kWQFlush = CRT_WQFLUSH;
 static constexpr int kWQSteps = CRT_WQSTEPS;
 static constexpr int kWQCap = kWQFlush + 32 * 8 * kWQSteps;
@@ -296,7 +300,14 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     const unsigned long long kNoHit = ((unsigned long long)0x7f7fffffu << 32) | 0x7fffffffull;   // t = FLT_MAX
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+#if CRT_WSSTACK
+    // first CRT_WSSTACK entries of every lane's stack in shared memory, [entry][thread]: a push / pop is one
+    // conflict-free wavefront and a short-scoreboard wait instead of a local-memory round trip
+    uint2 stack[kWideStack - CRT_WSSTACK];
+    __shared__ uint2 s_wstack[CRT_WSSTACK][128];
+#else
     uint2 stack[kWideStack];
+#endif
     int sp = 0;
     uint32_t g_base = 0, g_bits = 0, oinv = 0;
     uint32_t idx = 0;
@@ -307,17 +318,17 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
-#if CRT_CHUNK
-    RayFetch rf;
-    rf.init(n);
-    rf.reserve(n, fetch, lane, pre);
-#endif
     for (;;) {
         // A. node steps; leaf children go to the queue
 #pragma unroll
         for (int r = 0; r < kWQSteps; ++r) {
             if ((g_bits & 0xffu) == 0u && sp > 0) {
-                const uint2 e = stack[--sp];
+                --sp;
+#if CRT_WSSTACK
+                const uint2 e = sp < CRT_WSSTACK ? s_wstack[sp][threadIdx.x] : stack[sp - CRT_WSSTACK];
+#else
+                const uint2 e = stack[sp];
+#endif
                 g_base = e.x; g_bits = e.y;
             }
 #if CRT_WQBALLOT
@@ -344,14 +355,23 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                     while (s.leaf_hits) {
                         const int lp = 31 - __clz((int)s.leaf_hits);
                         s.leaf_hits &= ~(1u << lp);
-                        q.q_slot[pos] = wide_leaf_slot(s, lp, oinv);
+                        const int lslot = wide_leaf_slot(s, lp, oinv);
+                        q.q_slot[pos] = lslot;
                         q.q_lane[pos] = (unsigned char)lane;
                         ++pos;
                     }
                 }
 #endif
                 if (s.node_hits) {
-                    if (g_bits & 0xffu) stack[sp++] = make_uint2(g_base, g_bits);
+                    if (g_bits & 0xffu) {
+#if CRT_WSSTACK
+                        if (sp < CRT_WSSTACK) s_wstack[sp][threadIdx.x] = make_uint2(g_base, g_bits);
+                        else stack[sp - CRT_WSSTACK] = make_uint2(g_base, g_bits);
+#else
+                        stack[sp] = make_uint2(g_base, g_bits);
+#endif
+                        ++sp;
+                    }
                     g_base = s.child_base;
                     g_bits = (s.imask << 8) | s.node_hits;
                 }
@@ -439,15 +459,11 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
         if (idle) {
             const int n_idle = __popc(idle);
             if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
-#if CRT_CHUNK
-                const uint32_t my_i = rf.take(n, fetch, lane, __popc(idle & lt_mask), n_idle, pre);
-#else
                 const int leader = __ffs(idle) - 1;
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
                 base = __shfl_sync(kFull, base, leader);
                 const uint32_t my_i = base + __popc(idle & lt_mask);
-#endif
                 if (!have) {
                     const uint32_t i = my_i;
                     if (i < n) {
@@ -471,11 +487,7 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
                         have = true;
                     }
                 }
-#if CRT_CHUNK
-                exhausted = rf.exhausted();
-#else
                 if (base + (uint32_t)n_idle >= n) exhausted = true;
-#endif
                 __syncwarp();
             }
             if (idle == kFull && !__any_sync(kFull, have)) {
