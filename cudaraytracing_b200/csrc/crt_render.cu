@@ -249,9 +249,10 @@ int random_rays_device(const DeviceScene& ds, float4* d_rays, uint64_t n, uint64
 struct Counters {
     unsigned long long work_next, work_end, gen_work0;
     unsigned long long stat_extend, stat_shadow, stat_probe;
-    uint32_t n_cur, n_next, n_shadow, n_probe_cur, n_probe_next;
+    uint32_t n_cur, n_next, n_probe_cur, n_probe_next;
+    uint32_t n_shadow[2], fetch_shadow[2];      // by iteration parity: k_shadow of iteration k overlaps k_prepare .. k_extend of k + 1
     uint32_t gen_base, gen_count;
-    uint32_t fetch_extend, fetch_shadow, fetch_probe;
+    uint32_t fetch_extend, fetch_probe;
     uint32_t iterations;
     uint32_t tail_n, fetch_tail;       // paths handed to k_tail by the last k_prepare (0: none)
 };
@@ -292,19 +293,21 @@ struct Wavefront {
     HostStatus* status_dev = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaStream_t st_shadow = nullptr;                     // k_shadow of iteration k runs here, beside k_prepare .. k_extend of k + 1
+    cudaEvent_t ev_shaded = nullptr, ev_shadowed = nullptr;
     int grid_trace = 0, grid_shade = 0, grid_tail = 0;
 };
 
 // =============================================================================================
 // kernels
 // =============================================================================================
-__global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostStatus* status) {
-    c->stat_shadow += c->n_shadow;
+__global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostStatus* status, int par) {
+    c->stat_shadow += c->n_shadow[par];          // the shadow rays of iteration k - 2, traced long ago
     uint32_t n_cur = c->n_next;
     uint32_t n_probe = c->n_probe_next;
     c->n_next = 0;
     c->n_probe_next = 0;
-    c->n_shadow = 0;
+    c->n_shadow[par] = 0;
     unsigned long long remaining = c->work_end - c->work_next;
     uint32_t room = pool - n_cur;
     uint32_t n_new = remaining < (unsigned long long)room ? (uint32_t)remaining : room;
@@ -313,7 +316,7 @@ __global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostSta
     c->gen_work0 = c->work_next;
     n_cur += n_new;
     c->work_next += n_new;
-    c->fetch_extend = c->fetch_shadow = c->fetch_probe = c->fetch_tail = 0;
+    c->fetch_extend = c->fetch_shadow[par] = c->fetch_probe = c->fetch_tail = 0;
     c->iterations += n_cur ? 1u : 0u;
     // tail: every camera path has been started and few paths are alive -> k_tail finishes them
     const bool tail = remaining == 0 && n_cur > 0 && n_cur <= tail_max;
@@ -664,7 +667,7 @@ __global__ void __launch_bounds__(128, EST == CRT_ESTIMATOR_COMPAT ? CRT_SHADE_M
                                                       float4* __restrict__ pr_o_next, float4* __restrict__ pr_d_next,
                                                       float4* __restrict__ pr_w_next, uint32_t* __restrict__ pr_list_next,
                                                       float4* __restrict__ sh_o, float4* __restrict__ sh_d,
-                                                      float4* __restrict__ sh_c, long long* __restrict__ accum) {
+                                                      float4* __restrict__ sh_c, long long* __restrict__ accum, int par) {
     const uint32_t n = c->n_cur;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 qo = q_o[i], qd = q_d[i], qT = q_T[i];
@@ -679,7 +682,7 @@ __global__ void __launch_bounds__(128, EST == CRT_ESTIMATOR_COMPAT ? CRT_SHADE_M
         ProbeState npr;
         const uint32_t pixel = ps.pixel;
         auto shadow = [&](bool needs_trace, V3 pos, float tmax, V3 dir, V3 contrib) {
-            int k = warp_append(&c->n_shadow, needs_trace);
+            int k = warp_append(&c->n_shadow[par], needs_trace);
             if (k >= 0) {
                 sh_o[k] = make_float4(pos.x, pos.y, pos.z, tmax);
                 sh_d[k] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pixel));
@@ -771,13 +774,13 @@ __global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderP
 template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
                                                 const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
-                                                long long* __restrict__ accum) {
+                                                long long* __restrict__ accum, int par) {
 #if CRT_SHADOW_SCRATCH
     // the contribution and pixel of the ray a lane owns wait in shared memory (loaded with the ray, one DRAM round trip
     // instead of a second one when the ray finishes: 3.7 % of this kernel's stall samples, profiles/r01_s20.md)
     __shared__ float4 s_contrib[128];
     trace_queue<1, WIDE>(
-        sc, c->n_shadow, &c->fetch_shadow,
+        sc, c->n_shadow[par], &c->fetch_shadow[par],
         [&](uint32_t i, V3& o, V3& d, float& tmax) {
             const float4 a = sh_o[i], b = sh_d[i], cc = sh_c[i];
             o = mk3(a); tmax = a.w; d = mk3(b);
@@ -789,7 +792,7 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters
         });
 #else
     trace_queue<1, WIDE>(
-        sc, c->n_shadow, &c->fetch_shadow,
+        sc, c->n_shadow[par], &c->fetch_shadow[par],
         [&](uint32_t i, V3& o, V3& d, float& tmax) { const float4 a = sh_o[i]; o = mk3(a); tmax = a.w; d = mk3(sh_d[i]); return true; },
         [&](uint32_t i, const HitRec& h) {
             if (h.slot < 0) accum_add(accum, __float_as_uint(sh_d[i].w), mk3(sh_c[i]));
@@ -914,6 +917,9 @@ void wavefront_destroy(Wavefront* w) {
     for (int k = 0; k < 4; ++k) if (w->ev[k]) cudaEventDestroy(w->ev[k]);
     if (w->ev_begin) cudaEventDestroy(w->ev_begin);
     if (w->ev_end) cudaEventDestroy(w->ev_end);
+    if (w->ev_shaded) cudaEventDestroy(w->ev_shaded);
+    if (w->ev_shadowed) cudaEventDestroy(w->ev_shadowed);
+    if (w->st_shadow) cudaStreamDestroy(w->st_shadow);
     delete w;
 }
 
@@ -952,6 +958,15 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     cudaEvent_t se[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const uint32_t tail_max = rs.stage_timing ? 0u : env_u32("CRT_TAIL", kTailDefault);
     if (rs.stage_timing) for (auto& e : se) cudaEventCreate(&e);
+    // CRT_OVERLAP (default on): k_shadow of iteration k runs on a second stream beside k_prepare, k_generate and k_extend
+    // of iteration k + 1 (it only adds to the accumulation buffer; its counters are indexed by iteration parity), so the
+    // drain of one persistent kernel is filled by the start of the next. k_shade(k + 1) waits for it (one shadow queue).
+    const bool overlap = !rs.stage_timing && env_u32("CRT_OVERLAP", 1) != 0;
+    if (overlap && !w->st_shadow) {
+        CRT_CUDA(cudaStreamCreateWithFlags(&w->st_shadow, cudaStreamNonBlocking));
+        CRT_CUDA(cudaEventCreateWithFlags(&w->ev_shaded, cudaEventDisableTiming));
+        CRT_CUDA(cudaEventCreateWithFlags(&w->ev_shadowed, cudaEventDisableTiming));
+    }
     uint32_t it = 0;
     for (;; ++it) {
         if (it >= 2) {
@@ -959,7 +974,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
             if (w->status_host->done) break;
         }
         const int cur = it & 1, nxt = cur ^ 1;
-        k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, tail_max, w->status_dev);
+        k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, tail_max, w->status_dev, cur);
         if (rs.stage_timing) cudaEventRecord(se[0], st);
         k_generate<<<w->grid_shade, 256, 0, st>>>(w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], mis ? w->q_pdf[cur] : nullptr);
         if (rs.stage_timing) cudaEventRecord(se[1], st);
@@ -972,22 +987,30 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
             launches++;
         }
         if (rs.stage_timing) cudaEventRecord(se[2], st);
+        if (overlap && it > 0) CRT_CUDA(cudaStreamWaitEvent(st, w->ev_shadowed, 0));      // k_shadow(it - 1) still reads the shadow queue
         if (mis)
             k_shade<CRT_ESTIMATOR_MIS><<<w->grid_shade, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
                                                                        w->q_pdf[nxt], w->hit_t, w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt],
                                                                        w->q_d[nxt], w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
-                                                                       w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum);
+                                                                       w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
         else
             k_shade<CRT_ESTIMATOR_COMPAT><<<w->grid_shade, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
                                                                           w->q_pdf[nxt], w->hit_t, w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt],
                                                                           w->q_d[nxt], w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
-                                                                          w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum);
+                                                                          w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
 #ifdef CRT_EXP_SORT
         exp_sort(ds, w->counters, 1, w->sh_o, w->sh_d, w->sh_c, w->shadow_cap, st);
 #endif
         if (rs.stage_timing) cudaEventRecord(se[3], st);
-        if (wide) k_shadow<true><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum);
-        else k_shadow<false><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum);
+        cudaStream_t ss = st;
+        if (overlap) {
+            CRT_CUDA(cudaEventRecord(w->ev_shaded, st));
+            CRT_CUDA(cudaStreamWaitEvent(w->st_shadow, w->ev_shaded, 0));
+            ss = w->st_shadow;
+        }
+        if (wide) k_shadow<true><<<w->grid_trace, 128, 0, ss>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
+        else k_shadow<false><<<w->grid_trace, 128, 0, ss>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
+        if (overlap) CRT_CUDA(cudaEventRecord(w->ev_shadowed, ss));
         if (rs.stage_timing) cudaEventRecord(se[4], st);
 #ifdef CRT_EXP_SORT
         exp_sort(ds, w->counters, 0, w->q_o[nxt], w->q_d[nxt], w->q_T[nxt], w->pool, st);
@@ -1007,6 +1030,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         CRT_CUDA(cudaEventRecord(w->ev[it & 3], st));
         CRT_CUDA(cudaGetLastError());
     }
+    if (overlap && it > 0) CRT_CUDA(cudaStreamWaitEvent(st, w->ev_shadowed, 0));
     CRT_CUDA(cudaEventRecord(w->ev_end, st));
     CRT_CUDA(cudaStreamSynchronize(st));
     if (rs.stage_timing) for (auto& e : se) cudaEventDestroy(e);
@@ -1015,7 +1039,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         memset(stats, 0, sizeof(*stats));
         stats->samples = h.work_end - w_begin;
         stats->extend_rays = h.stat_extend;
-        stats->shadow_rays = h.stat_shadow + h.n_shadow;
+        stats->shadow_rays = h.stat_shadow + h.n_shadow[0] + h.n_shadow[1];
         stats->probe_rays = h.stat_probe;
         stats->iterations = h.iterations;
         stats->kernel_launches = launches;
