@@ -183,6 +183,30 @@ def test_matched_seed_radiance_synthetic_specular_and_options(gpu, orc):
     assert R.stats()["iterations"] <= 66
 
 
+def test_scheduling_knobs_do_not_change_the_image(gpu, orc, scene_files, monkeypatch):
+    """k_shadow on a second stream beside the next iteration's extend (CRT_OVERLAP), the pool size and the hand-over to
+    k_tail only reorder work: the integer accumulation buffer and the ray counts stay the same."""
+    cfg, a, b = _pair(gpu, orc, scene_files, "cornell-box")
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    W, H, spp = 256, 192, 5
+    want = None
+    for env in ({}, {"CRT_OVERLAP": "0"}, {"CRT_OVERLAP": "1", "CRT_POOL": "8192"}, {"CRT_OVERLAP": "1", "CRT_TAIL": "0"},
+                {"CRT_OVERLAP": "0", "CRT_POOL": "4096", "CRT_TAIL": "1000000"}):
+        for k in ("CRT_OVERLAP", "CRT_POOL", "CRT_TAIL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        R = gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n)
+        R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+        got, st = R.get_accum_i64().copy(), R.stats()
+        if want is None:
+            want, want_st = got, st
+            oacc, ost = b.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 0, spp, cfg.P_RR, cfg.light_sample_n)
+            assert np.array_equal(want, oacc) and st["shadow_rays"] == ost["shadow_rays"]
+        assert np.array_equal(got, want), env
+        assert (st["extend_rays"], st["shadow_rays"]) == (want_st["extend_rays"], want_st["shadow_rays"]), env
+
+
 def test_render_is_deterministic_and_shards_add_up(gpu, orc, scene_files):
     """Multi-GPU invariance on one GPU: any split of the work index space sums to the full buffer exactly,
     and repeated runs are identical (atomics are integer, so ordering cannot matter)."""
