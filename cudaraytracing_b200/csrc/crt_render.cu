@@ -24,8 +24,10 @@
 #ifndef CRT_SHADOW_SCRATCH
 #define CRT_SHADOW_SCRATCH 1
 #endif
+// __launch_bounds__ min blocks/SM of the traversal kernels. 8 caps the wide-node kernels at 64 registers (no spills; the
+// compiler's own choice is 77-79 = 6 blocks): cornell-box +3 %, C5 (HBM-latency bound) 4793 -> 5394 Mrays/s (r01_s27).
 #ifndef CRT_MINB
-#define CRT_MINB 1     // __launch_bounds__ min blocks/SM of the traversal kernels (register cap experiment)
+#define CRT_MINB 8
 #endif
 
 #include <algorithm>
