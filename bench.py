@@ -494,6 +494,13 @@ def ours_c5(args):
         cpu_dt = time.time() - t0
         bpr = st["inner"] / st["rays"] * (S_NODE_WIDE if cfg.builder & 1 else S_NODE) + st["tris"] / st["rays"] * S_TRI + S_RAY_IO_CLOSEST
         ach = res["closest"]["mrays"] * 1e6 * bpr / 1e9
+        traffic = None                     # ncu dram bytes of one captured launch, scaled to this launch's ray count
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                t5 = json.load(f).get("c5", {})
+            if t5.get("k_trace_batch") and t5.get("rays"):
+                traffic = int(t5["k_trace_batch"] * (n / t5["rays"]))
         print(json.dumps({
             "metric": "Mrays/s (closest-hit)", "value": round(res["closest"]["mrays"], 1), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(res["closest"]["ms"], 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -507,7 +514,7 @@ def ours_c5(args):
                     "note": "crt_trace_rays with host buffers on a %d-ray batch" % nb},
             "gpu_launches": 2 * args.steps, "clocks": res.get("clocks"),
             "roofline": {"bound": "hbm", "kernel": "k_trace_batch<closest>", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None, "peak_kind": peak_kind,
+                         "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_kind": peak_kind,
                          "per_ray": {"inner": round(st["inner"] / st["rays"], 2), "tris": round(st["tris"] / st["rays"], 2), "bytes": round(bpr, 1)}},
             "cpu_baseline": {"value": round(len(sample) / cpu_dt / 1e6, 3), "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "%d of the same rays, oracle traversal, %.1f s" % (len(sample), cpu_dt)},
