@@ -83,7 +83,6 @@ __global__ void k_scan_sums(uint32_t* __restrict__ sums, uint32_t n_blocks, uint
 
 __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
                              const uint32_t* __restrict__ block_offsets, uint32_t n) {
-    __shared__ uint32_t buf[kScanTile];
     __shared__ uint32_t tsum[256];
     uint32_t base = blockIdx.x * kScanTile;
     // blocked arrangement: thread t owns items 4t..4t+3 of the tile
@@ -108,7 +107,6 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restri
         if (i < n) out[i] = run;
         run += v[k];
     }
-    (void)buf;
 }
 
 // out may alias in. scratch must hold ceil(n/1024) uint32. total (device pointer) optional.

@@ -314,7 +314,9 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
     int pending = 0;
-    int qn = 0;                                            // CRT_WQBALLOT: queued leaves, the same value in every lane
+#if CRT_WQBALLOT
+    int qn = 0;                                            // queued leaves, the same value in every lane
+#endif
     bool have = false, exhausted = false, zray = false;
     if (lane == 0) q.count = 0;
     __syncwarp();
