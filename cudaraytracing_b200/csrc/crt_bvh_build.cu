@@ -490,13 +490,8 @@ __global__ void k_emit_tris(uint32_t n, const uint32_t* __restrict__ order, cons
     float4 sh = face_shade[f];
     uint32_t fw = f | (last_flag[slot] ? kLastBit : 0u);
     tri_geom[3 * (size_t)slot + 0] = make_float4(v[0], v[1], v[2], __uint_as_float(fw));
-#if CRT_TRI40       // (e1, e2.x) (e2.y, e2.z, mat, 0): the triangle test reads the first 40 bytes (crt_device.cuh load_tri)
-    tri_geom[3 * (size_t)slot + 1] = make_float4(v[3] - v[0], v[4] - v[1], v[5] - v[2], v[6] - v[0]);
-    tri_geom[3 * (size_t)slot + 2] = make_float4(v[7] - v[1], v[8] - v[2], sh.w, 0.0f);
-#else
     tri_geom[3 * (size_t)slot + 1] = make_float4(v[3] - v[0], v[4] - v[1], v[5] - v[2], sh.w);
     tri_geom[3 * (size_t)slot + 2] = make_float4(v[6] - v[0], v[7] - v[1], v[8] - v[2], 0.0f);
-#endif
     tri_shade[slot] = sh;
 }
 

@@ -215,9 +215,6 @@ struct HitRec { float t; int slot; int face; };
 #ifndef CRT_LD256
 #define CRT_LD256 1
 #endif
-#ifndef CRT_N3_64
-#define CRT_N3_64 0
-#endif
 CRT_DEV void load_node(const float4* __restrict__ nodes, int cur, float4& n0, float4& n1, float4& n2, float4& n3) {
     const float4* p = nodes + 4 * (size_t)cur;
 #if CRT_LD256
@@ -226,31 +223,17 @@ CRT_DEV void load_node(const float4* __restrict__ nodes, int cur, float4& n0, fl
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w) : "l"(p + 2));
 #else
-    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2);
-#if CRT_N3_64
-    { const float2 ch = __ldg((const float2*)(p + 3)); n3 = make_float4(ch.x, ch.y, 0.0f, 0.0f); }   // children only: 56 of the 64 bytes
-#else
-    n3 = __ldg(p + 3);
-#endif
+    n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3);
 #endif
 }
 
-// One triangle record (48-byte stride). CRT_TRI40 = 1: the record is (v1, face|last) (e1, e2.x) (e2.y, e2.z, mat, 0) and the
-// test reads 40 bytes (LDG.128, LDG.128, LDG.64) instead of 48 - the traversal kernels are bound by the L1 data pipe
-// (profiles/r01_s17.md), which moves what the lanes ask for, used or not.
-#ifndef CRT_TRI40
-#define CRT_TRI40 0
-#endif
+// One triangle record: (v1, face|last) (e1, mat) (e2, 0). Reading only the 40 bytes the test needs (a re-laid-out record,
+// LDG.128 + LDG.128 + LDG.64) and only 56 of a node's 64 bytes was measured: -1.5 % and 0 (profiles/r01_s18.md) - the L1
+// data pipe is paid per load instruction and distinct line, not per byte.
 CRT_DEV uint32_t load_tri(const float4* __restrict__ tri_geom, int slot, V3& v1, V3& e1, V3& e2) {
     const float4* p = tri_geom + 3 * (size_t)slot;
-    const float4 a = __ldg(p), b = __ldg(p + 1);
-    v1 = mk3(a); e1 = mk3(b);
-#if CRT_TRI40
-    const float2 c = __ldg((const float2*)(p + 2));
-    e2 = mk3(b.w, c.x, c.y);
-#else
-    e2 = mk3(__ldg(p + 2));
-#endif
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    v1 = mk3(a); e1 = mk3(b); e2 = mk3(c);
     return __float_as_uint(a.w);
 }
 
@@ -322,13 +305,9 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
 //   * "while-while" phases (Aila & Laine 2009): all lanes walk inner nodes until each holds a leaf, then
 //     all lanes intersect their leaf, which keeps lanes on the same instructions.
 // load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result.
-// Prefetch functor slot of the persistent kernels (kept as a no-op). Measured and removed (B200, profiles/r01_s21.md): a warp
-// reserving 32-128 ray indices at a time with one reservation of lookahead + L2 prefetch of those rays is 8-12 % SLOWER
-// than one global atomicAdd per refill, on short frames and at steady state alike: with per-refill fetches all warps
-// of an SM work on neighbouring queue entries and share nodes / triangles in L1; private chunks pull them apart.
-struct NoPrefetch { CRT_DEV void operator()(int, uint32_t, uint32_t) const {} };
-CRT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
+// Measured and removed (B200, profiles/r01_s21.md): a warp reserving 32-128 ray indices at a time with one reservation of
+// lookahead + L2 prefetch of those rays is 8-12 % SLOWER than one global atomicAdd per refill, on short frames and at
+// steady state alike; prefetch.global.L1 of a queued leaf's triangles costs 5 %.
 static constexpr int kDone = 0x7ffffffe;
 #ifndef CRT_REFILL_LANES
 #define CRT_REFILL_LANES 12
@@ -482,8 +461,8 @@ struct WarpLeafQueue {
     int count;
 };
 
-template <int MODE, typename Load, typename Done, typename Pre>
-CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
+template <int MODE, typename Load, typename Done>
+CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
     __shared__ WarpLeafQueue s_wq[4];                      // launched with 128 threads per block
     WarpLeafQueue& q = s_wq[threadIdx.x >> 5];
     const unsigned kFull = 0xffffffffu;
@@ -660,9 +639,9 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
     }
 }
 
-template <int MODE, int STRAT, typename Load, typename Done, typename Pre>
-CRT_DEV void trace_rays_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
-    if (STRAT == 2) trace_persistent_queue<MODE>(sc, n, fetch, load, done, pre);
+template <int MODE, int STRAT, typename Load, typename Done>
+CRT_DEV void trace_rays_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    if (STRAT == 2) trace_persistent_queue<MODE>(sc, n, fetch, load, done);
     else trace_persistent<MODE, STRAT>(sc, n, fetch, load, done);
 }
 

@@ -131,14 +131,10 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device
 // =============================================================================================
 // node-layout dispatch: WIDE = false: 64-byte child-pair nodes, true: 80-byte 8-wide compressed nodes
 // =============================================================================================
-template <int MODE, bool WIDE, typename Load, typename Done, typename Pre>
-CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
-    if (WIDE) trace_rays_persistent_wide<MODE, CRT_WSTRAT>(sc, n, fetch, load, done, pre);
-    else trace_rays_persistent<MODE, CRT_STRAT>(sc, n, fetch, load, done, pre);
-}
 template <int MODE, bool WIDE, typename Load, typename Done>
 CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    trace_queue<MODE, WIDE>(sc, n, fetch, load, done, NoPrefetch());
+    if (WIDE) trace_rays_persistent_wide<MODE, CRT_WSTRAT>(sc, n, fetch, load, done);
+    else trace_rays_persistent<MODE, CRT_STRAT>(sc, n, fetch, load, done);
 }
 template <int MODE, bool WIDE>
 CRT_DEV HitRec trace_one(const SceneView& sc, V3 o, V3 d, float tmax) {

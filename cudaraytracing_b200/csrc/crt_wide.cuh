@@ -291,8 +291,8 @@ struct WarpLeafQueueW {
     int count;
 };
 
-template <int MODE, typename Load, typename Done, typename Pre>
-CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
+template <int MODE, typename Load, typename Done>
+CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
     __shared__ WarpLeafQueueW s_wq[4];                     // launched with 128 threads per block
     WarpLeafQueueW& q = s_wq[threadIdx.x >> 5];
     const uint4* nodes = (const uint4*)sc.nodes;
@@ -499,9 +499,9 @@ CRT_DEV void trace_persistent_wide_queue(const SceneView& sc, uint32_t n, uint32
     }
 }
 
-template <int MODE, int STRAT, typename Load, typename Done, typename Pre>
-CRT_DEV void trace_rays_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Pre pre) {
-    if (STRAT == 2) trace_persistent_wide_queue<MODE>(sc, n, fetch, load, done, pre);
+template <int MODE, int STRAT, typename Load, typename Done>
+CRT_DEV void trace_rays_persistent_wide(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    if (STRAT == 2) trace_persistent_wide_queue<MODE>(sc, n, fetch, load, done);
     else trace_persistent_wide<MODE>(sc, n, fetch, load, done);
 }
 
