@@ -21,6 +21,12 @@
 #define CRT_WSTRAT 2
 #endif
 
+// 1: the queue counters every warp adds to sit in 128-byte lines of their own. With n_cur / n_next / n_shadow / fetch_* in
+// one 32-byte sector the compat shade stage took 24.7 - 34.1 ms for the same work depending on the box (1080p spp 128,
+// profiles/r01_s35.md); apart it takes 24.7 ms.
+#ifndef CRT_COUNTER_LINES
+#define CRT_COUNTER_LINES 1
+#endif
 #ifndef CRT_SHADOW_SCRATCH
 #define CRT_SHADOW_SCRATCH 1
 #endif
@@ -247,12 +253,24 @@ int random_rays_device(const DeviceScene& ds, float4* d_rays, uint64_t n, uint64
 struct Counters {
     unsigned long long work_next, work_end, gen_work0;
     unsigned long long stat_extend, stat_shadow, stat_probe;
-    uint32_t n_cur, n_next, n_probe_cur, n_probe_next;
-    uint32_t n_shadow[2], fetch_shadow[2];      // by iteration parity: k_shadow of iteration k overlaps k_prepare .. k_extend of k + 1
+    uint32_t n_cur, n_probe_cur, n_probe_next;
     uint32_t gen_base, gen_count;
-    uint32_t fetch_extend, fetch_probe;
     uint32_t iterations;
     uint32_t tail_n, fetch_tail;       // paths handed to k_tail by the last k_prepare (0: none)
+    uint32_t fetch_probe;
+#if CRT_COUNTER_LINES
+    // the words every warp of a kernel adds to, each alone in a 128-byte line (same-address atomics serialise in one L2
+    // slice; n_next and n_shadow shared a 32-byte sector, and so did the fetch counters)
+    alignas(128) uint32_t n_next;
+    alignas(128) uint32_t n_shadow[2];          // by iteration parity: k_shadow of iteration k overlaps k_prepare .. k_extend of k + 1
+    alignas(128) uint32_t fetch_extend;
+    alignas(128) uint32_t fetch_shadow[2];
+    alignas(128) uint32_t pad_;
+#else
+    uint32_t n_next;
+    uint32_t n_shadow[2], fetch_shadow[2];      // by iteration parity: k_shadow of iteration k overlaps k_prepare .. k_extend of k + 1
+    uint32_t fetch_extend;
+#endif
 };
 struct HostStatus { volatile uint32_t done; volatile uint32_t n_cur; volatile unsigned long long work_next; };
 
@@ -863,7 +881,7 @@ static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings
     uint32_t pool = env_u32("CRT_POOL", 0);
     if (pool == 0) {
         pool = 1u << 20;
-        while (pool < (1u << 24) && pool < work_items) pool <<= 1;
+        while (pool < (1u << 25) && pool < work_items) pool <<= 1;       // 2^25: +2 % over 2^24 at steady state (r01_s35), 7 GB
     }
     uint64_t per_vertex = (uint64_t)std::max<uint32_t>(ds.n_lights, 1) * std::max<uint32_t>(rs.light_sample_n, 1);
     const uint64_t shadow_budget = 1ull << 26;        // 64 Mi shadow rays in flight at most (3 GiB)
