@@ -309,8 +309,9 @@ def ours(args):
                 traffic = json.load(f).get(args.workload, {}).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(kernels[dom]["achieved_gbs"], 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(kernels[dom]["achieved_gbs"] / peaks["hbm_gbs"], 4), "traffic": traffic, "peak_kind": peak_kind,
-                "traffic_note": "ncu dram bytes of ONE steady-state launch of this kernel in the committed capture (profiles/r01_s29.md, "
-                                "2^24 paths in flight); launches of a frame this size now carry up to 2^25 paths",
+                "traffic_note": ("ncu dram bytes of ONE steady-state launch of this kernel in the committed capture (profiles/r01_s29.md, "
+                                 "2^24 paths in flight); launches of a frame this size now carry up to 2^25 paths" if args.workload == "c3" else
+                                 "ncu dram bytes of one launch of this kernel in the committed capture of this workload (profiles/), if any"),
                 "note": "algorithmic bytes = oracle-counted node (%d B) and triangle (48 B) visits + ray I/O per ray x rays per launch; " % s_node +
                         ("the BVH and triangles (%.0f MB) exceed the 126 MB L2 on this workload: node and triangle fetches are HBM sector traffic" %
                          ((scene.counts()["n_nodes"] * s_node + scene.counts()["n_tris"] * 64) / 1e6) if cfg.source == "synthetic" else
