@@ -1,6 +1,8 @@
 // crt_host.cpp — host ingest of the product: OBJ/MTL, derived triangle/material/object data,
 // camera matrix. Semantics follow the reference loader (include/OBJLoader.h:61-203,
-// include/Loader.h:40-124); the implementation is a single pass over a memory-mapped file.
+// include/Loader.h:40-124); the implementation reads a memory-mapped file in newline-aligned chunks on all host
+// threads and stitches them in file order, so the result - triangle order, material
+// slots, the first error and its line number - is the one a sequential pass gives.
 // Compiled with -ffp-contract=off: derived values equal the reference's Eigen host arithmetic.
 #include "crt_host.h"
 
@@ -9,12 +11,15 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <array>
 #include <charconv>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string_view>
+#include <thread>
 
 namespace crt {
 
@@ -124,22 +129,29 @@ void finish_material(HostMaterial& m) {
     }
 }
 
-bool push_triangle(HostScene& s, const float vin[9], int mat, int obj) {
-    float v[9];
+// One triangle's derived data (Triangle.h:27,39 with Eigen's host arithmetic: cross by separate products, sum as
+// x+(y+z)). false: a coordinate is not finite.
+static bool triangle_record(const float vin[9], float v[9], float nrm[3], float* area) {
     for (int k = 0; k < 9; ++k) {
         if (!std::isfinite(vin[k])) return false;
         v[k] = vin[k] + 0.0f;                                     // -0 -> +0: min/max stay unambiguous
     }
-    // Triangle.h:27,39 with Eigen's host arithmetic: cross by separate products, sum as x+(y+z)
     float ax = v[3] - v[0], ay = v[4] - v[1], az = v[5] - v[2];
     float bx = v[6] - v[0], by = v[7] - v[1], bz = v[8] - v[2];
     float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
     float n2 = cx * cx + (cy * cy + cz * cz);
-    float nx = cx, ny = cy, nz = cz;
-    if (n2 > 0.0f) { float l = sqrtf(n2); nx = cx / l; ny = cy / l; nz = cz / l; }
+    nrm[0] = cx; nrm[1] = cy; nrm[2] = cz;
+    if (n2 > 0.0f) { float l = sqrtf(n2); nrm[0] = cx / l; nrm[1] = cy / l; nrm[2] = cz / l; }
+    *area = sqrtf(n2) * 0.5f;
+    return true;
+}
+
+bool push_triangle(HostScene& s, const float vin[9], int mat, int obj) {
+    float v[9], nrm[3], area;
+    if (!triangle_record(vin, v, nrm, &area)) return false;
     s.verts.insert(s.verts.end(), v, v + 9);
-    s.normal.push_back(nx); s.normal.push_back(ny); s.normal.push_back(nz);
-    s.area.push_back(sqrtf(n2) * 0.5f);
+    s.normal.push_back(nrm[0]); s.normal.push_back(nrm[1]); s.normal.push_back(nrm[2]);
+    s.area.push_back(area);
     s.area_of_obj.push_back(0.0f);
     s.mat.push_back(mat);
     s.obj.push_back(obj);
@@ -179,35 +191,51 @@ void finish_objects(HostScene& s) {
     for (HostMaterial& m : s.mats) m.pdf_area = (m.has_emit && W > 0.0) ? (float)((double)lum(m.ke) / W) : 0.0f;
 }
 
-int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
-    MappedFile f;
-    if (!f.open(obj_path)) { set_error(std::string("Unable to open OBJ file: ") + obj_path); return CRT_ERR_IO; }
-    std::vector<float> pos;                  // 3 per `v`
-    std::vector<float> uv;                   // 2 per `vt` (only read when a material has map_Kd)
-    std::vector<uint32_t> idx;               // 3 per kept face
-    std::vector<Shape> shapes;
-    std::string mtl_name;
-    pos.reserve(f.size / 24);
-    idx.reserve(f.size / 48);
-    const char* p = f.data;
-    const char* fend = f.data + f.size;
-    size_t line_no = 0;
+// ---------------------------------------------------------------------------------------------
+// OBJ text in newline-aligned chunks, one per host thread
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct FaceRec {
+    long long v[3];        // the indices as written (1-based, or negative = relative to the vertices read so far)
+    uint32_t line;         // line of the chunk (1-based)
+    uint32_t nv_before;    // `v` lines of this chunk before the face
+};
+struct ShapeMark { std::string material; size_t face_local; };
+struct ObjChunk {
+    const char* begin = nullptr;
+    const char* end = nullptr;
+    std::vector<float> pos, uv;
+    std::vector<FaceRec> faces;
+    std::vector<ShapeMark> marks;
+    std::string mtllib;
+    bool has_mtllib = false;
+    size_t lines = 0;
+    size_t bad_line = 0;   // line of the chunk of the first face that does not parse (0: none); the chunk stops there
+};
+
+void parse_obj_chunk(ObjChunk& ck) {
+    const char* p = ck.begin;
+    const char* fend = ck.end;
+    ck.pos.reserve((size_t)(fend - p) / 24);
+    ck.faces.reserve((size_t)(fend - p) / 48);
     while (p < fend) {
         const char* nl = (const char*)memchr(p, '\n', (size_t)(fend - p));
         const char* le = nl ? nl : fend;
-        ++line_no;
+        ++ck.lines;
         LineCursor c{p, le};
         std::string_view key = c.token();
         if (key == "v") {
             float x = c.number(), y = c.number(), z = c.number();
-            pos.push_back(x); pos.push_back(y); pos.push_back(z);
+            ck.pos.push_back(x); ck.pos.push_back(y); ck.pos.push_back(z);
         } else if (key == "vt") {
             float a = c.number(), b = c.number();
-            uv.push_back(a); uv.push_back(b);
+            ck.uv.push_back(a); ck.uv.push_back(b);
         } else if (key == "f") {
             // "v", "v/vt", "v//vn", "v/vt/vn"; only the vertex index matters (Triangle.h:27-28
             // recomputes the normal) and only the first three corners are used (Loader.h:62-68).
-            uint32_t corner[3];
+            FaceRec fr;
+            fr.line = (uint32_t)ck.lines;
+            fr.nv_before = (uint32_t)(ck.pos.size() / 3);
             int nc = 0;
             bool bad = false;
             for (;;) {
@@ -222,29 +250,116 @@ int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
                 if (b < e && *b == '+') ++b;
                 auto r = std::from_chars(b, e, v);
                 if (r.ec != std::errc()) { bad = true; break; }
-                long long nv = (long long)(pos.size() / 3);
-                long long zero_based = v > 0 ? v - 1 : nv + v;          // OBJLoader.h:106
-                if (zero_based < 0 || zero_based >= nv) { bad = true; break; }
-                corner[nc++] = (uint32_t)zero_based;
+                fr.v[nc++] = v;
             }
-            if (bad || nc < 3) {
-                set_error(std::string(obj_path) + ":" + std::to_string(line_no) + ": malformed face");
-                return CRT_ERR_IO;
-            }
-            if (!shapes.empty()) {                                       // OBJLoader.h:120-123
-                idx.push_back(corner[0]); idx.push_back(corner[1]); idx.push_back(corner[2]);
-                shapes.back().face_end = idx.size() / 3;
-            }
+            if (bad || nc < 3) { ck.bad_line = ck.lines; return; }
+            ck.faces.push_back(fr);
         } else if (key == "usemtl") {
-            Shape sh;
-            sh.material = std::string(c.token());
-            sh.face_begin = sh.face_end = idx.size() / 3;
-            shapes.push_back(sh);
+            ck.marks.push_back(ShapeMark{std::string(c.token()), ck.faces.size()});
         } else if (key == "mtllib") {
-            mtl_name = std::string(c.token());
+            ck.mtllib = std::string(c.token());
+            ck.has_mtllib = true;
         }
         p = nl ? nl + 1 : fend;
     }
+}
+
+unsigned ingest_threads(size_t bytes) {
+    unsigned t = std::thread::hardware_concurrency();
+    if (const char* e = getenv("CRT_INGEST_THREADS")) t = (unsigned)atoi(e);
+    t = std::max(1u, std::min(t, 64u));
+    const size_t by_size = bytes / (256u << 10);           // at least 256 KB of text per thread
+    return (unsigned)std::max<size_t>(1, std::min<size_t>(t, by_size));
+}
+
+template <typename F>
+void parallel_for(unsigned n, F&& body) {                   // body(k) for k in [0, n), one thread each (n is small)
+    if (n <= 1) { if (n == 1) body(0u); return; }
+    std::vector<std::thread> th;
+    th.reserve(n - 1);
+    for (unsigned k = 1; k < n; ++k) th.emplace_back([&body, k] { body(k); });
+    body(0u);
+    for (auto& t : th) t.join();
+}
+}  // namespace
+
+int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
+    MappedFile f;
+    if (!f.open(obj_path)) { set_error(std::string("Unable to open OBJ file: ") + obj_path); return CRT_ERR_IO; }
+    // 1. chunks on line boundaries, parsed independently
+    const unsigned T = ingest_threads(f.size);
+    std::vector<ObjChunk> chunks(T);
+    {
+        const char* fend = f.data + f.size;
+        const char* b = f.data;
+        for (unsigned k = 0; k < T; ++k) {
+            const char* e = fend;
+            if (k + 1 < T) {
+                const char* guess = f.data + (size_t)((unsigned long long)f.size * (k + 1) / T);
+                if (guess < b) guess = b;
+                const char* nl = (const char*)memchr(guess, '\n', (size_t)(fend - guess));
+                e = nl ? nl + 1 : fend;
+            }
+            chunks[k].begin = b; chunks[k].end = e;
+            b = e;
+        }
+    }
+    parallel_for(T, [&](unsigned k) { parse_obj_chunk(chunks[k]); });
+    // 2. stitch in file order: prefix counts, the first error, the first usemtl
+    std::vector<size_t> nv0(T + 1, 0), nuv0(T + 1, 0), nf0(T + 1, 0), line0(T + 1, 0);
+    for (unsigned k = 0; k < T; ++k) {
+        nv0[k + 1] = nv0[k] + chunks[k].pos.size() / 3;
+        nuv0[k + 1] = nuv0[k] + chunks[k].uv.size() / 2;
+        nf0[k + 1] = nf0[k] + chunks[k].faces.size();
+        line0[k + 1] = line0[k] + chunks[k].lines;
+    }
+    std::string mtl_name;
+    for (unsigned k = 0; k < T; ++k) if (chunks[k].has_mtllib) mtl_name = chunks[k].mtllib;      // the last one wins
+    size_t first_kept = (size_t)-1;                          // faces before the first usemtl are dropped (OBJLoader.h:120-123)
+    for (unsigned k = 0; k < T && first_kept == (size_t)-1; ++k)
+        if (!chunks[k].marks.empty()) first_kept = nf0[k] + chunks[k].marks[0].face_local;
+    const size_t n_faces = nf0[T];
+    const size_t n_kept = first_kept == (size_t)-1 ? 0 : n_faces - first_kept;
+    std::vector<float> pos(3 * nv0[T]);                      // 3 per `v`
+    std::vector<float> uv(2 * nuv0[T]);                      // 2 per `vt` (only read when a material has map_Kd)
+    std::vector<uint32_t> idx(3 * n_kept);                   // 3 per kept face
+    std::vector<size_t> err_line(T, 0);                      // global line of the chunk's first malformed face (0: none)
+    parallel_for(T, [&](unsigned k) {
+        ObjChunk& ck = chunks[k];
+        if (!ck.pos.empty()) memcpy(&pos[3 * nv0[k]], ck.pos.data(), sizeof(float) * ck.pos.size());
+        if (!ck.uv.empty()) memcpy(&uv[2 * nuv0[k]], ck.uv.data(), sizeof(float) * ck.uv.size());
+        for (size_t fi = 0; fi < ck.faces.size(); ++fi) {
+            const FaceRec& fr = ck.faces[fi];
+            const long long nv = (long long)(nv0[k] + fr.nv_before);       // vertices read before this face
+            uint32_t corner[3];
+            bool bad = false;
+            for (int c = 0; c < 3; ++c) {
+                const long long zero_based = fr.v[c] > 0 ? fr.v[c] - 1 : nv + fr.v[c];       // OBJLoader.h:106
+                if (zero_based < 0 || zero_based >= nv) { bad = true; break; }
+                corner[c] = (uint32_t)zero_based;
+            }
+            if (bad) { err_line[k] = line0[k] + fr.line; break; }
+            const size_t g = nf0[k] + fi;
+            if (first_kept != (size_t)-1 && g >= first_kept) memcpy(&idx[3 * (g - first_kept)], corner, sizeof(corner));
+        }
+        if (ck.bad_line && (err_line[k] == 0 || line0[k] + ck.bad_line < err_line[k])) err_line[k] = line0[k] + ck.bad_line;
+    });
+    for (unsigned k = 0; k < T; ++k)
+        if (err_line[k]) {
+            set_error(std::string(obj_path) + ":" + std::to_string(err_line[k]) + ": malformed face");
+            return CRT_ERR_IO;
+        }
+    std::vector<Shape> shapes;
+    for (unsigned k = 0; k < T; ++k)
+        for (const ShapeMark& mk : chunks[k].marks) {
+            Shape sh;
+            sh.material = mk.material;
+            sh.face_begin = sh.face_end = nf0[k] + mk.face_local - first_kept;
+            if (!shapes.empty()) shapes.back().face_end = sh.face_begin;
+            shapes.push_back(sh);
+        }
+    if (!shapes.empty()) shapes.back().face_end = n_kept;
+    chunks.clear();
 
     // MTL: newmtl / Kd / Ks / Ke / Ns (OBJLoader.h:154-200); other keys are ignored like there.
     std::map<std::string, HostMaterial> table;
@@ -274,6 +389,54 @@ int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
     }
 
     // One material slot and (if it has faces) one object per shape, in file order (main.cu:131-144).
+    bool textured = false;
+    for (const Shape& sh : shapes) {
+        auto it = table.find(sh.material);
+        if (it != table.end() && !it->second.map_kd.empty() && sh.face_end > sh.face_begin) textured = true;
+    }
+    if (!textured) {
+        // no map_Kd in use: a triangle's material and object are its shape's, so all triangles are filled in at once
+        struct Span { size_t face_begin, face_end; int mat, obj; };
+        std::vector<Span> spans;
+        for (const Shape& sh : shapes) {
+            HostMaterial m;
+            auto it = table.find(sh.material);
+            if (it != table.end()) m = it->second;
+            m.name = sh.material;
+            finish_material(m);
+            const int mat = (int)s.mats.size();
+            s.mats.push_back(m);
+            if (sh.face_end == sh.face_begin) continue;
+            spans.push_back(Span{sh.face_begin, sh.face_end, mat, s.n_objects++});
+        }
+        const size_t t0 = s.n_tris();
+        s.verts.resize(9 * (t0 + n_kept)); s.normal.resize(3 * (t0 + n_kept));
+        s.area.resize(t0 + n_kept); s.area_of_obj.resize(t0 + n_kept, 0.0f);
+        s.mat.resize(t0 + n_kept); s.obj.resize(t0 + n_kept);
+        std::vector<char> bad(T, 0);
+        parallel_for(T, [&](unsigned k) {
+            const size_t fb = n_kept * k / T, fe = n_kept * (k + 1) / T;
+            size_t sp = 0;
+            while (sp < spans.size() && spans[sp].face_end <= fb) ++sp;
+            for (size_t fi = fb; fi < fe; ++fi) {
+                while (spans[sp].face_end <= fi) ++sp;
+                float v[9];
+                for (int c = 0; c < 3; ++c) memcpy(v + 3 * c, &pos[3 * (size_t)idx[3 * fi + c]], 3 * sizeof(float));
+                const size_t t = t0 + fi;
+                if (!triangle_record(v, &s.verts[9 * t], &s.normal[3 * t], &s.area[t])) { bad[k] = 1; return; }
+                s.mat[t] = spans[sp].mat;
+                s.obj[t] = spans[sp].obj;
+            }
+        });
+        for (unsigned k = 0; k < T; ++k)
+            if (bad[k]) {
+                s.verts.resize(9 * t0); s.normal.resize(3 * t0); s.area.resize(t0); s.area_of_obj.resize(t0); s.mat.resize(t0); s.obj.resize(t0);
+                set_error(std::string(obj_path) + ": non-finite vertex coordinate");
+                return CRT_ERR_IO;
+            }
+        finish_objects(s);
+        return CRT_OK;
+    }
     for (const Shape& sh : shapes) {
         HostMaterial m;
         auto it = table.find(sh.material);

@@ -246,3 +246,72 @@ def test_map_kd_errors(crt, tmp_path):
         f.write("mtllib textured.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0.5 0.5\nusemtl t_rgba\nf 1 2 3\n")
     with pytest.raises(crt.CrtError):
         crt.Scene().add_obj(os.path.join(str(tmp_path), "few.obj"), str(tmp_path))
+
+
+def _big_obj(path, n_quads=12000, bad_at=None, forward_ref_at=None, reference_forms_only=False):
+    """An OBJ large enough to be read in several chunks: relative and absolute indices, faces before the first usemtl,
+    several usemtl, two mtllib lines (the last one wins), v/vt/vn forms. Returns the number of lines."""
+    rng = np.random.default_rng(11)
+    lines = ["# generated", "mtllib wrong.mtl", "v 0 0 0", "v 1 0 0", "v 0 1 0", "f 1 2 3", "mtllib big.mtl"]   # dropped face
+    for q in range(n_quads):
+        x, y, z = rng.uniform(-50, 50, 3)
+        lines += ["v %.6f %.6f %.6f" % (x, y, z), "v %.6f %.6f %.6f" % (x + 1, y, z), "v %.6f %.6f %.6f" % (x + 1, y + 1, z + 0.25),
+                  "v %.6f %.6f %.6f" % (x, y + 1, z), "vt 0.5 0.5"]
+        if q % 3000 == 0:
+            lines.append("usemtl m%d" % (q // 3000 % 3))
+        if reference_forms_only:            # what the reference's stoull-based reader accepts: positive v or v/vt/vn
+            base = 3 + 4 * q
+            lines += ["f %d/1/1 %d/1/1 %d/1/1" % (base + 1, base + 2, base + 3), "f %d %d %d %d" % (base + 1, base + 3, base + 4, base + 2)]
+        elif q % 2:
+            lines += ["f -4 -3 -2", "f -4/1/1 -2/1/1 -1/1/1 -3"]          # relative; a fourth corner is ignored
+        else:
+            base = 3 + 4 * q
+            lines += ["f %d//7 %d//7 %d//7" % (base + 1, base + 2, base + 3), "f +%d %d %d" % (base + 1, base + 3, base + 4)]
+        if bad_at is not None and q == bad_at:
+            lines.append("f 1 2 x")
+        if forward_ref_at is not None and q == forward_ref_at:
+            lines.append("f 1 2 %d" % (3 + 4 * (q + 1) + 1))                # a vertex that is defined only later
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return lines
+
+
+def test_chunked_ingest_is_independent_of_the_thread_count(crt, orc, tmp_path, monkeypatch):
+    (tmp_path / "big.mtl").write_text("newmtl m0\nKd .5 .5 .5\nnewmtl m1\nKd .1 .2 .3\nKe 5 5 5\nnewmtl m2\nKd .3 .2 .1\nNs 40\n")
+    (tmp_path / "wrong.mtl").write_text("newmtl m0\nKd 1 0 0\n")
+    for ref_forms in (False, True):
+        obj = str(tmp_path / ("big%d.obj" % ref_forms))
+        _big_obj(obj, reference_forms_only=ref_forms)
+        assert os.path.getsize(obj) > (1 << 20)
+        want = None
+        for th in ("1", "2", "5", "8"):
+            monkeypatch.setenv("CRT_INGEST_THREADS", th)
+            S = crt.Scene().add_obj(obj, str(tmp_path))
+            tr = S.tris()
+            blob = b"".join(np.ascontiguousarray(tr[k]).tobytes() for k in ("verts", "normal", "area", "area_of_obj", "mat", "obj")) + S.mats().tobytes()
+            if want is None:
+                want = blob
+                assert S.counts()["n_tris"] == 24000 and len(S.lights()) == 1 and S.counts()["n_mats"] == 4
+                if ref_forms:                   # the restatement of the reference's reader gives the same scene
+                    O = orc.Scene().add_obj(obj, str(tmp_path))
+                    ot = O.tris()
+                    for k in ("verts", "normal", "area", "area_of_obj", "mat", "obj"):
+                        assert np.array_equal(tr[k].view(np.uint32), ot[k].view(np.uint32)), k
+                    assert np.array_equal(S.mats(), O.mats()) and len(O.lights()) == 1
+            assert blob == want, th
+
+
+def test_chunked_ingest_reports_the_first_error_with_its_line(crt, tmp_path, monkeypatch):
+    (tmp_path / "big.mtl").write_text("newmtl m0\nKd .5 .5 .5\n")
+    (tmp_path / "wrong.mtl").write_text("newmtl m0\nKd 1 0 0\n")
+    for kind in ("bad", "forward"):
+        obj = str(tmp_path / ("err_%s.obj" % kind))
+        lines = _big_obj(obj, bad_at=9000 if kind == "bad" else 11000, forward_ref_at=7000 if kind == "forward" else 10000)
+        first = min(i for i, ln in enumerate(lines) if ln == "f 1 2 x" or (ln.startswith("f 1 2 ") and ln != "f 1 2 3")) + 1
+        msgs = set()
+        for th in ("1", "3", "8"):
+            monkeypatch.setenv("CRT_INGEST_THREADS", th)
+            with pytest.raises(crt.CrtError) as e:
+                crt.Scene().add_obj(obj, str(tmp_path))
+            msgs.add(str(e.value))
+        assert len(msgs) == 1 and (":%d: malformed face" % first) in msgs.pop()
