@@ -4,11 +4,14 @@
 
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
+#include <thread>
 #include <vector>
 
 namespace crt {
@@ -196,17 +199,64 @@ void put_chunk(std::vector<uint8_t>& out, const char type[4], const uint8_t* dat
 }
 }  // namespace
 
+// RGB8 PNG, filter 0 on every row, deflate level 6. The scanlines are cut into bands of about 1 MB (a function of the
+// image size only, so the file does not depend on the machine); every band is deflated on its own as a raw stream that
+// ends on a byte boundary (Z_SYNC_FLUSH; the last one with Z_FINISH) and the pieces are concatenated behind one zlib
+// header, with the Adler-32 of the whole combined from the bands' (the pigz construction). A 3840x2160 frame takes
+// ~1.6 s on one thread; the bands are compressed on all host threads.
 int write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height) {
     if (!path || !rgb8 || width == 0 || height == 0) { set_error("write_png: invalid argument"); return CRT_ERR_INVALID; }
     const size_t row = (size_t)width * 3;
-    std::vector<uint8_t> raw((row + 1) * height);
-    for (uint32_t y = 0; y < height; ++y) {
-        raw[(row + 1) * y] = 0;
-        memcpy(&raw[(row + 1) * y + 1], rgb8 + row * y, row);
+    const uint32_t band_rows = (uint32_t)std::max<size_t>(1, (size_t)(1u << 20) / (row + 1));
+    const uint32_t n_bands = (height + band_rows - 1) / band_rows;
+    struct Band { std::vector<uint8_t> z; uLong adler = 1; size_t raw_len = 0; bool ok = false; };
+    std::vector<Band> bands(n_bands);
+    std::atomic<uint32_t> next(0);
+    auto work = [&]() {
+        std::vector<uint8_t> raw;
+        for (;;) {
+            const uint32_t b = next.fetch_add(1);
+            if (b >= n_bands) return;
+            const uint32_t y0 = b * band_rows, y1 = std::min(height, y0 + band_rows);
+            raw.resize((row + 1) * (size_t)(y1 - y0));
+            for (uint32_t y = y0; y < y1; ++y) {
+                raw[(row + 1) * (size_t)(y - y0)] = 0;
+                memcpy(&raw[(row + 1) * (size_t)(y - y0) + 1], rgb8 + row * y, row);
+            }
+            Band& bd = bands[b];
+            bd.raw_len = raw.size();
+            bd.adler = adler32(adler32(0L, Z_NULL, 0), raw.data(), (uInt)raw.size());
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) continue;
+            bd.z.resize(deflateBound(&zs, (uLong)raw.size()) + 16);
+            zs.next_in = raw.data(); zs.avail_in = (uInt)raw.size();
+            zs.next_out = bd.z.data(); zs.avail_out = (uInt)bd.z.size();
+            const bool last = b + 1 == n_bands;
+            const int rc = deflate(&zs, last ? Z_FINISH : Z_SYNC_FLUSH);
+            bd.ok = (last ? rc == Z_STREAM_END : rc == Z_OK) && zs.avail_in == 0;
+            bd.z.resize(bd.z.size() - zs.avail_out);
+            deflateEnd(&zs);
+        }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char* e = getenv("CRT_INGEST_THREADS")) nt = (unsigned)atoi(e);      // one knob for the host-side thread count
+    nt = std::max(1u, std::min(std::min(nt, 64u), n_bands));
+    {
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < nt; ++k) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
     }
-    uLongf bound = compressBound((uLong)raw.size());
-    std::vector<uint8_t> z(bound);
-    if (compress2(z.data(), &bound, raw.data(), (uLong)raw.size(), 6) != Z_OK) { set_error("write_png: deflate failed"); return CRT_ERR_NOMEM; }
+    std::vector<uint8_t> z;
+    z.push_back(0x78); z.push_back(0x9c);                          // zlib header: deflate, 32 KB window, default level
+    uLong adler = adler32(0L, Z_NULL, 0);
+    for (const Band& bd : bands) {
+        if (!bd.ok) { set_error("write_png: deflate failed"); return CRT_ERR_NOMEM; }
+        z.insert(z.end(), bd.z.begin(), bd.z.end());
+        adler = adler32_combine(adler, bd.adler, (z_off_t)bd.raw_len);
+    }
+    put_be32(z, (uint32_t)adler);
     std::vector<uint8_t> out;
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
     out.insert(out.end(), sig, sig + 8);
@@ -214,7 +264,7 @@ int write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t he
     put_be32(ihdr, width); put_be32(ihdr, height);
     ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
     put_chunk(out, "IHDR", ihdr.data(), ihdr.size());
-    put_chunk(out, "IDAT", z.data(), bound);
+    put_chunk(out, "IDAT", z.data(), z.size());
     put_chunk(out, "IEND", nullptr, 0);
     FILE* f = fopen(path, "wb");
     if (!f) { set_error(std::string("write_png: cannot open ") + path); return CRT_ERR_IO; }

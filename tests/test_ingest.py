@@ -315,3 +315,25 @@ def test_chunked_ingest_reports_the_first_error_with_its_line(crt, tmp_path, mon
                 crt.Scene().add_obj(obj, str(tmp_path))
             msgs.add(str(e.value))
         assert len(msgs) == 1 and (":%d: malformed face" % first) in msgs.pop()
+
+
+def test_png_writer_bands_do_not_depend_on_the_thread_count(crt, tmp_path, monkeypatch):
+    """Frames above ~1 MB are deflated in bands on all host threads; the file is a function of the image only."""
+    rng = np.random.default_rng(6)
+    for (h, w) in [(92, 3840), (400, 1500), (1, 1)]:            # 2 bands (91 rows each at this width), 3 bands, 1 band
+        img = np.clip(rng.integers(-20, 20, (h, w, 3)) + (np.arange(w)[None, :, None] * 255 // max(w - 1, 1)), 0, 255).astype(np.uint8)
+        blobs = set()
+        for th in ("1", "3", "8"):
+            monkeypatch.setenv("CRT_INGEST_THREADS", th)
+            p = str(tmp_path / ("t%s.png" % th))
+            crt.write_png(p, img)
+            blobs.add(open(p, "rb").read())
+        assert len(blobs) == 1
+        data = blobs.pop()
+        pos, idat = 8, b""
+        while pos < len(data):
+            n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+            if typ == b"IDAT": idat += data[pos + 8:pos + 8 + n]
+            pos += 12 + n
+        rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + w * 3)
+        assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(h, w, 3), img)
