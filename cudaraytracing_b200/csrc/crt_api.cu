@@ -125,12 +125,10 @@ int crt_scene_add_triangles(crt_scene* s, const float* verts, const uint32_t* ma
         h.mats.push_back(hm);
     }
     uint32_t max_obj = 0;
-    for (uint64_t t = 0; t < n_tris; ++t) {
-        if (!push_triangle(h, verts + 9 * t, mat0 + (int)mat_id[t], obj0 + (int)obj_id[t])) {
-            set_error("crt_scene_add_triangles: non-finite vertex coordinate");
-            return CRT_ERR_INVALID;
-        }
-        if (obj_id[t] > max_obj) max_obj = obj_id[t];
+    for (uint64_t t = 0; t < n_tris; ++t) if (obj_id[t] > max_obj) max_obj = obj_id[t];
+    if (!append_triangles(h, verts, mat_id, obj_id, (size_t)n_tris, mat0, obj0)) {
+        set_error("crt_scene_add_triangles: non-finite vertex coordinate");
+        return CRT_ERR_INVALID;
     }
     if (n_tris) h.n_objects = obj0 + (int)max_obj + 1;
     finish_objects(h);

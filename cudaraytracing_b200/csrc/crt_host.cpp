@@ -283,6 +283,29 @@ void parallel_for(unsigned n, F&& body) {                   // body(k) for k in 
 }
 }  // namespace
 
+bool append_triangles(HostScene& s, const float* verts, const uint32_t* mat_id, const uint32_t* obj_id, size_t n, int mat0, int obj0) {
+    const size_t t0 = s.n_tris();
+    s.verts.resize(9 * (t0 + n)); s.normal.resize(3 * (t0 + n));
+    s.area.resize(t0 + n); s.area_of_obj.resize(t0 + n, 0.0f);
+    s.mat.resize(t0 + n); s.obj.resize(t0 + n);
+    const unsigned T = ingest_threads(n * 36);
+    std::vector<char> bad(T, 0);
+    parallel_for(T, [&](unsigned k) {
+        for (size_t i = n * k / T, e = n * (k + 1) / T; i < e; ++i) {
+            const size_t t = t0 + i;
+            if (!triangle_record(verts + 9 * i, &s.verts[9 * t], &s.normal[3 * t], &s.area[t])) { bad[k] = 1; return; }
+            s.mat[t] = mat0 + (int)mat_id[i];
+            s.obj[t] = obj0 + (int)obj_id[i];
+        }
+    });
+    for (unsigned k = 0; k < T; ++k)
+        if (bad[k]) {
+            s.verts.resize(9 * t0); s.normal.resize(3 * t0); s.area.resize(t0); s.area_of_obj.resize(t0); s.mat.resize(t0); s.obj.resize(t0);
+            return false;
+        }
+    return true;
+}
+
 int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
     MappedFile f;
     if (!f.open(obj_path)) { set_error(std::string("Unable to open OBJ file: ") + obj_path); return CRT_ERR_IO; }

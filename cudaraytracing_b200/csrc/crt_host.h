@@ -46,6 +46,9 @@ struct HostScene {
 void finish_material(HostMaterial& m);
 // Append one triangle (derives normal and area like Triangle.h:23-41). Returns false on NaN/inf.
 bool push_triangle(HostScene& s, const float v[9], int mat, int obj);
+// n triangles at once (verts: 9 floats each), derived data filled in on all host threads; material / object ids are
+// offset by mat0 / obj0. false (scene unchanged): a coordinate is not finite.
+bool append_triangles(HostScene& s, const float* verts, const uint32_t* mat_id, const uint32_t* obj_id, size_t n, int mat0, int obj0);
 // Object areas and the light list (Object.h:12-26, Scene.h:38-48). Call after adding triangles.
 void finish_objects(HostScene& s);
 // OBJLoader::parse + Loader::load_object semantics over a memory-mapped file.
