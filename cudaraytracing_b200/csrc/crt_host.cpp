@@ -268,7 +268,9 @@ unsigned ingest_threads(size_t bytes) {
     unsigned t = std::thread::hardware_concurrency();
     if (const char* e = getenv("CRT_INGEST_THREADS")) t = (unsigned)atoi(e);
     t = std::max(1u, std::min(t, 64u));
-    const size_t by_size = bytes / (256u << 10);           // at least 256 KB of text per thread
+    size_t min_chunk = 256u << 10;                         // at least 256 KB of text per thread
+    if (const char* e = getenv("CRT_INGEST_MIN_CHUNK")) min_chunk = (size_t)std::max(1L, atol(e));    // tests: chunk tiny files
+    const size_t by_size = bytes / min_chunk;
     return (unsigned)std::max<size_t>(1, std::min<size_t>(t, by_size));
 }
 

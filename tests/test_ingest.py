@@ -337,3 +337,64 @@ def test_png_writer_bands_do_not_depend_on_the_thread_count(crt, tmp_path, monke
             pos += 12 + n
         rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + w * 3)
         assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(h, w, 3), img)
+
+
+def test_chunked_ingest_fuzz_against_the_single_thread_pass(crt, tmp_path, monkeypatch):
+    """Random small OBJ texts cut into many tiny chunks (CRT_INGEST_MIN_CHUNK forces it): the scene, or the error message
+    with its line number, must equal the one-chunk pass - relative indices across chunk borders, faces before the
+    first usemtl, usemtl / mtllib anywhere, malformed and out-of-range faces, blank lines, no trailing newline."""
+    rng = np.random.default_rng(2024)
+    (tmp_path / "f.mtl").write_text("newmtl a\nKd .5 .5 .5\nnewmtl b\nKd .2 .2 .2\nKe 3 3 3\nnewmtl c\nNs 50\nKd .1 .1 .1\n")
+    mats = ["a", "b", "c", "missing"]
+
+    def scene_blob(S):
+        tr = S.tris()
+        return b"".join(np.ascontiguousarray(tr[k]).tobytes() for k in ("verts", "normal", "area", "area_of_obj", "mat", "obj")) + \
+            S.mats().tobytes() + repr([(f.tolist(), float(a)) for f, a in S.lights()]).encode()
+
+    n_err = n_ok = 0
+    for case in range(120):
+        lines, nv = [], 0
+        if rng.random() < 0.8:
+            lines.append("mtllib f.mtl")
+        for _ in range(int(rng.integers(5, 60))):
+            r = rng.random()
+            if r < 0.45:
+                lines.append("v %.3f %.3f %.3f" % tuple(rng.uniform(-9, 9, 3)))
+                nv += 1
+            elif r < 0.50:
+                lines.append("vt 0.1 0.2")
+            elif r < 0.60:
+                lines.append("usemtl " + mats[int(rng.integers(0, 4))])
+            elif r < 0.63:
+                lines.append("" if rng.random() < 0.5 else "# c")
+            elif r < 0.65:
+                lines.append("mtllib f.mtl")
+            elif nv >= 3 or rng.random() < 0.1:
+                kind = rng.random()
+                if kind < 0.06:
+                    lines.append("f 1 2")                                   # too few corners
+                elif kind < 0.10:
+                    lines.append("f 1 x 3")                                 # does not parse
+                elif kind < 0.16:
+                    lines.append("f 1 2 %d" % (nv + int(rng.integers(1, 4))))     # not read yet
+                elif kind < 0.55 and nv >= 3:
+                    lines.append("f %d %d %d" % tuple(-int(x) for x in rng.integers(1, nv + 1, 3)))
+                elif nv >= 3:
+                    a, b, c = (int(x) for x in rng.integers(1, nv + 1, 3))
+                    lines.append("f %d/1/1 %d//2 +%d 1" % (a, b, c))
+        text = "\n".join(lines) + ("" if rng.random() < 0.3 else "\n")
+        obj = tmp_path / ("z%d.obj" % case)
+        obj.write_text(text)
+        results = []
+        for th, mc in (("1", "1000000"), ("7", "16"), ("3", "40"), ("64", "1")):
+            monkeypatch.setenv("CRT_INGEST_THREADS", th)
+            monkeypatch.setenv("CRT_INGEST_MIN_CHUNK", mc)
+            try:
+                results.append(("ok", scene_blob(crt.Scene().add_obj(str(obj), str(tmp_path)))))
+            except crt.CrtError as e:
+                results.append(("err", str(e)))
+        assert all(r == results[0] for r in results), (case, text, [r[0] if r[0] == "ok" else r for r in results])
+        n_err += results[0][0] == "err"
+        n_ok += results[0][0] == "ok"
+    assert n_ok >= 20 and n_err >= 20            # both outcomes are exercised
