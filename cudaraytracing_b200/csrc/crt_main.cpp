@@ -155,12 +155,13 @@ int main(int argc, char** argv) {
     }
     double t4 = now_ms();
     DIE_IF(crt_render_save_png(render, out.c_str()), "save_png");
+    double t5 = now_ms();
     double msamples = st.ms_total > 0 ? (double)samples_rendered / (st.ms_total * 1e3) : 0.0;
     printf("{\"triangles\": %llu, \"nodes\": %llu, \"materials\": %u, \"lights\": %u, \"load_ms\": %.2f, \"bvh_build_gpu_ms\": %.3f, "
-           "\"upload_and_build_ms\": %.2f, \"render_ms\": %.3f, \"render_wall_ms\": %.2f, \"msamples_per_s\": %.2f, "
+           "\"upload_and_build_ms\": %.2f, \"render_ms\": %.3f, \"render_wall_ms\": %.2f, \"png_ms\": %.2f, \"msamples_per_s\": %.2f, "
            "\"extend_rays\": %llu, \"shadow_rays\": %llu, \"probe_rays\": %llu, \"iterations\": %llu, \"resumed_from\": %llu, \"out\": \"%s\"}\n",
            (unsigned long long)n_tris, (unsigned long long)n_nodes, n_mats, n_lights, t1 - t0, build_ms, t2 - t1, st.ms_total, t4 - t3,
-           msamples, (unsigned long long)st.extend_rays, (unsigned long long)st.shadow_rays, (unsigned long long)st.probe_rays,
+           t5 - t4, msamples, (unsigned long long)st.extend_rays, (unsigned long long)st.shadow_rays, (unsigned long long)st.probe_rays,
            (unsigned long long)st.iterations, (unsigned long long)resumed_from, out.c_str());
     crt_render_destroy(render);
     crt_scene_destroy(scene);
