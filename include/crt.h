@@ -118,7 +118,10 @@ int crt_inverse_view_matrix(const float eye[3], const float lookat[3], const flo
 /* Scene::Scene, include/Scene.h:28 (width/height live on the render handle here). */
 int crt_scene_create(crt_scene** out);
 /* Loader::read_OBJ + the load_object / add_normal_obj / add_light_obj loop, src/main.cu:122-145,
- * include/Loader.h:30-124, include/OBJLoader.h:61-203. May be called once per OBJ_paths entry. */
+ * include/Loader.h:30-124, include/OBJLoader.h:61-203. May be called once per OBJ_paths entry.
+ * The text is parsed in newline-aligned chunks on all host threads (environment CRT_INGEST_THREADS overrides the count);
+ * the scene, the first error and its line number do not depend on the thread count. Besides the reference's "v" and
+ * "v/vt/vn" corners, "v//vn", "v/vt", a leading '+' and negative (relative) indices are read. */
 int crt_scene_add_obj(crt_scene* s, const char* obj_path, const char* mtl_dir);
 /* Same, from memory: verts n_tris*9 (v1 v2 v3), mat_id / obj_id per triangle (obj = usemtl group,
  * numbered from 0 in first-use order), mats[n_mats]. */
@@ -221,7 +224,8 @@ int crt_render_set_stage_timing(crt_render* r, int on);
 /* Render::free, include/Render.cuh:477-487 */
 int crt_render_destroy(crt_render* r);
 
-/* PNG writer used by save_png, exposed for the host tools: rgb8 is width*height*3, top row first. */
+/* PNG writer used by save_png, exposed for the host tools: rgb8 is width*height*3, top row first. 8-bit RGB, filter 0,
+ * scanline bands of about 1 MB deflated on all host threads; the file depends on the image only. */
 int crt_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height);
 
 #ifdef __cplusplus
