@@ -207,6 +207,8 @@ class Scene:
         verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
         mat_id = np.ascontiguousarray(mat_id, np.uint32)
         obj_id = np.ascontiguousarray(obj_id, np.uint32)
+        if not (len(mat_id) == len(obj_id) == verts.shape[0]):
+            raise ValueError("mat_id and obj_id need one entry per triangle (%d triangles, %d / %d ids)" % (verts.shape[0], len(mat_id), len(obj_id)))
         mats = np.asarray(mats, np.float32)
         if mats.ndim != 2 or mats.shape[1] not in (7, 10):
             raise ValueError("mats must be n x 7 (kd,ke,ns) or n x 10 (kd,ks,ke,ns)")

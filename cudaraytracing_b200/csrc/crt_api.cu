@@ -64,6 +64,24 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 }  // namespace crt
 
+// No C++ exception crosses the C ABI: allocation failures (std::vector / std::string in the loaders, the checkpoint
+// code, the PNG reader) and anything else thrown below an entry point become a status + message.
+template <typename F>
+static int guarded(const char* fn, F&& f) noexcept {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        try { set_error(std::string(fn) + ": out of memory"); } catch (...) {}
+        return CRT_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        try { set_error(std::string(fn) + ": " + e.what()); } catch (...) {}
+        return CRT_ERR_INVALID;
+    } catch (...) {
+        try { set_error(std::string(fn) + ": unknown exception"); } catch (...) {}
+        return CRT_ERR_INVALID;
+    }
+}
+
 #define CHECK_ARG(cond, msg)                         \
     do {                                             \
         if (!(cond)) { set_error(msg); return CRT_ERR_INVALID; } \
@@ -74,68 +92,96 @@ extern "C" {
 const char* crt_last_error(void) { return get_error(); }
 int crt_abi_version(void) { return CRT_ABI_VERSION; }
 int crt_device_count(void) {
+    return guarded("crt_device_count", [&]() -> int {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+    });
 }
 
 int crt_config_load(const char* json_path, crt_config* out) {
+    return guarded("crt_config_load", [&]() -> int {
     CHECK_ARG(json_path && out, "crt_config_load: null argument");
     return load_config(json_path, out);
+    });
 }
 
 int crt_inverse_view_matrix(const float eye[3], const float lookat[3], const float up[3], float out9[9]) {
+    return guarded("crt_inverse_view_matrix", [&]() -> int {
     CHECK_ARG(eye && lookat && up && out9, "crt_inverse_view_matrix: null argument");
     inverse_view_matrix(eye, lookat, up, out9);
     return CRT_OK;
+    });
 }
 
 int crt_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height) {
+    return guarded("crt_write_png", [&]() -> int {
     return write_png(path, rgb8, width, height);
+    });
 }
 
 // ---- scene -------------------------------------------------------------------------------
 int crt_scene_create(crt_scene** out) {
+    return guarded("crt_scene_create", [&]() -> int {
     CHECK_ARG(out, "crt_scene_create: null argument");
     *out = new (std::nothrow) crt_scene();
     if (!*out) { set_error("out of memory"); return CRT_ERR_NOMEM; }
     return CRT_OK;
+    });
 }
 
 int crt_scene_add_obj(crt_scene* s, const char* obj_path, const char* mtl_dir) {
+    return guarded("crt_scene_add_obj", [&]() -> int {
     CHECK_ARG(s && obj_path && mtl_dir, "crt_scene_add_obj: null argument");
     if (s->built) { set_error("crt_scene_add_obj: BVH already built"); return CRT_ERR_STATE; }
     return load_obj(s->host, obj_path, mtl_dir);
+    });
 }
 
 int crt_scene_add_triangles(crt_scene* s, const float* verts, const uint32_t* mat_id, const uint32_t* obj_id, uint64_t n_tris,
                             const crt_material* mats, uint32_t n_mats) {
+    return guarded("crt_scene_add_triangles", [&]() -> int {
     CHECK_ARG(s && (n_tris == 0 || (verts && mat_id && obj_id)) && (n_mats == 0 || mats), "crt_scene_add_triangles: null argument");
     if (s->built) { set_error("crt_scene_add_triangles: BVH already built"); return CRT_ERR_STATE; }
     HostScene& h = s->host;
     const int mat0 = (int)h.mats.size(), obj0 = h.n_objects;
-    for (uint64_t t = 0; t < n_tris; ++t) CHECK_ARG(mat_id[t] < n_mats, "crt_scene_add_triangles: mat_id out of range");
-    for (uint32_t m = 0; m < n_mats; ++m) {
-        HostMaterial hm;
-        memcpy(hm.kd, mats[m].kd, sizeof(hm.kd));
-        memcpy(hm.ks, mats[m].ks, sizeof(hm.ks));
-        memcpy(hm.ke, mats[m].ke, sizeof(hm.ke));
-        hm.ns = mats[m].ns;
-        finish_material(hm);
-        h.mats.push_back(hm);
-    }
+    // object ids number the usemtl groups of this call: at most one per triangle
     uint32_t max_obj = 0;
-    for (uint64_t t = 0; t < n_tris; ++t) if (obj_id[t] > max_obj) max_obj = obj_id[t];
-    if (!append_triangles(h, verts, mat_id, obj_id, (size_t)n_tris, mat0, obj0)) {
+    for (uint64_t t = 0; t < n_tris; ++t) {
+        CHECK_ARG(mat_id[t] < n_mats, "crt_scene_add_triangles: mat_id out of range");
+        CHECK_ARG((uint64_t)obj_id[t] < n_tris, "crt_scene_add_triangles: obj_id out of range (ids number the groups of this call: < n_tris)");
+        if (obj_id[t] > max_obj) max_obj = obj_id[t];
+    }
+    CHECK_ARG(n_tris <= 0x7fffffffull / 4 && (uint64_t)obj0 + max_obj + 1 <= 0x7fffffffull, "crt_scene_add_triangles: scene too large");
+    if (!append_triangles(h, verts, mat_id, obj_id, (size_t)n_tris, mat0, obj0)) {      // leaves the scene unchanged when it fails
         set_error("crt_scene_add_triangles: non-finite vertex coordinate");
         return CRT_ERR_INVALID;
     }
-    if (n_tris) h.n_objects = obj0 + (int)max_obj + 1;
-    finish_objects(h);
+    try {
+        for (uint32_t m = 0; m < n_mats; ++m) {
+            HostMaterial hm;
+            memcpy(hm.kd, mats[m].kd, sizeof(hm.kd));
+            memcpy(hm.ks, mats[m].ks, sizeof(hm.ks));
+            memcpy(hm.ke, mats[m].ke, sizeof(hm.ke));
+            hm.ns = mats[m].ns;
+            finish_material(hm);
+            h.mats.push_back(hm);
+        }
+        if (n_tris) h.n_objects = obj0 + (int)max_obj + 1;
+        finish_objects(h);
+    } catch (...) {                                        // allocation failure: back to the scene as it was
+        const size_t t0 = h.n_tris() - (size_t)n_tris;
+        h.verts.resize(9 * t0); h.normal.resize(3 * t0); h.area.resize(t0); h.area_of_obj.resize(t0); h.mat.resize(t0); h.obj.resize(t0);
+        h.mats.resize(mat0);
+        h.n_objects = obj0;
+        throw;
+    }
     return CRT_OK;
+    });
 }
 
 int crt_scene_build_bvh(crt_scene* s, uint32_t thresh_n, int builder, int device, float* build_ms) {
+    return guarded("crt_scene_build_bvh", [&]() -> int {
     CHECK_ARG(s, "crt_scene_build_bvh: null scene");
     CHECK_ARG(builder >= CRT_BUILDER_LBVH && builder <= CRT_BUILDER_PLOC8, "crt_scene_build_bvh: unknown builder");
     int n = crt_device_count();
@@ -145,18 +191,22 @@ int crt_scene_build_bvh(crt_scene* s, uint32_t thresh_n, int builder, int device
     s->built = rc == CRT_OK;
     s->thresh_n = thresh_n;
     return rc;
+    });
 }
 
 int crt_scene_counts(crt_scene* s, uint64_t* n_tris, uint32_t* n_mats, uint32_t* n_lights, uint64_t* n_nodes) {
+    return guarded("crt_scene_counts", [&]() -> int {
     CHECK_ARG(s, "crt_scene_counts: null scene");
     if (n_tris) *n_tris = s->host.n_tris();
     if (n_mats) *n_mats = (uint32_t)s->host.mats.size();
     if (n_lights) *n_lights = (uint32_t)s->host.lights.size();
     if (n_nodes) *n_nodes = s->built ? s->dev.n_nodes : 0;
     return CRT_OK;
+    });
 }
 
 int crt_scene_export_tris(crt_scene* s, float* verts, float* normal, float* area, float* area_of_obj, int32_t* mat, int32_t* obj) {
+    return guarded("crt_scene_export_tris", [&]() -> int {
     CHECK_ARG(s, "crt_scene_export_tris: null scene");
     const HostScene& h = s->host;
     const size_t n = h.n_tris();
@@ -167,9 +217,11 @@ int crt_scene_export_tris(crt_scene* s, float* verts, float* normal, float* area
     if (mat) memcpy(mat, h.mat.data(), sizeof(int32_t) * n);
     if (obj) memcpy(obj, h.obj.data(), sizeof(int32_t) * n);
     return CRT_OK;
+    });
 }
 
 int crt_scene_export_mats(crt_scene* s, float* out) {
+    return guarded("crt_scene_export_mats", [&]() -> int {
     CHECK_ARG(s && out, "crt_scene_export_mats: null argument");
     for (size_t m = 0; m < s->host.mats.size(); ++m) {
         const HostMaterial& hm = s->host.mats[m];
@@ -178,9 +230,11 @@ int crt_scene_export_mats(crt_scene* s, float* out) {
         o[6] = hm.ns; o[7] = (float)hm.has_emit; o[8] = (float)hm.mode;
     }
     return CRT_OK;
+    });
 }
 
 int crt_scene_export_light(crt_scene* s, uint32_t li, int32_t* faces, uint32_t* n, float* area) {
+    return guarded("crt_scene_export_light", [&]() -> int {
     CHECK_ARG(s && n, "crt_scene_export_light: null argument");
     CHECK_ARG(li < s->host.lights.size(), "crt_scene_export_light: light index out of range");
     const HostLight& L = s->host.lights[li];
@@ -191,9 +245,11 @@ int crt_scene_export_light(crt_scene* s, uint32_t li, int32_t* faces, uint32_t* 
     *n = (uint32_t)L.faces.size();
     if (area) *area = L.area;
     return CRT_OK;
+    });
 }
 
 int crt_scene_export_bvh(crt_scene* s, crt_bvh_node* nodes, int32_t* tri_order, uint8_t* last, float bounds[6]) {
+    return guarded("crt_scene_export_bvh", [&]() -> int {
     CHECK_ARG(s, "crt_scene_export_bvh: null scene");
     if (!s->built) { set_error("crt_scene_export_bvh: BVH not built"); return CRT_ERR_STATE; }
     if (s->dev.wide) { set_error("crt_scene_export_bvh: the scene has 8-wide nodes (use crt_scene_export_bvh8)"); return CRT_ERR_STATE; }
@@ -203,9 +259,11 @@ int crt_scene_export_bvh(crt_scene* s, crt_bvh_node* nodes, int32_t* tri_order, 
     if (last && s->dev.n_tris) CRT_CUDA(cudaMemcpy(last, s->dev.last, s->dev.n_tris, cudaMemcpyDeviceToHost));
     if (bounds) memcpy(bounds, s->dev.bounds, sizeof(float) * 6);
     return CRT_OK;
+    });
 }
 
 int crt_scene_export_bvh8(crt_scene* s, crt_bvh8_node* nodes, int32_t* tri_order, uint8_t* last, float bounds[6]) {
+    return guarded("crt_scene_export_bvh8", [&]() -> int {
     static_assert(sizeof(crt_bvh8_node) == 80, "crt_bvh8_node must be 80 bytes");
     CHECK_ARG(s, "crt_scene_export_bvh8: null scene");
     if (!s->built) { set_error("crt_scene_export_bvh8: BVH not built"); return CRT_ERR_STATE; }
@@ -216,34 +274,42 @@ int crt_scene_export_bvh8(crt_scene* s, crt_bvh8_node* nodes, int32_t* tri_order
     if (last && s->dev.n_tris) CRT_CUDA(cudaMemcpy(last, s->dev.last, s->dev.n_tris, cudaMemcpyDeviceToHost));
     if (bounds) memcpy(bounds, s->dev.bounds, sizeof(float) * 6);
     return CRT_OK;
+    });
 }
 
 int crt_scene_bvh_kind(crt_scene* s, int* builder) {
+    return guarded("crt_scene_bvh_kind", [&]() -> int {
     CHECK_ARG(s && builder, "crt_scene_bvh_kind: null argument");
     if (!s->built) { set_error("crt_scene_bvh_kind: BVH not built"); return CRT_ERR_STATE; }
     *builder = s->dev.builder;
     return CRT_OK;
+    });
 }
 
 int crt_scene_destroy(crt_scene* s) {
+    return guarded("crt_scene_destroy", [&]() -> int {
     if (!s) return CRT_OK;
     if (s->built) { cudaSetDevice(s->dev.device); s->dev.release(); }
     delete s;
     return CRT_OK;
+    });
 }
 
 // ---- ray batches ---------------------------------------------------------------------------
 int crt_trace_rays_device(crt_scene* s, const void* d_rays, uint64_t n, int mode, void* d_t_out, void* d_face_out, void* stream,
                           float* kernel_ms) {
+    return guarded("crt_trace_rays_device", [&]() -> int {
     CHECK_ARG(s && (n == 0 || d_rays), "crt_trace_rays_device: null argument");
     CHECK_ARG(mode == CRT_RAY_CLOSEST || mode == CRT_RAY_ANY, "crt_trace_rays_device: unknown mode");
     if (!s->built) { set_error("crt_trace_rays: BVH not built"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(s->dev.device));
     if (n == 0) { if (kernel_ms) *kernel_ms = 0; return CRT_OK; }
     return trace_rays_device(s->dev, (const float4*)d_rays, n, mode, (float*)d_t_out, (int*)d_face_out, (cudaStream_t)stream, kernel_ms);
+    });
 }
 
 int crt_trace_rays(crt_scene* s, const float* rays, uint64_t n, int mode, float* t_out, int32_t* face_out, float* kernel_ms) {
+    return guarded("crt_trace_rays", [&]() -> int {
     CHECK_ARG(s && (n == 0 || rays), "crt_trace_rays: null argument");
     if (!s->built) { set_error("crt_trace_rays: BVH not built"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(s->dev.device));
@@ -265,17 +331,21 @@ int crt_trace_rays(crt_scene* s, const float* rays, uint64_t n, int mode, float*
     }
     cudaFree(d_rays); cudaFree(d_t); cudaFree(d_face);
     return rc;
+    });
 }
 
 int crt_random_rays_device(crt_scene* s, void* d_rays, uint64_t n, uint64_t start, uint32_t key, int any_hit, void* stream) {
+    return guarded("crt_random_rays_device", [&]() -> int {
     CHECK_ARG(s && (n == 0 || d_rays), "crt_random_rays_device: null argument");
     if (!s->built) { set_error("crt_random_rays_device: BVH not built"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(s->dev.device));
     return random_rays_device(s->dev, (float4*)d_rays, n, start, key, any_hit, (cudaStream_t)stream);
+    });
 }
 
 // ---- render ----------------------------------------------------------------------------------
 int crt_render_create(crt_scene* s, uint32_t width, uint32_t height, crt_render** out) {
+    return guarded("crt_render_create", [&]() -> int {
     CHECK_ARG(s && out, "crt_render_create: null argument");
     CHECK_ARG(width > 0 && height > 0 && (uint64_t)width * height <= (1ull << 28), "crt_render_create: bad image size");
     if (!s->built) { set_error("crt_render_create: build the BVH first (crt_scene_build_bvh)"); return CRT_ERR_STATE; }
@@ -295,63 +365,85 @@ int crt_render_create(crt_scene* s, uint32_t width, uint32_t height, crt_render*
     if (rc != CRT_OK) { crt_render_destroy(r); return rc; }
     *out = r;
     return CRT_OK;
+    });
 }
 
 int crt_render_set_spp(crt_render* r, uint32_t spp) {
+    return guarded("crt_render_set_spp", [&]() -> int {
     CHECK_ARG(r && spp > 0, "crt_render_set_spp: invalid argument");
     r->rs.spp = spp;
     return CRT_OK;
+    });
 }
 int crt_render_set_p_rr(crt_render* r, float p_rr) {
+    return guarded("crt_render_set_p_rr", [&]() -> int {
     CHECK_ARG(r && p_rr >= 0.0f && p_rr <= 1.0f, "crt_render_set_p_rr: P_RR must be in [0,1]");
     r->rs.p_rr = p_rr;
     return CRT_OK;
+    });
 }
 int crt_render_set_light_sample_n(crt_render* r, uint32_t n) {
+    return guarded("crt_render_set_light_sample_n", [&]() -> int {
     CHECK_ARG(r && n > 0 && n <= 4096, "crt_render_set_light_sample_n: invalid argument");
     r->rs.light_sample_n = n;
     return CRT_OK;
+    });
 }
 int crt_render_set_seed(crt_render* r, uint32_t seed) {
+    return guarded("crt_render_set_seed", [&]() -> int {
     CHECK_ARG(r, "crt_render_set_seed: null handle");
     r->rs.seed = seed;
     return CRT_OK;
+    });
 }
 int crt_render_set_estimator(crt_render* r, int estimator) {
+    return guarded("crt_render_set_estimator", [&]() -> int {
     CHECK_ARG(r && (estimator == CRT_ESTIMATOR_COMPAT || estimator == CRT_ESTIMATOR_MIS), "crt_render_set_estimator: unknown estimator");
     r->rs.estimator = estimator;
     return CRT_OK;
+    });
 }
 int crt_render_set_sample_range(crt_render* r, uint32_t begin, uint32_t end) {
+    return guarded("crt_render_set_sample_range", [&]() -> int {
     CHECK_ARG(r && begin <= end, "crt_render_set_sample_range: invalid range");
     const unsigned long long npix = (unsigned long long)r->rs.width * r->rs.height;
     r->rs.work_begin = npix * begin; r->rs.work_end = npix * end; r->rs.range_set = true;
     return CRT_OK;
+    });
 }
 int crt_render_set_work_range(crt_render* r, uint64_t begin, uint64_t end) {
+    return guarded("crt_render_set_work_range", [&]() -> int {
     CHECK_ARG(r && begin <= end, "crt_render_set_work_range: invalid range");
     r->rs.work_begin = begin; r->rs.work_end = end; r->rs.range_set = true;
     return CRT_OK;
+    });
 }
 int crt_render_clear_range(crt_render* r) {
+    return guarded("crt_render_clear_range", [&]() -> int {
     CHECK_ARG(r, "crt_render_clear_range: null handle");
     r->rs.range_set = false;
     return CRT_OK;
+    });
 }
 int crt_render_set_stream(crt_render* r, void* cuda_stream) {
+    return guarded("crt_render_set_stream", [&]() -> int {
     CHECK_ARG(r, "crt_render_set_stream: null handle");
     if (r->own_stream && r->stream) cudaStreamDestroy(r->stream);
     r->stream = (cudaStream_t)cuda_stream;
     r->own_stream = false;
     return CRT_OK;
+    });
 }
 int crt_render_set_stage_timing(crt_render* r, int on) {
+    return guarded("crt_render_set_stage_timing", [&]() -> int {
     CHECK_ARG(r, "crt_render_set_stage_timing: null handle");
     r->rs.stage_timing = on != 0;
     return CRT_OK;
+    });
 }
 
 int crt_render_run_view(crt_render* r, const float eye[3], const float inv_view[9], float fovy_rad) {
+    return guarded("crt_render_run_view", [&]() -> int {
     CHECK_ARG(r && eye && inv_view, "crt_render_run_view: null argument");
     CRT_CUDA(cudaSetDevice(r->scene->dev.device));
     if (r->rs.accumulate && r->cam_set && !same_camera(r, eye, inv_view, fovy_rad)) {
@@ -365,23 +457,29 @@ int crt_render_run_view(crt_render* r, const float eye[3], const float inv_view[
     int rc = wavefront_render(r->wf, r->scene->dev, r->rs, eye, inv_view, tan_half, r->stream, &r->stats);
     r->rendered = rc == CRT_OK;
     return rc;
+    });
 }
 
 int crt_render_set_accumulate(crt_render* r, int on) {
+    return guarded("crt_render_set_accumulate", [&]() -> int {
     CHECK_ARG(r, "crt_render_set_accumulate: null handle");
     r->rs.accumulate = on != 0;
     return CRT_OK;
+    });
 }
 int crt_render_clear_accum(crt_render* r) {
+    return guarded("crt_render_clear_accum", [&]() -> int {
     CHECK_ARG(r, "crt_render_clear_accum: null handle");
     CRT_CUDA(cudaSetDevice(r->scene->dev.device));
     CRT_CUDA(cudaMemsetAsync(wavefront_accum(r->wf), 0, sizeof(int64_t) * 3 * (size_t)r->rs.width * r->rs.height, r->stream));
     CRT_CUDA(cudaStreamSynchronize(r->stream));
     r->cam_set = false;
     return CRT_OK;
+    });
 }
 
 int crt_render_save_checkpoint(crt_render* r, const char* path, uint64_t work_done) {
+    return guarded("crt_render_save_checkpoint", [&]() -> int {
     CHECK_ARG(r && path, "crt_render_save_checkpoint: null argument");
     if (!r->cam_set) { set_error("crt_render_save_checkpoint: nothing rendered yet"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(r->scene->dev.device));
@@ -403,9 +501,11 @@ int crt_render_save_checkpoint(crt_render* r, const char* path, uint64_t work_do
     ok = (fclose(f) == 0) && ok;
     if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); set_error(std::string("crt_render_save_checkpoint: write failed: ") + path); return CRT_ERR_IO; }
     return CRT_OK;
+    });
 }
 
 int crt_render_load_checkpoint(crt_render* r, const char* path, uint64_t* work_done, float eye[3], float inv_view[9], float* fovy_rad) {
+    return guarded("crt_render_load_checkpoint", [&]() -> int {
     CHECK_ARG(r && path, "crt_render_load_checkpoint: null argument");
     FILE* f = fopen(path, "rb");
     if (!f) { set_error(std::string("crt_render_load_checkpoint: cannot open ") + path); return CRT_ERR_IO; }
@@ -443,19 +543,24 @@ int crt_render_load_checkpoint(crt_render* r, const char* path, uint64_t* work_d
     if (inv_view) memcpy(inv_view, h.M, sizeof(h.M));
     if (fovy_rad) *fovy_rad = h.fovy;
     return CRT_OK;
+    });
 }
 
 int crt_render_device_accum(crt_render* r, void** d_accum) {
+    return guarded("crt_render_device_accum", [&]() -> int {
     CHECK_ARG(r && d_accum, "crt_render_device_accum: null argument");
     *d_accum = wavefront_accum(r->wf);
     return CRT_OK;
+    });
 }
 
 int crt_render_get_accum_i64(crt_render* r, int64_t* out) {
+    return guarded("crt_render_get_accum_i64", [&]() -> int {
     CHECK_ARG(r && out, "crt_render_get_accum_i64: null argument");
     CRT_CUDA(cudaSetDevice(r->scene->dev.device));
     CRT_CUDA(cudaMemcpy(out, wavefront_accum(r->wf), sizeof(int64_t) * 3 * (size_t)r->rs.width * r->rs.height, cudaMemcpyDeviceToHost));
     return CRT_OK;
+    });
 }
 
 static int resolve_to(crt_render* r, float* lin_host, uint8_t* rgb_host) {
@@ -470,27 +575,36 @@ static int resolve_to(crt_render* r, float* lin_host, uint8_t* rgb_host) {
 }
 
 int crt_render_get_accum(crt_render* r, float* rgb) {
+    return guarded("crt_render_get_accum", [&]() -> int {
     CHECK_ARG(r && rgb, "crt_render_get_accum: null argument");
     return resolve_to(r, rgb, nullptr);
+    });
 }
 int crt_render_get_rgb8(crt_render* r, uint8_t* out) {
+    return guarded("crt_render_get_rgb8", [&]() -> int {
     CHECK_ARG(r && out, "crt_render_get_rgb8: null argument");
     return resolve_to(r, nullptr, out);
+    });
 }
 int crt_render_save_png(crt_render* r, const char* path) {
+    return guarded("crt_render_save_png", [&]() -> int {
     CHECK_ARG(r && path, "crt_render_save_png: null argument");
     std::vector<uint8_t> rgb(3 * (size_t)r->rs.width * r->rs.height);
     int rc = resolve_to(r, nullptr, rgb.data());
     if (rc != CRT_OK) return rc;
     return write_png(path, rgb.data(), r->rs.width, r->rs.height);
+    });
 }
 int crt_render_get_stats(crt_render* r, crt_render_stats* out) {
+    return guarded("crt_render_get_stats", [&]() -> int {
     CHECK_ARG(r && out, "crt_render_get_stats: null argument");
     *out = r->stats;
     return CRT_OK;
+    });
 }
 
 int crt_render_destroy(crt_render* r) {
+    return guarded("crt_render_destroy", [&]() -> int {
     if (!r) return CRT_OK;
     if (r->scene) cudaSetDevice(r->scene->dev.device);
     wavefront_destroy(r->wf);
@@ -499,6 +613,7 @@ int crt_render_destroy(crt_render* r) {
     if (r->own_stream && r->stream) cudaStreamDestroy(r->stream);
     delete r;
     return CRT_OK;
+    });
 }
 
 }  // extern "C"

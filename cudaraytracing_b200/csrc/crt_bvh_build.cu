@@ -821,6 +821,16 @@ int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face
                 BUILD_CHECK(cudaStreamSynchronize(st));
                 if (merged == 0 || merged > m / 2) { set_error("PLOC: a round merged nothing"); rc = CRT_ERR_STATE; goto done; }
                 round_start.push_back(created);
+                // Every round adds at most one level, so the number of rounds bounds the depth of the tree. The pair-node
+                // traversal pushes onto a stack of kStackSize entries without a bounds check (a Karras tree cannot be deeper
+                // than 63 Morton bits + duplicate levels; PLOC has no such bound: boxes that grow geometrically merge one
+                // pair per round, a chain of depth ~n), and every round costs a host synchronisation.
+                if (round_start.size() >= (size_t)(wide ? 1024 : kStackSize - 1)) {
+                    set_error("PLOC: the agglomeration needs more rounds than the traversal stack is deep (" + std::to_string(round_start.size()) +
+                              "); build this scene with CRT_BUILDER_LBVH / CRT_BUILDER_LBVH8");
+                    rc = CRT_ERR_STATE;
+                    goto done;
+                }
                 created += merged;
                 m -= merged;
                 cur ^= 1;

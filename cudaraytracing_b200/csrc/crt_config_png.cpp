@@ -70,7 +70,11 @@ struct JParser {
         ++p;
         return true;
     }
+    int depth = 0;                    // nesting of the value being parsed: a config is 3 levels deep; 64 bounds the recursion
+    struct DepthGuard { int& d; explicit DepthGuard(int& x) : d(x) { ++d; } ~DepthGuard() { --d; } };
     bool parse(JValue& v) {
+        DepthGuard guard(depth);
+        if (depth > 64) return fail("nesting too deep");
         ws();
         if (p >= end) return fail("unexpected end");
         if (*p == '{') {
@@ -320,6 +324,9 @@ int read_png(const std::vector<uint8_t>& file, int* w, int* h, int* ch, std::vec
     const size_t bpp_bits = (size_t)nc * depth;
     const size_t stride = ((size_t)W * bpp_bits + 7) / 8;
     const size_t fb = bpp_bits >= 8 ? bpp_bits / 8 : 1;                    // filter byte distance
+    // the header is untrusted: deflate expands at most 1032:1, so a W x H the IDAT stream cannot fill is rejected before
+    // anything of that size is allocated (and a texture beyond 2^28 samples is not a map_Kd anyone ships)
+    if ((stride + 1) > ((size_t)1 << 40) / H || (stride + 1) * H > idat.size() * 1032 + 1024 || (size_t)W * H > ((size_t)1 << 28)) return 2;
     std::vector<uint8_t> raw((stride + 1) * H);
     uLongf raw_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) return 2;

@@ -296,260 +296,142 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
     return best;
 }
 
-// ---- persistent-lane traversal -------------------------------------------------------------
-// The per-ray rule is exactly traverse<MODE> above (same visits in the same order, so the oracle's
-// node/triangle counts apply); what changes is how a warp's lanes are kept busy:
-//   * every lane owns one ray at a time and, when it finishes, takes the next ray of the queue
-//     (warp-aggregated atomicAdd on `fetch`) as soon as at least kRefillLanes lanes are idle, instead of
-//     waiting for the slowest ray of a fixed group of 32;
-//   * "while-while" phases (Aila & Laine 2009): all lanes walk inner nodes until each holds a leaf, then
-//     all lanes intersect their leaf, which keeps lanes on the same instructions.
-// load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result.
-// Measured and removed (B200, profiles/r01_s21.md): a warp reserving 32-128 ray indices at a time with one reservation of
-// lookahead + L2 prefetch of those rays is 8-12 % SLOWER than one global atomicAdd per refill, on short frames and at
-// steady state alike; prefetch.global.L1 of a queued leaf's triangles costs 5 %.
-static constexpr int kDone = 0x7ffffffe;
+// ---- persistent-lane traversal with a per-warp leaf queue ------------------------------------------
+// The per-ray rule is traverse<MODE> above (pair nodes) / traverse_wide<MODE> (crt_wide.cuh); what changes is how a
+// warp's lanes are kept busy (measured alternatives - fixed 32-ray batches, while-while, if-if - in DESIGN.md 7.1):
+//   * every lane owns one ray at a time and takes the next ray of the queue when it finishes (RayFetch below), as
+//     soon as kRefillLanes lanes are idle, instead of waiting for the slowest ray of a fixed group of 32;
+//   * node steps and triangle tests are decoupled: a lane that reaches a leaf does not test it, it appends
+//     (lane, first slot) to a queue in shared memory and goes on with its next node, so every live lane does a node
+//     step in every iteration (in a while-while loop ~10 of 32 lanes were active in the node phase, profiles/r01_c3.md);
+//   * when enough leaves are queued (or no lane has a node left) the whole warp tests them, one queue entry per
+//     lane, against the owners' rays (mirrored in shared memory); the owners' best hits are combined with a 64-bit
+//     shared-memory atomicMin on (t bits, face id), which is exactly the "smaller t, ties -> lower face id" rule;
+//   * the price is speculation: a lane keeps walking with the t-limit of the last flush, so it visits somewhat more
+//     nodes than the sequential rule (the oracle's counts are the algorithmic minimum).
+// One template for both node layouts: the Walker policy (PairWalker below, WideWalker in crt_wide.cuh) owns the
+// per-lane traversal state and does the node steps; this function owns the queue flush, the finished rays and the refill.
+// load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result;
+// prefetch(first, count) is called by the whole warp for the rays it will load a chunk later (RayFetch).
 #ifndef CRT_REFILL_LANES
 #define CRT_REFILL_LANES 12
 #endif
 static constexpr int kRefillLanes = CRT_REFILL_LANES;
-#ifndef CRT_NODE_BREAK
-#define CRT_NODE_BREAK 0
-#endif
-static constexpr int kNodeBreak = CRT_NODE_BREAK;
 
-template <int MODE, int STRAT, typename Load, typename Done>
-CRT_DEV void trace_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int stack[kStackSize];
-    int sp = 0, cur = kDone;
-    uint32_t idx = 0;
-    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 0);
-    float tmax = 0.0f, tlimit = 0.0f;
-    HitRec best;
-    best.t = FLT_MAX; best.slot = -1; best.face = -1;
-    bool have = false, exhausted = false, zray = false;
-    for (;;) {
-        const unsigned idle = __ballot_sync(0xffffffffu, !have);
-        if (idle) {
-            const int n_idle = __popc(idle);
-            if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
-                const int leader = __ffs(idle) - 1;
-                uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (!have) {
-                    const uint32_t i = base + __popc(idle & lt_mask);
-                    if (i < n) {
-                        idx = i;
-                        const bool live = load(i, o, d, tmax);
-                        inv = box_inv3(d);
-                        zray = has_parallel_axis(inv);
-                        tlimit = MODE == 0 ? FLT_MAX : tmax;
-                        best.t = FLT_MAX; best.slot = -1; best.face = -1;
-                        sp = 0;
-                        cur = (live && sc.n_nodes) ? 0 : kDone;
-                        have = true;
-                    }
-                }
-                if (base + (uint32_t)n_idle >= n) exhausted = true;
-            }
-            if (!__any_sync(0xffffffffu, have)) {
-                if (exhausted) break;
-                continue;
-            }
-        }
-        if (have) {
-            // inner nodes until this lane holds a leaf (or is finished)
-            // STRAT 0: while-while (walk nodes until a leaf); STRAT 1: if-if (one node step per turn)
-            bool first = true;
-            while (cur >= 0 && cur != kDone && (STRAT == 0 || first)) {
-                first = false;
-                if (cur == kEmptyChild) { cur = sp ? stack[--sp] : kDone; continue; }   // absent child of a one-leaf scene
-                float4 n0, n1, n2, n3;
-                load_node(sc.nodes, cur, n0, n1, n2, n3);
-                const float lim = tlimit * 1.0001f;
-                float e0, e1;
-                const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0, zray);
-                const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1, zray);
-                const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-                if (h0 && h1) {
-                    int nearc = c0, farc = c1;
-                    if (e1 < e0) { nearc = c1; farc = c0; }
-                    stack[sp++] = farc;
-                    cur = nearc;
-                } else if (h0) cur = c0;
-                else if (h1) cur = c1;
-                else cur = sp ? stack[--sp] : kDone;
-                // leave the node phase once fewer than kNodeBreak lanes are still walking nodes: the
-                // others are waiting with a leaf in hand (fresh rays have long first descents)
-                if (kNodeBreak > 0 && __popc(__activemask()) < kNodeBreak) break;
-            }
-            if (cur < 0 && (STRAT == 0 || first)) {   // one leaf
-                int slot = ~cur;
-                bool stop = false;
-                for (;; ++slot) {
-                    V3 tv1, te1, te2;
-                    const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
-                    const int face = (int)(fw & ~kLastBit);
-                    float t;
-                    if (tri_test(tv1, te1, te2, o, d, &t) && t > kEps) {
-                        if (MODE == 0) {
-                            if (t < best.t || (t == best.t && face < best.face)) {
-                                best.t = t; best.slot = slot; best.face = face;
-                                tlimit = t;
-                            }
-                        } else if (tmax - t > kEps) {
-                            best.t = t; best.slot = slot; best.face = face;
-                            stop = true;
-                            break;
-                        }
-                    }
-                    if (fw & kLastBit) break;
-                }
-                cur = (stop || sp == 0) ? kDone : stack[--sp];
-            }
-            if (cur == kDone) {
-                done(idx, best);
-                have = false;
-            }
-        }
+// How a warp takes ray indices from the queue counter `fetch`:
+//   0: one global atomicAdd of the idle-lane count per refill (round 1). Every warp of the grid adds to one address and
+//      waits for the round trip: at C3 steady state ~30 % of the stall samples of k_shadow sat on the shuffle that
+//      broadcasts the returned value (profiles/r02_s02.md);
+//   4: the queue is cut into chunks of CRT_FETCH_CHUNK rays; the first 7/8 of the chunks are dealt round-robin to the
+//      warps of the grid (warp w takes chunks w, w + W, w + 2W ...: no atomic, and the next chunk is known, so its rays
+//      are prefetched into L2 while the current one is traced), the last 1/8 are taken dynamically with one atomicAdd per
+//      chunk to level the finish. (ptxas wraps its own warp aggregation - vote + shuffle of the result right behind the
+//      atomic - around an atomic in `if (lane == 0)`, inline PTX included, so a reservation "one chunk ahead" still waits
+//      for the round trip on the spot: r02_s03.)
+#ifndef CRT_FETCH
+#define CRT_FETCH 4
+#endif
+#ifndef CRT_FETCH_CHUNK
+#define CRT_FETCH_CHUNK 128
+#endif
+struct RayFetch {
+    uint32_t next = 0, end = 0;        // the warp's current chunk [next, end) (the same in every lane)
+    uint32_t cursor = 0;               // next chunk of this warp's round-robin share
+    bool exhausted = false;            // nothing left to take
+    CRT_DEV static uint32_t n_chunks(uint32_t n) { return (n + (uint32_t)CRT_FETCH_CHUNK - 1u) / (uint32_t)CRT_FETCH_CHUNK; }
+    CRT_DEV static uint32_t n_static(uint32_t n) { const uint32_t c = n_chunks(n); return c - c / 8u; }
+    CRT_DEV static uint32_t n_warps() { return gridDim.x * (blockDim.x >> 5); }
+    CRT_DEV void init(uint32_t n) {
+        cursor = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (n == 0) exhausted = true;
     }
+    CRT_DEV bool drained() const { return exhausted && next == end; }
+    // Called by the whole warp with `want` idle lanes: returns how many indices [first, first + take) it may hand out.
+    // prefetch(first, count): the chunk this warp will take after the one it adopts now.
+    template <typename Prefetch>
+    CRT_DEV uint32_t take(uint32_t* fetch, uint32_t n, int lane, uint32_t want, uint32_t& first, Prefetch&& prefetch) {
+#if CRT_FETCH == 0
+        if (exhausted) return 0;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(fetch, want);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + want >= n) exhausted = true;
+        first = base;
+        return base < n ? min(want, n - base) : 0u;
+#else
+        if (next == end && !exhausted) {
+            const uint32_t nc = n_chunks(n), ns = n_static(n);
+            uint32_t c;
+            if (cursor < ns) {
+                c = cursor;
+                cursor += n_warps();
+                if (cursor < ns) prefetch(cursor * (uint32_t)CRT_FETCH_CHUNK, min((uint32_t)CRT_FETCH_CHUNK, n - cursor * (uint32_t)CRT_FETCH_CHUNK));
+            } else {
+                uint32_t ticket = 0;
+                if (lane == 0) ticket = atomicAdd(fetch, 1u);
+                c = ns + __shfl_sync(0xffffffffu, ticket, 0);
+            }
+            if (c >= nc) { exhausted = true; next = end = 0; }
+            else { next = c * (uint32_t)CRT_FETCH_CHUNK; end = min(next + (uint32_t)CRT_FETCH_CHUNK, n); }
+        }
+        const uint32_t k = min(want, end - next);
+        first = next;
+        next += k;
+        return k;
+#endif
+    }
+};
+// prefetch.global.L2 of `count` records of `stride` bytes starting at record `first`: one 128-byte line per lane and round
+CRT_DEV void prefetch_l2(const void* base, uint32_t first, uint32_t count, uint32_t stride, int lane) {
+    const char* p = (const char*)base + (size_t)first * stride;
+    const uint32_t bytes = count * stride;
+    for (uint32_t off = (uint32_t)lane * 128u; off < bytes; off += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
 }
 
-// ---- persistent lanes with a per-warp leaf queue (STRAT 2) --------------------------------------
-// Same BVH, same box and triangle tests, same result (closest: smallest (t, face); any: blocked or
-// not) - but node steps and triangle tests are decoupled, because in the while-while loop above only
-// ~10 of 32 lanes are active in the node loop (ncu, profiles/r01_c3.md): every lane waits for the
-// lane with the longest walk to its next leaf.
-//   * a lane that reaches a leaf does not test it: it appends (lane, first slot) to a queue in shared
-//     memory and goes on with the next entry of its stack, so every live lane does a node step in
-//     every iteration;
-//   * when 32 leaves are queued (or no lane has a node left) the whole warp tests them, one queue
-//     entry per lane, against the owners' rays (mirrored in shared memory); the owners' best hits are
-//     combined with a 64-bit shared-memory atomicMin on (t bits, face id), which is exactly the
-//     "smaller t, ties -> lower face id" rule;
-//   * the price is speculation: a lane keeps walking with the t-limit of the last flush, so it visits
-//     somewhat more nodes than the sequential rule (the oracle's counts are the algorithmic minimum).
-#ifndef CRT_QFLUSH
-#define CRT_QFLUSH 16
-#endif
-#ifndef CRT_QSTEPS
-#define CRT_QSTEPS 6
-#endif
-#ifndef CRT_QBALLOT
-#define CRT_QBALLOT 1      // queue positions from one ballot instead of a shared atomicAdd that serialises the lanes (+2 %, r01_s18)
-#endif
-// CRT_SSTACK = N > 0: the first N entries of every lane's traversal stack live in shared memory, laid out
-// [entry][thread] so that a push / pop is one conflict-free wavefront whatever the lanes' depths are; a
-// local-memory stack costs one L1 wavefront per distinct depth in the warp, and the traversal kernels are
-// bound by L1 wavefronts (profiles/r01_s11.md). Deeper entries spill to the local array.
-#ifndef CRT_SSTACK
-#define CRT_SSTACK 8       // with CRT_LD256 and CRT_QBALLOT: +7 % on cornell-box, +3 % on veach-mis (profiles/r01_s18.md)
-#endif
-static constexpr int kSharedStack = CRT_SSTACK;
-static constexpr int kQueueFlush = CRT_QFLUSH;       // queued leaves that trigger a flush
-static constexpr int kQueueSteps = CRT_QSTEPS;       // node steps between two looks at the queue
-static constexpr int kQueueCap = kQueueFlush + 32 * kQueueSteps;
+template <int CAP>
 struct WarpLeafQueue {
-    float ox[32], oy[32], oz[32], dx[32], dy[32], dz[32], tmax[32];
-    unsigned long long best[32];
+    float ox[32], oy[32], oz[32], dx[32], dy[32], dz[32], tmax[32];     // the rays the lanes own
+    unsigned long long best[32];                                         // (t bits, face id) of the owner's best hit
     int best_slot[32];
-    int q_slot[kQueueCap];
-    unsigned char q_lane[kQueueCap];
+    int q_slot[CAP];                                                     // queued leaves: first triangle slot ...
+    unsigned char q_lane[CAP];                                           // ... and the lane that owns the ray
     int count;
 };
+static constexpr unsigned long long kNoHitKey = ((unsigned long long)0x7f7fffffu << 32) | 0x7fffffffull;   // t = FLT_MAX
 
-template <int MODE, typename Load, typename Done>
-CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    __shared__ WarpLeafQueue s_wq[4];                      // launched with 128 threads per block
-    WarpLeafQueue& q = s_wq[threadIdx.x >> 5];
+template <int MODE, typename Walker, typename Load, typename Done, typename Prefetch>
+CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Prefetch prefetch) {
+    typedef WarpLeafQueue<Walker::kCap> Queue;
+    __shared__ Queue s_wq[4];                              // launched with 128 threads per block
+    Queue& q = s_wq[threadIdx.x >> 5];
     const unsigned kFull = 0xffffffffu;
-    const unsigned long long kNoHit = ((unsigned long long)0x7f7fffffu << 32) | 0x7fffffffull;   // t = FLT_MAX
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int stack[kStackSize - kSharedStack];
-    __shared__ int s_stack[kSharedStack > 0 ? kSharedStack : 1][128];
-    int sp = 0, cur = kDone;                               // kDone: no node in hand and the stack is empty
-    auto push = [&](int v) {
-        if (kSharedStack > 0 && sp < kSharedStack) s_stack[sp][threadIdx.x] = v;
-        else stack[sp - kSharedStack] = v;
-        ++sp;
-    };
-    auto pop = [&]() -> int {
-        --sp;
-        if (kSharedStack > 0 && sp < kSharedStack) return s_stack[sp][threadIdx.x];
-        return stack[sp - kSharedStack];
-    };
+    // the deep part of the traversal stack is a plain local array next to the walker, not a member of it: a struct with
+    // a dynamically indexed array stays in local memory as a whole, scalars and all (r02_s03: pair-node kernels 1.6x slower)
+    typename Walker::Entry stack[Walker::kLocal];
+    Walker wk;
+    wk.init();
     uint32_t idx = 0;
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
-    int pending = 0;
-    int qn = 0;                                            // CRT_QBALLOT: queued leaves, the same value in every lane
-    bool have = false, exhausted = false, zray = false;
+    int pending = 0;                                       // leaves of this lane's ray waiting in the queue
+    bool have = false, zray = false;
+    RayFetch rf;
+    rf.init(n);
     if (lane == 0) q.count = 0;
     __syncwarp();
     for (;;) {
-        // A. node steps; a leaf in hand goes to the queue and the lane takes the next entry of its stack
-#pragma unroll
-        for (int r = 0; r < kQueueSteps; ++r) {
-#if CRT_QBALLOT
-            {   // the queue belongs to this warp and every lane is here: positions from a ballot, no shared atomic
-                const bool leaf = cur < 0;
-                const unsigned lm = __ballot_sync(kFull, leaf);
-                if (leaf) {
-                    const int pos = qn + __popc(lm & lt_mask);
-                    q.q_slot[pos] = ~cur;
-                    q.q_lane[pos] = (unsigned char)lane;
-                    pending++;
-                    cur = sp ? pop() : kDone;
-                }
-                qn += __popc(lm);
-            }
-#else
-            if (cur < 0) {
-                const int pos = atomicAdd(&q.count, 1);
-                q.q_slot[pos] = ~cur;
-                q.q_lane[pos] = (unsigned char)lane;
-                pending++;
-                cur = sp ? pop() : kDone;
-            }
-#endif
-            if (cur >= 0 && cur != kDone) {
-                if (cur == kEmptyChild) {
-                    cur = sp ? pop() : kDone;
-                } else {
-                    float4 n0, n1, n2, n3;
-                    load_node(sc.nodes, cur, n0, n1, n2, n3);
-                    const float lim = tlimit * 1.0001f;
-                    float e0, e1;
-                    const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0, zray);
-                    const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1, zray);
-                    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-                    if (h0 && h1) {
-                        int nearc = c0, farc = c1;
-                        if (e1 < e0) { nearc = c1; farc = c0; }
-                        push(farc);
-                        cur = nearc;
-                    } else if (h0) cur = c0;
-                    else if (h1) cur = c1;
-                    else cur = sp ? pop() : kDone;
-                }
-            }
-        }
-        // B. flush the leaf queue when it is full enough, or when no lane has a node or leaf in hand
-        const unsigned walking = __ballot_sync(kFull, cur != kDone);
+        // A. node steps; leaves go to the queue
+        wk.steps(sc, q, stack, o, inv, tlimit * 1.0001f, zray, lane, lt_mask, pending);
+        // B. flush the leaf queue when it is full enough, or when no lane has a node in hand
+        const unsigned walking = __ballot_sync(kFull, wk.walking());
         __syncwarp();
-#if CRT_QBALLOT
-        const int q_count = qn;
-#else
-        const int q_count = q.count;
-#endif
-        if (q_count >= kQueueFlush || (walking == 0 && q_count > 0)) {
+        const int q_count = wk.queued(q);
+        if (q_count >= Walker::kFlush || (walking == 0 && q_count > 0)) {
             for (int base = 0; base < q_count; base += 32) {
                 const int k = base + lane;
-                unsigned long long mykey = kNoHit;
+                unsigned long long mykey = kNoHitKey;
                 int myslot = -1, owner = 0;
                 if (k < q_count) {
                     owner = q.q_lane[k];
@@ -575,26 +457,22 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
                 if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
                 __syncwarp();
             }
-#if CRT_QBALLOT
-            qn = 0;
-#else
-            if (lane == 0) q.count = 0;
-#endif
+            wk.reset_queue(q, lane);
             pending = 0;
             if (have) {
                 const unsigned long long b = q.best[lane];
                 if (MODE == 0) tlimit = __uint_as_float((uint32_t)(b >> 32));
-                else if (b != kNoHit) { cur = kDone; sp = 0; }      // blocked: nothing left to learn
+                else if (b != kNoHitKey) wk.stop();                  // blocked: nothing left to learn
             }
             __syncwarp();
         }
         // C. finished rays
-        if (have && cur == kDone && pending == 0) {
+        if (have && !wk.walking() && pending == 0) {
             const unsigned long long b = q.best[lane];
             HitRec h;
             h.t = __uint_as_float((uint32_t)(b >> 32));
-            h.face = b == kNoHit ? -1 : (int)(uint32_t)b;
-            h.slot = b == kNoHit ? -1 : q.best_slot[lane];
+            h.face = b == kNoHitKey ? -1 : (int)(uint32_t)b;
+            h.slot = b == kNoHitKey ? -1 : q.best_slot[lane];
             done(idx, h);
             have = false;
         }
@@ -602,48 +480,114 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
         const unsigned idle = __ballot_sync(kFull, !have);
         if (idle) {
             const int n_idle = __popc(idle);
-            if (!exhausted && (n_idle >= kRefillLanes || n_idle == 32)) {
-                const int leader = __ffs(idle) - 1;
-                uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(fetch, (uint32_t)n_idle);
-                base = __shfl_sync(kFull, base, leader);
-                const uint32_t my_i = base + __popc(idle & lt_mask);
-                if (!have) {
-                    const uint32_t i = my_i;
-                    if (i < n) {
-                        idx = i;
-                        V3 d;
-                        float tmax;
-                        const bool live = load(i, o, d, tmax);
-                        inv = box_inv3(d);
-                        zray = has_parallel_axis(inv);
-                        tlimit = MODE == 0 ? FLT_MAX : tmax;
-                        q.ox[lane] = o.x; q.oy[lane] = o.y; q.oz[lane] = o.z;
-                        q.dx[lane] = d.x; q.dy[lane] = d.y; q.dz[lane] = d.z;
-                        q.tmax[lane] = tmax;
-                        q.best[lane] = kNoHit;
-                        q.best_slot[lane] = -1;
-                        sp = 0;
-                        pending = 0;
-                        cur = (live && sc.n_nodes) ? 0 : kDone;
-                        have = true;
-                    }
+            if (!rf.drained() && (n_idle >= kRefillLanes || n_idle == 32)) {
+                uint32_t first = 0;
+                const uint32_t got = rf.take(fetch, n, lane, (uint32_t)n_idle, first, prefetch);
+                const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
+                if (!have && rank < got) {
+                    idx = first + rank;
+                    V3 d;
+                    float tmax;
+                    const bool live = load(idx, o, d, tmax);
+                    inv = box_inv3(d);
+                    zray = has_parallel_axis(inv);
+                    tlimit = MODE == 0 ? FLT_MAX : tmax;
+                    q.ox[lane] = o.x; q.oy[lane] = o.y; q.oz[lane] = o.z;
+                    q.dx[lane] = d.x; q.dy[lane] = d.y; q.dz[lane] = d.z;
+                    q.tmax[lane] = tmax;
+                    q.best[lane] = kNoHitKey;
+                    q.best_slot[lane] = -1;
+                    pending = 0;
+                    wk.start(live && sc.n_nodes, inv);
+                    have = true;
                 }
-                if (base + (uint32_t)n_idle >= n) exhausted = true;
                 __syncwarp();
             }
-            if (idle == kFull && !__any_sync(kFull, have)) {
-                if (exhausted) break;
-            }
+            if (idle == kFull && rf.drained() && !__any_sync(kFull, have)) break;
         }
     }
 }
 
-template <int MODE, int STRAT, typename Load, typename Done>
-CRT_DEV void trace_rays_persistent(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    if (STRAT == 2) trace_persistent_queue<MODE>(sc, n, fetch, load, done);
-    else trace_persistent<MODE, STRAT>(sc, n, fetch, load, done);
-}
+// ---- Walker for the 64-byte child-pair nodes: same visits in the same order as traverse<MODE>.
+#ifndef CRT_QFLUSH
+#define CRT_QFLUSH 16
+#endif
+#ifndef CRT_QSTEPS
+#define CRT_QSTEPS 6
+#endif
+// CRT_SSTACK = N > 0: the first N entries of every lane's traversal stack live in shared memory, laid out
+// [entry][thread] so that a push / pop is one conflict-free wavefront whatever the lanes' depths are; a
+// local-memory stack costs one L1 wavefront per distinct depth in the warp, and the pair-node kernels are
+// bound by L1 wavefronts (profiles/r01_s11.md). Deeper entries spill to the local array.
+#ifndef CRT_SSTACK
+#define CRT_SSTACK 8       // with 256-bit node loads and ballot queue slots: +7 % on cornell-box, +3 % on veach-mis (profiles/r01_s18.md)
+#endif
+static constexpr int kDone = 0x7ffffffe;               // no node in hand and the stack is empty
+struct PairWalker {
+    static constexpr int kFlush = CRT_QFLUSH;          // queued leaves that trigger a flush
+    static constexpr int kSteps = CRT_QSTEPS;          // node steps between two looks at the queue
+    static constexpr int kCap = kFlush + 32 * kSteps;
+    static constexpr int kShared = CRT_SSTACK;
+    static constexpr int kLocal = kStackSize - kShared;
+    typedef int Entry;
+    int sp, cur, qn;                                   // qn: queued leaves, the same value in every lane
+    CRT_DEV void init() { sp = 0; cur = kDone; qn = 0; }
+    CRT_DEV void start(bool live, V3) { sp = 0; cur = live ? 0 : kDone; }
+    CRT_DEV bool walking() const { return cur != kDone; }
+    CRT_DEV void stop() { cur = kDone; sp = 0; }
+    template <typename Q> CRT_DEV int queued(const Q&) const { return qn; }
+    template <typename Q> CRT_DEV void reset_queue(Q&, int) { qn = 0; }
+    template <typename Q>
+    CRT_DEV void steps(const SceneView& sc, Q& q, int* stack, V3 o, V3 inv, float lim, bool zray, int lane, unsigned lt_mask, int& pending) {
+        __shared__ int s_stack[kShared > 0 ? kShared : 1][128];
+        auto push = [&](int v) {
+            if (kShared > 0 && sp < kShared) s_stack[sp][threadIdx.x] = v;
+            else stack[sp - kShared] = v;
+            ++sp;
+        };
+        auto pop = [&]() -> int {
+            --sp;
+            if (kShared > 0 && sp < kShared) return s_stack[sp][threadIdx.x];
+            return stack[sp - kShared];
+        };
+#pragma unroll
+        for (int r = 0; r < kSteps; ++r) {
+            {   // a leaf in hand goes to the queue and the lane takes the next entry of its stack. The queue belongs to this
+                // warp and every lane is here: positions from a ballot, no shared atomic (+2 %, profiles/r01_s18.md)
+                const bool leaf = cur < 0;
+                const unsigned lm = __ballot_sync(0xffffffffu, leaf);
+                if (leaf) {
+                    const int pos = qn + __popc(lm & lt_mask);
+                    q.q_slot[pos] = ~cur;
+                    q.q_lane[pos] = (unsigned char)lane;
+                    pending++;
+                    cur = sp ? pop() : kDone;
+                }
+                qn += __popc(lm);
+            }
+            if (cur >= 0 && cur != kDone) {
+                if (cur == kEmptyChild) {                  // absent child of a one-leaf scene
+                    cur = sp ? pop() : kDone;
+                } else {
+                    float4 n0, n1, n2, n3;
+                    load_node(sc.nodes, cur, n0, n1, n2, n3);
+                    float e0, e1;
+                    const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, o, inv, lim, &e0, zray);
+                    const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, o, inv, lim, &e1, zray);
+                    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                    if (h0 && h1) {
+                        int nearc = c0, farc = c1;
+                        if (e1 < e0) { nearc = c1; farc = c0; }
+                        push(farc);
+                        cur = nearc;
+                    } else if (h0) cur = c0;
+                    else if (h1) cur = c1;
+                    else cur = sp ? pop() : kDone;
+                }
+            }
+        }
+    }
+};
 
 // ---- fixed-point accumulation (DESIGN.md "Accumulation"): radiance * 2^32 summed in int64, which
 // makes the image independent of atomic ordering, wavefront scheduling and GPU count.

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <string_view>
 #include <thread>
@@ -210,7 +211,7 @@ struct ObjChunk {
     std::string mtllib;
     bool has_mtllib = false;
     size_t lines = 0;
-    size_t bad_line = 0;   // line of the chunk of the first face that does not parse (0: none); the chunk stops there
+    size_t bad_line = 0;   // line of the chunk of the first face that does not parse (0: none)
 };
 
 void parse_obj_chunk(ObjChunk& ck) {
@@ -252,8 +253,10 @@ void parse_obj_chunk(ObjChunk& ck) {
                 if (r.ec != std::errc()) { bad = true; break; }
                 fr.v[nc++] = v;
             }
-            if (bad || nc < 3) { ck.bad_line = ck.lines; return; }
-            ck.faces.push_back(fr);
+            // the first malformed face is remembered; the rest of the chunk is still read, so that the vertex count of the
+            // file (which bounds positive indices) does not depend on where the chunks were cut
+            if (bad || nc < 3) { if (!ck.bad_line) ck.bad_line = ck.lines; }
+            else ck.faces.push_back(fr);
         } else if (key == "usemtl") {
             ck.marks.push_back(ShapeMark{std::string(c.token()), ck.faces.size()});
         } else if (key == "mtllib") {
@@ -277,11 +280,23 @@ unsigned ingest_threads(size_t bytes) {
 template <typename F>
 void parallel_for(unsigned n, F&& body) {                   // body(k) for k in [0, n), one thread each (n is small)
     if (n <= 1) { if (n == 1) body(0u); return; }
+    // an exception in a worker (std::bad_alloc from a chunk's vectors) is carried to the caller: it must not leave a
+    // std::thread (std::terminate), and the caller's C-ABI guard turns it into a status
+    std::vector<std::exception_ptr> err(n);
+    auto run = [&body, &err](unsigned k) {
+        try { body(k); } catch (...) { err[k] = std::current_exception(); }
+    };
     std::vector<std::thread> th;
     th.reserve(n - 1);
-    for (unsigned k = 1; k < n; ++k) th.emplace_back([&body, k] { body(k); });
-    body(0u);
+    unsigned started = 1;
+    try {
+        for (; started < n; ++started) th.emplace_back(run, started);
+    } catch (...) {                                          // thread creation failed: the rest runs here
+        for (unsigned k = started; k < n; ++k) run(k);
+    }
+    run(0u);
     for (auto& t : th) t.join();
+    for (unsigned k = 0; k < n; ++k) if (err[k]) std::rethrow_exception(err[k]);
 }
 }  // namespace
 
@@ -308,7 +323,31 @@ bool append_triangles(HostScene& s, const float* verts, const uint32_t* mat_id, 
     return true;
 }
 
+static int load_obj_body(HostScene& s, const char* obj_path, const char* mtl_dir);
+
+// The scene is left exactly as it was when the file is rejected (or an allocation fails): triangles, material slots,
+// object count and the light tables are rolled back.
 int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
+    const size_t t0 = s.n_tris(), m0 = s.mats.size();
+    const int o0 = s.n_objects;
+    auto rollback = [&] {
+        s.verts.resize(9 * t0); s.normal.resize(3 * t0); s.area.resize(t0); s.area_of_obj.resize(t0); s.mat.resize(t0); s.obj.resize(t0);
+        s.mats.resize(m0);
+        s.n_objects = o0;
+        finish_objects(s);
+    };
+    int rc;
+    try {
+        rc = load_obj_body(s, obj_path, mtl_dir);
+    } catch (...) {
+        rollback();
+        throw;
+    }
+    if (rc != CRT_OK) rollback();
+    return rc;
+}
+
+static int load_obj_body(HostScene& s, const char* obj_path, const char* mtl_dir) {
     MappedFile f;
     if (!f.open(obj_path)) { set_error(std::string("Unable to open OBJ file: ") + obj_path); return CRT_ERR_IO; }
     // 1. chunks on line boundaries, parsed independently
@@ -356,11 +395,14 @@ int load_obj(HostScene& s, const char* obj_path, const char* mtl_dir) {
         for (size_t fi = 0; fi < ck.faces.size(); ++fi) {
             const FaceRec& fr = ck.faces[fi];
             const long long nv = (long long)(nv0[k] + fr.nv_before);       // vertices read before this face
+            const long long nv_all = (long long)nv0[T];
             uint32_t corner[3];
             bool bad = false;
             for (int c = 0; c < 3; ++c) {
-                const long long zero_based = fr.v[c] > 0 ? fr.v[c] - 1 : nv + fr.v[c];       // OBJLoader.h:106
-                if (zero_based < 0 || zero_based >= nv) { bad = true; break; }
+                // OBJLoader.h:106 resolves the indices after the whole file is read: a positive index may refer to a
+                // vertex defined later in the file; a negative one counts back from the vertices read so far
+                const long long zero_based = fr.v[c] > 0 ? fr.v[c] - 1 : nv + fr.v[c];
+                if (zero_based < 0 || zero_based >= (fr.v[c] > 0 ? nv_all : nv)) { bad = true; break; }
                 corner[c] = (uint32_t)zero_based;
             }
             if (bad) { err_line[k] = line0[k] + fr.line; break; }

@@ -11,24 +11,11 @@
 #include "crt_gpu.h"
 #include "crt_wide.cuh"
 
-// Traversal scheduling: 2 = persistent lanes + per-warp leaf queue (default), 0 = while-while, 1 = if-if
-// (crt_device.cuh; measured alternatives in DESIGN.md "Traversal scheduling").
-#ifndef CRT_STRAT
-#define CRT_STRAT 2
-#endif
-// Same for the 8-wide nodes (crt_wide.cuh): 2 = leaf queue, 0 = while-while
-#ifndef CRT_WSTRAT
-#define CRT_WSTRAT 2
-#endif
-
 // 1: the queue counters every warp adds to sit in 128-byte lines of their own. With n_cur / n_next / n_shadow / fetch_* in
 // one 32-byte sector the compat shade stage took 24.7 - 34.1 ms for the same work depending on the box (1080p spp 128,
 // profiles/r01_s35.md); apart it takes 24.7 ms.
 #ifndef CRT_COUNTER_LINES
 #define CRT_COUNTER_LINES 1
-#endif
-#ifndef CRT_SHADOW_SCRATCH
-#define CRT_SHADOW_SCRATCH 1
 #endif
 // __launch_bounds__ min blocks/SM of the traversal kernels. 8 caps the wide-node kernels at 64 registers (no spills; the
 // compiler's own choice is 77-79 = 6 blocks): cornell-box +3 %, C5 (HBM-latency bound) 4793 -> 5394 Mrays/s (r01_s27).
@@ -137,10 +124,10 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device
 // =============================================================================================
 // node-layout dispatch: WIDE = false: 64-byte child-pair nodes, true: 80-byte 8-wide compressed nodes
 // =============================================================================================
-template <int MODE, bool WIDE, typename Load, typename Done>
-CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    if (WIDE) trace_rays_persistent_wide<MODE, CRT_WSTRAT>(sc, n, fetch, load, done);
-    else trace_rays_persistent<MODE, CRT_STRAT>(sc, n, fetch, load, done);
+template <int MODE, bool WIDE, typename Load, typename Done, typename Prefetch>
+CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Prefetch prefetch) {
+    if (WIDE) trace_persistent_queue<MODE, WideWalker>(sc, n, fetch, load, done, prefetch);
+    else trace_persistent_queue<MODE, PairWalker>(sc, n, fetch, load, done, prefetch);
 }
 template <int MODE, bool WIDE>
 CRT_DEV HitRec trace_one(const SceneView& sc, V3 o, V3 d, float tmax) {
@@ -165,7 +152,8 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_trace_batch(SceneView sc, con
         [&](uint32_t i, const HitRec& h) {
             if (t_out) t_out[i] = h.t;
             if (face_out) face_out[i] = h.face;
-        });
+        },
+        [&](uint32_t first, uint32_t count) { prefetch_l2(rays, first, count, 32u, threadIdx.x & 31); });
 }
 
 static int g_num_sms = 0;
@@ -281,6 +269,12 @@ struct RenderParamsDev {
     uint32_t width, height;
     unsigned long long n_pixels;
     uint32_t s_begin;
+    // Order in which the work items of this run_view are started (any order gives the same buffer). tile_px > 0: the
+    // range is whole samples [tile_s0, tile_s0 + tile_S) and is walked tile by tile - all its samples of pixels
+    // [0, tile_px), then of the next tile_px pixels ... - so that the part of the accumulation buffer the paths in flight
+    // add to (24 B per pixel) stays L2-resident on frames whose whole buffer is not (4K: 199 MB against 126 MB of L2).
+    uint32_t tile_px, tile_s0, tile_S;
+    unsigned long long w_begin;
     float p_rr;
     int light_sample_n;
     uint32_t seed;
@@ -357,8 +351,19 @@ __global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c
         unsigned long long w = w0 + k;
         // (an 8x4-tile order of the pixels inside a sample, alone or in blocks of 4-16 tiles, changes nothing measurable:
         //  profiles/r01_s21.md - the camera rays are a third of the extend rays and the cheapest ones)
-        uint32_t pixel = (uint32_t)(w % p.n_pixels);
-        uint32_t sample = p.s_begin + (uint32_t)(w / p.n_pixels);
+        uint32_t pixel, sample;
+        if (p.tile_px) {
+            const unsigned long long j = w - p.w_begin, per_tile = (unsigned long long)p.tile_px * p.tile_S;
+            const uint32_t t = (uint32_t)(j / per_tile);
+            const unsigned long long jj = j - (unsigned long long)t * per_tile;
+            const uint32_t first = t * p.tile_px;
+            const uint32_t px = (uint32_t)min((unsigned long long)p.tile_px, p.n_pixels - first);
+            sample = p.tile_s0 + (uint32_t)(jj / px);
+            pixel = first + (uint32_t)(jj % px);
+        } else {
+            pixel = (uint32_t)(w % p.n_pixels);
+            sample = p.s_begin + (uint32_t)(w / p.n_pixels);
+        }
         uint32_t i = pixel % p.width, j = pixel / p.width;
         uint4 r = draw(pixel, sample, kCameraBounce, 0, p.seed);
         float u1 = u01(r.x), u2 = u01(r.y);
@@ -382,7 +387,11 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_extend(SceneView sc, Counters
     trace_queue<0, WIDE>(
         sc, c->n_cur, &c->fetch_extend,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
-        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });
+        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; },
+        [&](uint32_t first, uint32_t count) {
+            prefetch_l2(q_o, first, count, 16u, threadIdx.x & 31);
+            prefetch_l2(q_d, first, count, 16u, threadIdx.x & 31);
+        });
 }
 
 // SPECULAR probe rays (reference Render.cuh:303): traced only when the continuation ray hit.
@@ -399,7 +408,8 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_probe(SceneView sc, Counters*
             o = mk3(pr_o[i]); d = mk3(pr_d[i]); tmax = FLT_MAX; traced++;
             return true;
         },
-        [&](uint32_t k, const HitRec& h) { pr_hit[list[k]] = h.slot; });
+        [&](uint32_t k, const HitRec& h) { pr_hit[list[k]] = h.slot; },
+        [&](uint32_t first, uint32_t count) { prefetch_l2(list, first, count, 4u, threadIdx.x & 31); });
     const int lane = threadIdx.x & 31;
     for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
     if (lane == 0 && traced) atomicAdd(&c->stat_probe, traced);
@@ -791,7 +801,6 @@ template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
                                                 const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
                                                 long long* __restrict__ accum, int par) {
-#if CRT_SHADOW_SCRATCH
     // the contribution and pixel of the ray a lane owns wait in shared memory (loaded with the ray, one DRAM round trip
     // instead of a second one when the ray finishes: 3.7 % of this kernel's stall samples, profiles/r01_s20.md)
     __shared__ float4 s_contrib[128];
@@ -805,15 +814,12 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters
         },
         [&](uint32_t i, const HitRec& h) {
             if (h.slot < 0) { const float4 cc = s_contrib[threadIdx.x]; accum_add(accum, __float_as_uint(cc.w), mk3(cc)); }
+        },
+        [&](uint32_t first, uint32_t count) {
+            prefetch_l2(sh_o, first, count, 16u, threadIdx.x & 31);
+            prefetch_l2(sh_d, first, count, 16u, threadIdx.x & 31);
+            prefetch_l2(sh_c, first, count, 16u, threadIdx.x & 31);
         });
-#else
-    trace_queue<1, WIDE>(
-        sc, c->n_shadow[par], &c->fetch_shadow[par],
-        [&](uint32_t i, V3& o, V3& d, float& tmax) { const float4 a = sh_o[i]; o = mk3(a); tmax = a.w; d = mk3(sh_d[i]); return true; },
-        [&](uint32_t i, const HitRec& h) {
-            if (h.slot < 0) accum_add(accum, __float_as_uint(sh_d[i].w), mk3(sh_c[i]));
-        });
-#endif
 }
 
 // E11 (reference Render.cuh:348,350): mean over spp, clamp, pow 0.6, *255, truncate.
@@ -958,6 +964,16 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     p.width = w->width; p.height = w->height; p.n_pixels = npix;
     p.s_begin = 0; p.p_rr = rs.p_rr; p.light_sample_n = (int)rs.light_sample_n; p.seed = rs.seed;
     p.max_vertices = 64;                                           // BOUNCE_STACK_SIZE, Global.h:18
+    p.w_begin = w_begin;
+    p.tile_px = p.tile_s0 = p.tile_S = 0;
+    {
+        const uint32_t tile_px = env_u32("CRT_TILE_PX", 1u << 21);    // 48 MB of accumulation buffer per tile
+        if (tile_px && npix > tile_px && w_end > w_begin && w_begin % npix == 0 && w_end % npix == 0) {
+            p.tile_px = tile_px;
+            p.tile_s0 = (uint32_t)(w_begin / npix);
+            p.tile_S = (uint32_t)((w_end - w_begin) / npix);
+        }
+    }
     Counters h;
     memset(&h, 0, sizeof(h));
     h.work_next = w_begin;

@@ -67,6 +67,48 @@ void* ref_host_load(const char* obj_path, const char* mtl_dir, unsigned width, u
     st->ms_parse = t1 - t0; st->ms_load = t2 - t1; st->ms_bvh = t4 - t3;
     return st;
 }
+// C4 / C5 (synthetic scenes that exist only as arrays): the triangles go through the reference's public classes the
+// way Loader::load_object (Loader.h:107-120) and main.cu:131-144 feed them - Material, Triangle, one Object per
+// (contiguous) obj id, add_light_obj when the material emits - and then through Scene::set_BVH, which is timed.
+// verts n*9, mat / obj per triangle, mats7 rows of kd(3) ke(3) ns. No OBJ text is involved (ms_parse = 0).
+void* ref_host_from_arrays(const float* verts, const int* mat, const int* obj, long long n, const float* mats7, int n_mats,
+                           unsigned width, unsigned height) {
+    RefState* st = new RefState();
+    st->width = width; st->height = height;
+    st->scene = new Scene(width, height);
+    double t0 = now_ms();
+    std::vector<Triangle> group;
+    auto flush = [&](bool emits) {
+        if (group.empty()) return;
+        Object o(group);
+        if (emits) st->scene->add_light_obj(o); else st->scene->add_normal_obj(o);
+        group.clear();
+    };
+    bool cur_emits = false;
+    for (long long i = 0; i < n; ++i) {
+        const float* m7 = mats7 + 7 * (size_t)mat[i];
+        Eigen::Vector3f kd(m7[0], m7[1], m7[2]), ke(m7[3], m7[4], m7[5]), zero(0, 0, 0);
+        Material m(kd, zero, zero, ke, m7[6], m7[6] > 1 ? SPECULAR : DIFFUSE);
+        if (i > 0 && (obj[i] != obj[i - 1] || m.has_emission() != cur_emits)) flush(cur_emits);
+        cur_emits = m.has_emission();
+        const float* v = verts + 9 * (size_t)i;
+        group.push_back(Triangle(Eigen::Vector3f(v[0], v[1], v[2]), Eigen::Vector3f(v[3], v[4], v[5]), Eigen::Vector3f(v[6], v[7], v[8]),
+                                 Eigen::Vector3f(0, 1, 0), m));
+    }
+    flush(cur_emits);
+    (void)n_mats;
+    st->ms_load = now_ms() - t0;
+    return st;
+}
+// Scene::set_BVH (Scene.h:50-54 -> BVH.h:30-84) on a state made by ref_host_from_arrays; returns the wall-clock ms.
+double ref_build_bvh(void* h, unsigned thresh_n) {
+    RefState* st = (RefState*)h;
+    double t0 = now_ms();
+    st->scene->set_BVH(thresh_n);
+    st->ms_bvh = now_ms() - t0;
+    return st->ms_bvh;
+}
+
 void ref_host_times(void* h, double* ms3) { RefState* st = (RefState*)h; ms3[0] = st->ms_parse; ms3[1] = st->ms_load; ms3[2] = st->ms_bvh; }
 int ref_n_tris(void* h) { return (int)((RefState*)h)->scene->get_triangles().size(); }
 int ref_n_nodes(void* h) { return (int)((RefState*)h)->scene->get_bvh().get_nodes_size(); }

@@ -248,7 +248,7 @@ def test_map_kd_errors(crt, tmp_path):
         crt.Scene().add_obj(os.path.join(str(tmp_path), "few.obj"), str(tmp_path))
 
 
-def _big_obj(path, n_quads=12000, bad_at=None, forward_ref_at=None, reference_forms_only=False):
+def _big_obj(path, n_quads=12000, bad_at=None, forward_ref_at=None, reference_forms_only=False, out_of_range_at=None):
     """An OBJ large enough to be read in several chunks: relative and absolute indices, faces before the first usemtl,
     several usemtl, two mtllib lines (the last one wins), v/vt/vn forms. Returns the number of lines."""
     rng = np.random.default_rng(11)
@@ -271,6 +271,8 @@ def _big_obj(path, n_quads=12000, bad_at=None, forward_ref_at=None, reference_fo
             lines.append("f 1 2 x")
         if forward_ref_at is not None and q == forward_ref_at:
             lines.append("f 1 2 %d" % (3 + 4 * (q + 1) + 1))                # a vertex that is defined only later
+        if out_of_range_at is not None and q == out_of_range_at:
+            lines.append("f 1 2 %d" % (3 + 4 * n_quads + 1))               # one past the last vertex of the file
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
     return lines
@@ -304,9 +306,9 @@ def test_chunked_ingest_is_independent_of_the_thread_count(crt, orc, tmp_path, m
 def test_chunked_ingest_reports_the_first_error_with_its_line(crt, tmp_path, monkeypatch):
     (tmp_path / "big.mtl").write_text("newmtl m0\nKd .5 .5 .5\n")
     (tmp_path / "wrong.mtl").write_text("newmtl m0\nKd 1 0 0\n")
-    for kind in ("bad", "forward"):
+    for kind in ("bad", "range"):
         obj = str(tmp_path / ("err_%s.obj" % kind))
-        lines = _big_obj(obj, bad_at=9000 if kind == "bad" else 11000, forward_ref_at=7000 if kind == "forward" else 10000)
+        lines = _big_obj(obj, bad_at=9000 if kind == "bad" else 11000, out_of_range_at=7000 if kind == "range" else 10000)
         first = min(i for i, ln in enumerate(lines) if ln == "f 1 2 x" or (ln.startswith("f 1 2 ") and ln != "f 1 2 3")) + 1
         msgs = set()
         for th in ("1", "3", "8"):
@@ -315,6 +317,64 @@ def test_chunked_ingest_reports_the_first_error_with_its_line(crt, tmp_path, mon
                 crt.Scene().add_obj(obj, str(tmp_path))
             msgs.add(str(e.value))
         assert len(msgs) == 1 and (":%d: malformed face" % first) in msgs.pop()
+
+
+def test_forward_references_are_accepted_like_the_reference(crt, orc, tmp_path, monkeypatch):
+    """OBJLoader.h:106 resolves positive indices after the whole file is read: a face may name a vertex that is defined
+    later (in another chunk, too); negative indices count back from the vertices read so far."""
+    (tmp_path / "big.mtl").write_text("newmtl m0\nKd .5 .5 .5\nnewmtl m1\nKd .1 .2 .3\nKe 5 5 5\nnewmtl m2\nKd .3 .2 .1\nNs 40\n")
+    (tmp_path / "wrong.mtl").write_text("newmtl m0\nKd 1 0 0\n")
+    obj = str(tmp_path / "fwd.obj")
+    _big_obj(obj, forward_ref_at=7000, reference_forms_only=True)     # the forms the reference's stoull-based reader takes
+    O = orc.Scene().add_obj(obj, str(tmp_path))
+    for th in ("1", "5"):
+        monkeypatch.setenv("CRT_INGEST_THREADS", th)
+        S = crt.Scene().add_obj(obj, str(tmp_path))
+        assert S.counts()["n_tris"] == O.n_tris == 2 * 12000 + 1
+        assert np.array_equal(S.tris()["verts"].view(np.uint32), O.tris()["verts"].view(np.uint32))
+
+
+def test_failed_calls_leave_the_scene_unchanged(crt, tmp_path):
+    """A rejected OBJ or triangle batch rolls back triangles, material slots, objects and lights; ids are validated."""
+    (tmp_path / "m.mtl").write_text("newmtl a\nKd 1 1 1\nnewmtl glow\nKe 3 3 3\n")
+    (tmp_path / "ok.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nusemtl a\nf 1 2 3\nusemtl glow\nf 3 2 1\n")
+    (tmp_path / "nan.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 nan 0\nusemtl glow\nf 1 2 3\nusemtl a\nf 3 2 1\n")
+    S = crt.Scene().add_obj(str(tmp_path / "ok.obj"), str(tmp_path))
+    before = (S.counts(), S.tris()["verts"].tobytes(), S.mats().tobytes(), [(f.tolist(), a) for f, a in S.lights()])
+    with pytest.raises(crt.CrtError):
+        S.add_obj(str(tmp_path / "nan.obj"), str(tmp_path))
+    tri = [[0, 0, 0, 1, 0, 0, 0, 1, 0]]
+    mat = [[.5, .5, .5, 0, 0, 0, 1]]
+    for bad in (dict(verts=[[0, 0, 0, 1, 0, 0, 0, float("inf"), 0]], mat_id=[0], obj_id=[0]),
+                dict(verts=tri, mat_id=[0], obj_id=[1]),                      # ids number this call's groups: < n_tris
+                dict(verts=tri, mat_id=[0], obj_id=[0xFFFFFFFF]),
+                dict(verts=tri, mat_id=[1], obj_id=[0])):
+        with pytest.raises(crt.CrtError):
+            S.add_triangles(bad["verts"], bad["mat_id"], bad["obj_id"], mat)
+    with pytest.raises(ValueError):
+        S.add_triangles(tri + tri, [0], [0, 0], mat)                          # array lengths are checked by the binding
+    after = (S.counts(), S.tris()["verts"].tobytes(), S.mats().tobytes(), [(f.tolist(), a) for f, a in S.lights()])
+    assert before == after
+    S.add_triangles(tri, [0], [0], mat)
+    assert S.counts()["n_tris"] == 3 and S.counts()["n_mats"] == 3
+
+
+def test_hostile_inputs_are_errors_not_aborts(crt, tmp_path):
+    """A PNG header that promises 2^48 pixels behind a few bytes of IDAT and a config nested 10^5 deep come back as
+    CrtError (no exception crosses the C ABI, nothing of the promised size is allocated)."""
+    def chunk(typ, data):
+        return struct.pack(">I", len(data)) + typ + data + struct.pack(">I", zlib.crc32(typ + data) & 0xffffffff)
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 1 << 24, 1 << 24, 8, 2, 0, 0, 0)) + \
+        chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    (tmp_path / "t.mtl").write_text("newmtl t\nKd 1 1 1\nmap_Kd bomb.png\n")
+    (tmp_path / "bomb.png").write_bytes(png)
+    (tmp_path / "t.obj").write_text("mtllib t.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nusemtl t\nf 1/1 2/2 3/3\n")
+    with pytest.raises(crt.CrtError):
+        crt.Scene().add_obj(str(tmp_path / "t.obj"), str(tmp_path))
+    (tmp_path / "deep.json").write_text("[" * 100000 + "]" * 100000)
+    with pytest.raises(crt.CrtError) as e:
+        crt.load_config(str(tmp_path / "deep.json"))
+    assert "nesting too deep" in str(e.value)
 
 
 def test_png_writer_bands_do_not_depend_on_the_thread_count(crt, tmp_path, monkeypatch):

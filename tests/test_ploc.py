@@ -246,3 +246,30 @@ def test_gpu_ploc_synthetic_heightfield(gpu, orc):
     b = orc.Scene().add_arrays(v, m.astype(np.int32), o.astype(np.int32), mats)
     for builder in (PLOC, PLOC8):
         _same_build(gpu, a if builder == PLOC else gpu.Scene().add_triangles(v, m, o, mats), b, 2, builder)
+
+
+@pytest.mark.gpu
+def test_gpu_ploc_chain_is_refused_not_overflowed(gpu, orc):
+    """Boxes that grow geometrically merge one pair per round: a chain as deep as the triangle count. The pair-node
+    traversal stack is kStackSize = 96 entries without a bounds check, so builder PLOC refuses such a tree with a
+    message (it used to overflow the stack); PLOC8 collapses the chain into shallow wide levels and traces it."""
+    n = 200
+    x = (1.5 ** np.arange(n)).astype(np.float32)
+    v = np.zeros((n, 9), np.float32)
+    v[:, 0] = x; v[:, 3] = x * 1.01; v[:, 6] = x; v[:, 7] = x * 0.01 + 1e-3
+    a = gpu.Scene().add_triangles(v, np.zeros(n, np.uint32), np.zeros(n, np.uint32), MAT)
+    with pytest.raises(gpu.CrtError) as e:
+        a.set_BVH(1, builder=PLOC)
+    assert "more rounds than the traversal stack" in str(e.value)
+    a = gpu.Scene().add_triangles(v, np.zeros(n, np.uint32), np.zeros(n, np.uint32), MAT)
+    b = _scene(orc, v)
+    _same_build(gpu, a, b, 1, PLOC8)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0] = x * 1.002; rays[:, 1] = (x * 0.01 + 1e-3) * 0.25; rays[:, 2] = -1.0; rays[:, 3] = 3e38; rays[:, 6] = 1.0
+    t, f, _ = a.trace_rays(rays, gpu.RAY_CLOSEST)
+    ot, of = b.trace(rays, which=3)                            # brute force
+    assert np.array_equal(f, of) and np.array_equal(t.view(np.uint32), ot.view(np.uint32)) and (f >= 0).sum() > n // 2
+    a = gpu.Scene().add_triangles(v, np.zeros(n, np.uint32), np.zeros(n, np.uint32), MAT)
+    a.set_BVH(1, builder=0)                                   # the Karras tree of the same scene is shallow enough
+    t2, f2, _ = a.trace_rays(rays, gpu.RAY_CLOSEST)
+    assert np.array_equal(f2, of)
