@@ -116,6 +116,14 @@ def load_library():
         "crt_render_save_png": [vp, C.c_char_p],
         "crt_render_get_stats": [vp, C.POINTER(_Stats)],
         "crt_render_destroy": [vp],
+        "crt_group_create": [vp, u32, u32, vp, u32, pp],
+        "crt_group_set_params": [vp, u32, f32, u32, u32, i32],
+        "crt_group_run_view": [vp, vp, vp, f32],
+        "crt_group_get_accum_i64": [vp, vp],
+        "crt_group_get_rgb8": [vp, vp],
+        "crt_group_save_png": [vp, C.c_char_p],
+        "crt_group_get_stats": [vp, u32, C.POINTER(_Stats), C.POINTER(f32)],
+        "crt_group_destroy": [vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -272,12 +280,18 @@ class Scene:
         _check(fn(self.h, _p(nodes), _p(order), _p(last), _p(bounds)))
         return nodes, order, last, bounds
 
-    def trace_rays(self, rays, mode=RAY_CLOSEST):
-        """rays: n x 8 float32 {o, tmax, d, 0}. Returns (t, face, kernel_ms)."""
+    def trace_rays(self, rays, mode=RAY_CLOSEST, out=None):
+        """rays: n x 8 float32 {o, tmax, d, 0}. Returns (t, face, kernel_ms). out = (t, face): caller-owned result arrays
+        (float32 / int32, n each), e.g. page-locked ones, which the library then fills by DMA without staging."""
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         n = rays.shape[0]
-        t = np.zeros(n, np.float32)
-        face = np.zeros(n, np.int32)
+        if out is not None:
+            t, face = out
+            if t.dtype != np.float32 or face.dtype != np.int32 or t.size < n or face.size < n or not (t.flags.c_contiguous and face.flags.c_contiguous):
+                raise ValueError("trace_rays: out must be contiguous (float32[n], int32[n])")
+        else:
+            t = np.zeros(n, np.float32)
+            face = np.zeros(n, np.int32)
         ms = C.c_float()
         _check(self.L.crt_trace_rays(self.h, _p(rays), n, mode, _p(t), _p(face), C.byref(ms)))
         return t, face, ms.value
@@ -396,3 +410,59 @@ class Render:
         s = _Stats()
         _check(self.L.crt_render_get_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+
+class RenderGroup:
+    """Render for several GPUs of one box driven by the calling thread (crt_group, include/crt.h): the built scene is copied
+    device to device, GPU g renders its share of the samples, one NCCL reduce sums the int64 buffers onto devices[0].
+    The reduced buffer and the frame are bit-identical to the single-GPU Render's."""
+
+    def __init__(self, scene, width, height, devices, spp=16, P_RR=0.8, light_sample_n=1, seed=0, estimator=ESTIMATOR_COMPAT):
+        self.L = load_library()
+        self.scene = scene
+        self.width, self.height = int(width), int(height)
+        self.devices = [int(d) for d in devices]
+        self.h = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _check(self.L.crt_group_create(scene.h, self.width, self.height, C.cast(arr, C.c_void_p), len(self.devices), C.byref(self.h)))
+        self.set_params(spp, P_RR, light_sample_n, seed, estimator)
+
+    def set_params(self, spp, P_RR, light_sample_n, seed=0, estimator=ESTIMATOR_COMPAT):
+        self.spp = int(spp)
+        _check(self.L.crt_group_set_params(self.h, int(spp), float(P_RR), int(light_sample_n), int(seed), int(estimator)))
+
+    def run_view(self, eye_pos, inv_view_mat, fovY):
+        eye = np.ascontiguousarray(eye_pos, np.float32)
+        M = np.ascontiguousarray(inv_view_mat, np.float32).reshape(9)
+        _check(self.L.crt_group_run_view(self.h, _p(eye), _p(M), float(fovY)))
+
+    def get_accum_i64(self):
+        out = np.zeros(self.width * self.height * 3, np.int64)
+        _check(self.L.crt_group_get_accum_i64(self.h, _p(out)))
+        return out
+
+    def get_frame_buffer(self):
+        out = np.zeros((self.height, self.width, 3), np.uint8)
+        _check(self.L.crt_group_get_rgb8(self.h, _p(out)))
+        return out
+
+    def save_frame_buffer(self, path):
+        _check(self.L.crt_group_save_png(self.h, os.fsencode(path)))
+
+    def stats(self, index=0):
+        st, ms = _Stats(), C.c_float()
+        _check(self.L.crt_group_get_stats(self.h, int(index), C.byref(st), C.byref(ms)))
+        d = {k: getattr(st, k) for k, _ in _Stats._fields_}
+        d["reduce_ms"] = ms.value
+        return d
+
+    def close(self):
+        if self.h:
+            self.L.crt_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -13,6 +13,7 @@ using namespace crt;
 struct crt_scene {
     HostScene host;
     DeviceScene dev;
+    RayBatcher* batcher = nullptr;
     bool built = false;
     uint32_t thresh_n = 0;
 };
@@ -289,13 +290,20 @@ int crt_scene_bvh_kind(crt_scene* s, int* builder) {
 int crt_scene_destroy(crt_scene* s) {
     return guarded("crt_scene_destroy", [&]() -> int {
     if (!s) return CRT_OK;
-    if (s->built) { cudaSetDevice(s->dev.device); s->dev.release(); }
+    if (s->built) { cudaSetDevice(s->dev.device); ray_batcher_destroy(s->batcher); s->dev.release(); }
     delete s;
     return CRT_OK;
     });
 }
 
 // ---- ray batches ---------------------------------------------------------------------------
+static int scene_batcher(crt_scene* s) {
+    if (s->batcher) return CRT_OK;
+    int rc = ray_batcher_create(s->dev, &s->batcher);
+    if (rc != CRT_OK) { ray_batcher_destroy(s->batcher); s->batcher = nullptr; }
+    return rc;
+}
+
 int crt_trace_rays_device(crt_scene* s, const void* d_rays, uint64_t n, int mode, void* d_t_out, void* d_face_out, void* stream,
                           float* kernel_ms) {
     return guarded("crt_trace_rays_device", [&]() -> int {
@@ -304,33 +312,22 @@ int crt_trace_rays_device(crt_scene* s, const void* d_rays, uint64_t n, int mode
     if (!s->built) { set_error("crt_trace_rays: BVH not built"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(s->dev.device));
     if (n == 0) { if (kernel_ms) *kernel_ms = 0; return CRT_OK; }
-    return trace_rays_device(s->dev, (const float4*)d_rays, n, mode, (float*)d_t_out, (int*)d_face_out, (cudaStream_t)stream, kernel_ms);
+    int rc = scene_batcher(s);
+    if (rc != CRT_OK) return rc;
+    return trace_rays_device(s->batcher, s->dev, (const float4*)d_rays, n, mode, (float*)d_t_out, (int*)d_face_out, (cudaStream_t)stream, kernel_ms);
     });
 }
 
 int crt_trace_rays(crt_scene* s, const float* rays, uint64_t n, int mode, float* t_out, int32_t* face_out, float* kernel_ms) {
     return guarded("crt_trace_rays", [&]() -> int {
     CHECK_ARG(s && (n == 0 || rays), "crt_trace_rays: null argument");
+    CHECK_ARG(mode == CRT_RAY_CLOSEST || mode == CRT_RAY_ANY, "crt_trace_rays: unknown mode");
     if (!s->built) { set_error("crt_trace_rays: BVH not built"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(s->dev.device));
     if (n == 0) { if (kernel_ms) *kernel_ms = 0; return CRT_OK; }
-    float4* d_rays = nullptr;
-    float* d_t = nullptr;
-    int* d_face = nullptr;
-    CRT_CUDA(cudaMalloc(&d_rays, sizeof(float) * 8 * n));
-    cudaError_t e1 = cudaMalloc(&d_t, sizeof(float) * n), e2 = cudaMalloc(&d_face, sizeof(int) * n);
-    int rc = CRT_OK;
-    if (e1 != cudaSuccess || e2 != cudaSuccess) rc = cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaMalloc ray outputs");
-    if (rc == CRT_OK) {
-        cudaMemcpy(d_rays, rays, sizeof(float) * 8 * n, cudaMemcpyHostToDevice);
-        rc = crt_trace_rays_device(s, d_rays, n, mode, d_t, d_face, nullptr, kernel_ms);
-    }
-    if (rc == CRT_OK) {
-        if (t_out) cudaMemcpy(t_out, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost);
-        if (face_out) cudaMemcpy(face_out, d_face, sizeof(int) * n, cudaMemcpyDeviceToHost);
-    }
-    cudaFree(d_rays); cudaFree(d_t); cudaFree(d_face);
-    return rc;
+    int rc = scene_batcher(s);
+    if (rc != CRT_OK) return rc;
+    return trace_rays_host(s->batcher, s->dev, rays, n, mode, t_out, face_out, kernel_ms);
     });
 }
 
@@ -614,6 +611,242 @@ int crt_render_destroy(crt_render* r) {
     delete r;
     return CRT_OK;
     });
+}
+
+// ---- group: N GPUs, one host thread --------------------------------------------------------------
+}  // extern "C"
+
+#include <dlfcn.h>
+#include <nccl.h>       // types and enums only: the library is loaded with dlopen when a group of more than one GPU is created
+#include <chrono>
+#include <thread>
+
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl() {
+    if (g_nccl.lib) return CRT_OK;
+    const char* name = getenv("CRT_NCCL_LIB");
+    void* h = dlopen(name && *name ? name : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { set_error(std::string("crt_group: cannot load NCCL: ") + dlerror()); return CRT_ERR_STATE; }
+    NcclApi a;
+    a.lib = h;
+    a.CommInitAll = (decltype(a.CommInitAll))dlsym(h, "ncclCommInitAll");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+    a.Reduce = (decltype(a.Reduce))dlsym(h, "ncclReduce");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!a.CommInitAll || !a.CommDestroy || !a.Reduce || !a.GroupStart || !a.GroupEnd || !a.GetErrorString) {
+        set_error("crt_group: the NCCL library lacks a symbol");
+        return CRT_ERR_STATE;
+    }
+    g_nccl = a;
+    return CRT_OK;
+}
+int nccl_fail(ncclResult_t r, const char* what) {
+    set_error(std::string("NCCL error: ") + g_nccl.GetErrorString(r) + " in " + what);
+    return CRT_ERR_CUDA;
+}
+#define CRT_NCCL(x)                                              \
+    do {                                                         \
+        ncclResult_t r__ = (x);                                  \
+        if (r__ != ncclSuccess) return nccl_fail(r__, #x);       \
+    } while (0)
+}  // namespace
+
+struct crt_group {
+    crt_scene* scene = nullptr;
+    uint32_t width = 0, height = 0;
+    std::vector<int> devices;
+    std::vector<DeviceScene> replicas;          // [0] unused: GPU 0 renders the scene handle's own tables
+    std::vector<Wavefront*> wf;
+    std::vector<cudaStream_t> streams;
+    std::vector<ncclComm_t> comms;
+    std::vector<crt_render_stats> stats;
+    RenderSettings rs;
+    cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;
+    float reduce_ms = 0;
+    float* d_linear = nullptr;
+    uint8_t* d_rgb8 = nullptr;
+    bool rendered = false;
+    const DeviceScene& scene_of(size_t g) const { return g == 0 ? scene->dev : replicas[g]; }
+};
+
+extern "C" {
+
+int crt_group_destroy(crt_group* g) {
+    if (!g) return CRT_OK;
+    for (size_t k = 0; k < g->devices.size(); ++k) {
+        cudaSetDevice(g->devices[k]);
+        if (k < g->wf.size()) wavefront_destroy(g->wf[k]);
+        if (k < g->streams.size() && g->streams[k]) cudaStreamDestroy(g->streams[k]);
+        if (k < g->comms.size() && g->comms[k]) g_nccl.CommDestroy(g->comms[k]);
+        if (k > 0 && k < g->replicas.size()) g->replicas[k].release();
+    }
+    if (!g->devices.empty()) cudaSetDevice(g->devices[0]);
+    if (g->ev_r0) cudaEventDestroy(g->ev_r0);
+    if (g->ev_r1) cudaEventDestroy(g->ev_r1);
+    cudaFree(g->d_linear);
+    cudaFree(g->d_rgb8);
+    delete g;
+    return CRT_OK;
+}
+
+int crt_group_create(crt_scene* s, uint32_t width, uint32_t height, const int* devices, uint32_t n_devices, crt_group** out) {
+    return guarded("crt_group_create", [&]() -> int {
+    CHECK_ARG(s && out && devices && n_devices > 0 && n_devices <= 64, "crt_group_create: invalid argument");
+    CHECK_ARG(width > 0 && height > 0 && (uint64_t)width * height <= (1ull << 28), "crt_group_create: bad image size");
+    if (!s->built) { set_error("crt_group_create: build the BVH first (crt_scene_build_bvh)"); return CRT_ERR_STATE; }
+    const int n_dev = crt_device_count();
+    for (uint32_t k = 0; k < n_devices; ++k) {
+        CHECK_ARG(devices[k] >= 0 && devices[k] < n_dev, "crt_group_create: device out of range");
+        for (uint32_t j = 0; j < k; ++j) CHECK_ARG(devices[j] != devices[k], "crt_group_create: a device is listed twice");
+    }
+    CHECK_ARG(devices[0] == s->dev.device, "crt_group_create: the scene must be built on devices[0]");
+    if (n_devices > 1) { int rc = load_nccl(); if (rc != CRT_OK) return rc; }
+    crt_group* g = new crt_group();
+    g->scene = s; g->width = width; g->height = height;
+    g->devices.assign(devices, devices + n_devices);
+    g->replicas.resize(n_devices);
+    g->wf.assign(n_devices, nullptr);
+    g->streams.assign(n_devices, nullptr);
+    g->comms.assign(n_devices, nullptr);
+    g->stats.resize(n_devices);
+    g->rs.width = width; g->rs.height = height;
+    auto build = [&]() -> int {
+        for (uint32_t k = 0; k < n_devices; ++k) {
+            if (k > 0) { int rc = clone_scene(s->dev, devices[k], g->replicas[k]); if (rc != CRT_OK) return rc; }
+            CRT_CUDA(cudaSetDevice(devices[k]));
+            int rc = wavefront_create(g->scene_of(k), width, height, &g->wf[k]);
+            if (rc != CRT_OK) return rc;
+            CRT_CUDA(cudaStreamCreateWithFlags(&g->streams[k], cudaStreamNonBlocking));
+        }
+        CRT_CUDA(cudaSetDevice(devices[0]));
+        CRT_CUDA(cudaMalloc(&g->d_linear, sizeof(float) * 3 * (size_t)width * height));
+        CRT_CUDA(cudaMalloc(&g->d_rgb8, 3 * (size_t)width * height));
+        CRT_CUDA(cudaEventCreate(&g->ev_r0));
+        CRT_CUDA(cudaEventCreate(&g->ev_r1));
+        if (n_devices > 1) CRT_NCCL(g_nccl.CommInitAll(g->comms.data(), (int)n_devices, devices));
+        return CRT_OK;
+    };
+    int rc = build();
+    if (rc != CRT_OK) { crt_group_destroy(g); return rc; }
+    *out = g;
+    return CRT_OK;
+    });
+}
+
+int crt_group_set_params(crt_group* g, uint32_t spp, float p_rr, uint32_t light_sample_n, uint32_t seed, int estimator) {
+    CHECK_ARG(g && spp > 0 && p_rr >= 0.0f && p_rr <= 1.0f && light_sample_n > 0 && light_sample_n <= 4096, "crt_group_set_params: invalid argument");
+    CHECK_ARG(estimator == CRT_ESTIMATOR_COMPAT || estimator == CRT_ESTIMATOR_MIS, "crt_group_set_params: unknown estimator");
+    g->rs.spp = spp; g->rs.p_rr = p_rr; g->rs.light_sample_n = light_sample_n; g->rs.seed = seed; g->rs.estimator = estimator;
+    return CRT_OK;
+}
+
+int crt_group_run_view(crt_group* g, const float eye[3], const float inv_view[9], float fovy_rad) {
+    return guarded("crt_group_run_view", [&]() -> int {
+    CHECK_ARG(g && eye && inv_view, "crt_group_run_view: null argument");
+    const size_t G = g->devices.size();
+    const unsigned long long npix = (unsigned long long)g->width * g->height, total = npix * g->rs.spp;
+    const float tan_half = tanf(fovy_rad / 2);
+    g->rendered = false;
+    // shares of the sample-major work index space: whole samples when spp >= G (every GPU renders whole frames), else pixel ranges
+    for (size_t k = 0; k < G; ++k) {
+        RenderSettings rs = g->rs;
+        rs.range_set = true;
+        if (g->rs.spp >= G) { rs.work_begin = (k * g->rs.spp / G) * npix; rs.work_end = ((k + 1) * g->rs.spp / G) * npix; }
+        else { rs.work_begin = k * total / G; rs.work_end = (k + 1) * total / G; }
+        CRT_CUDA(cudaSetDevice(g->devices[k]));
+        int rc = wavefront_begin(g->wf[k], g->scene_of(k), rs, eye, inv_view, tan_half, g->streams[k]);
+        if (rc != CRT_OK) return rc;
+    }
+    // one host thread feeds every GPU: a step enqueues one wavefront iteration where the GPU is ready for it
+    std::vector<char> done(G, 0);
+    for (size_t left = G; left > 0;) {
+        bool any = false;
+        for (size_t k = 0; k < G; ++k) {
+            if (done[k]) continue;
+            CRT_CUDA(cudaSetDevice(g->devices[k]));
+            bool d = false, progressed = false;
+            int rc = wavefront_step(g->wf[k], false, &d, &progressed);
+            if (rc != CRT_OK) return rc;
+            any = any || progressed;
+            if (d) { done[k] = 1; --left; }
+        }
+        if (!any) std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    for (size_t k = 0; k < G; ++k) {
+        CRT_CUDA(cudaSetDevice(g->devices[k]));
+        int rc = wavefront_finish(g->wf[k], &g->stats[k]);
+        if (rc != CRT_OK) return rc;
+    }
+    // ONE collective: sum of the int64 buffers onto devices[0] (integer addition: the same buffer for every G)
+    g->reduce_ms = 0;
+    if (G > 1) {
+        CRT_CUDA(cudaSetDevice(g->devices[0]));
+        CRT_CUDA(cudaEventRecord(g->ev_r0, g->streams[0]));
+        CRT_NCCL(g_nccl.GroupStart());
+        for (size_t k = 0; k < G; ++k) {
+            long long* acc = wavefront_accum(g->wf[k]);
+            CRT_NCCL(g_nccl.Reduce(acc, acc, (size_t)(3 * npix), ncclInt64, ncclSum, 0, g->comms[k], g->streams[k]));
+        }
+        CRT_NCCL(g_nccl.GroupEnd());
+        CRT_CUDA(cudaSetDevice(g->devices[0]));
+        CRT_CUDA(cudaEventRecord(g->ev_r1, g->streams[0]));
+        for (size_t k = 0; k < G; ++k) {
+            CRT_CUDA(cudaSetDevice(g->devices[k]));
+            CRT_CUDA(cudaStreamSynchronize(g->streams[k]));
+        }
+        CRT_CUDA(cudaSetDevice(g->devices[0]));
+        CRT_CUDA(cudaEventElapsedTime(&g->reduce_ms, g->ev_r0, g->ev_r1));
+    }
+    g->rendered = true;
+    return CRT_OK;
+    });
+}
+
+int crt_group_get_accum_i64(crt_group* g, int64_t* out) {
+    CHECK_ARG(g && out, "crt_group_get_accum_i64: null argument");
+    CRT_CUDA(cudaSetDevice(g->devices[0]));
+    CRT_CUDA(cudaMemcpy(out, wavefront_accum(g->wf[0]), sizeof(int64_t) * 3 * (size_t)g->width * g->height, cudaMemcpyDeviceToHost));
+    return CRT_OK;
+}
+
+int crt_group_get_rgb8(crt_group* g, uint8_t* out) {
+    CHECK_ARG(g && out, "crt_group_get_rgb8: null argument");
+    CRT_CUDA(cudaSetDevice(g->devices[0]));
+    const uint32_t npix = g->width * g->height;
+    int rc = resolve_device(wavefront_accum(g->wf[0]), npix, g->rs.spp, g->d_linear, g->d_rgb8, g->streams[0]);
+    if (rc != CRT_OK) return rc;
+    CRT_CUDA(cudaMemcpyAsync(out, g->d_rgb8, 3 * (size_t)npix, cudaMemcpyDeviceToHost, g->streams[0]));
+    CRT_CUDA(cudaStreamSynchronize(g->streams[0]));
+    return CRT_OK;
+}
+
+int crt_group_save_png(crt_group* g, const char* path) {
+    return guarded("crt_group_save_png", [&]() -> int {
+    CHECK_ARG(g && path, "crt_group_save_png: null argument");
+    std::vector<uint8_t> rgb(3 * (size_t)g->width * g->height);
+    int rc = crt_group_get_rgb8(g, rgb.data());
+    if (rc != CRT_OK) return rc;
+    return write_png(path, rgb.data(), g->width, g->height);
+    });
+}
+
+int crt_group_get_stats(crt_group* g, uint32_t index, crt_render_stats* out, float* reduce_ms) {
+    CHECK_ARG(g && out && index < g->devices.size(), "crt_group_get_stats: invalid argument");
+    *out = g->stats[index];
+    if (reduce_ms) *reduce_ms = g->reduce_ms;
+    return CRT_OK;
 }
 
 }  // extern "C"

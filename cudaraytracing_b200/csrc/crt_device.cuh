@@ -311,82 +311,32 @@ CRT_DEV HitRec traverse(const SceneView& sc, V3 o, V3 d, float tmax) {
 //     nodes than the sequential rule (the oracle's counts are the algorithmic minimum).
 // One template for both node layouts: the Walker policy (PairWalker below, WideWalker in crt_wide.cuh) owns the
 // per-lane traversal state and does the node steps; this function owns the queue flush, the finished rays and the refill.
-// load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result;
-// prefetch(first, count) is called by the whole warp for the rays it will load a chunk later (RayFetch).
+// load(i, o, d, tmax) reads ray i (false: report a miss without tracing); done(i, hit) consumes the result.
 #ifndef CRT_REFILL_LANES
 #define CRT_REFILL_LANES 12
 #endif
 static constexpr int kRefillLanes = CRT_REFILL_LANES;
-
-// How a warp takes ray indices from the queue counter `fetch`:
-//   0: one global atomicAdd of the idle-lane count per refill (round 1). Every warp of the grid adds to one address and
-//      waits for the round trip: at C3 steady state ~30 % of the stall samples of k_shadow sat on the shuffle that
-//      broadcasts the returned value (profiles/r02_s02.md);
-//   4: the queue is cut into chunks of CRT_FETCH_CHUNK rays; the first 7/8 of the chunks are dealt round-robin to the
-//      warps of the grid (warp w takes chunks w, w + W, w + 2W ...: no atomic, and the next chunk is known, so its rays
-//      are prefetched into L2 while the current one is traced), the last 1/8 are taken dynamically with one atomicAdd per
-//      chunk to level the finish. (ptxas wraps its own warp aggregation - vote + shuffle of the result right behind the
-//      atomic - around an atomic in `if (lane == 0)`, inline PTX included, so a reservation "one chunk ahead" still waits
-//      for the round trip on the spot: r02_s03.)
-#ifndef CRT_FETCH
-#define CRT_FETCH 4
-#endif
-#ifndef CRT_FETCH_CHUNK
-#define CRT_FETCH_CHUNK 128
-#endif
+// How a warp takes ray indices from the queue counter `fetch`: one global atomicAdd of the idle-lane count per refill.
+// Measured against it and removed (profiles/r02_fetch.md): per-warp reservations of 64-256 indices, with and without a
+// reservation of lookahead (ptxas wraps its own vote + shuffle aggregation around an atomic in `if (lane == 0)`, inline PTX
+// included, so the round trip is waited for on the spot anyway), and a static round-robin deal of 128-ray chunks with a
+// dynamic tail and L2 prefetch of the next chunk: k_extend 15 % slower, k_shadow 9 % slower at 1080p. The returned value of
+// this atomic is the largest single stall of k_shadow only when the accumulation buffer misses L2 (4K frames: its RED
+// traffic to DRAM queues in front of it); the tile order of k_generate removes that.
 struct RayFetch {
-    uint32_t next = 0, end = 0;        // the warp's current chunk [next, end) (the same in every lane)
-    uint32_t cursor = 0;               // next chunk of this warp's round-robin share
-    bool exhausted = false;            // nothing left to take
-    CRT_DEV static uint32_t n_chunks(uint32_t n) { return (n + (uint32_t)CRT_FETCH_CHUNK - 1u) / (uint32_t)CRT_FETCH_CHUNK; }
-    CRT_DEV static uint32_t n_static(uint32_t n) { const uint32_t c = n_chunks(n); return c - c / 8u; }
-    CRT_DEV static uint32_t n_warps() { return gridDim.x * (blockDim.x >> 5); }
-    CRT_DEV void init(uint32_t n) {
-        cursor = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (n == 0) exhausted = true;
-    }
-    CRT_DEV bool drained() const { return exhausted && next == end; }
+    bool exhausted = false;
+    CRT_DEV void init(uint32_t n) { exhausted = n == 0; }
+    CRT_DEV bool drained() const { return exhausted; }
     // Called by the whole warp with `want` idle lanes: returns how many indices [first, first + take) it may hand out.
-    // prefetch(first, count): the chunk this warp will take after the one it adopts now.
-    template <typename Prefetch>
-    CRT_DEV uint32_t take(uint32_t* fetch, uint32_t n, int lane, uint32_t want, uint32_t& first, Prefetch&& prefetch) {
-#if CRT_FETCH == 0
-        if (exhausted) return 0;
+    CRT_DEV uint32_t take(uint32_t* fetch, uint32_t n, int lane, uint32_t want, uint32_t& first) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(fetch, want);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base + want >= n) exhausted = true;
         first = base;
         return base < n ? min(want, n - base) : 0u;
-#else
-        if (next == end && !exhausted) {
-            const uint32_t nc = n_chunks(n), ns = n_static(n);
-            uint32_t c;
-            if (cursor < ns) {
-                c = cursor;
-                cursor += n_warps();
-                if (cursor < ns) prefetch(cursor * (uint32_t)CRT_FETCH_CHUNK, min((uint32_t)CRT_FETCH_CHUNK, n - cursor * (uint32_t)CRT_FETCH_CHUNK));
-            } else {
-                uint32_t ticket = 0;
-                if (lane == 0) ticket = atomicAdd(fetch, 1u);
-                c = ns + __shfl_sync(0xffffffffu, ticket, 0);
-            }
-            if (c >= nc) { exhausted = true; next = end = 0; }
-            else { next = c * (uint32_t)CRT_FETCH_CHUNK; end = min(next + (uint32_t)CRT_FETCH_CHUNK, n); }
-        }
-        const uint32_t k = min(want, end - next);
-        first = next;
-        next += k;
-        return k;
-#endif
     }
 };
-// prefetch.global.L2 of `count` records of `stride` bytes starting at record `first`: one 128-byte line per lane and round
-CRT_DEV void prefetch_l2(const void* base, uint32_t first, uint32_t count, uint32_t stride, int lane) {
-    const char* p = (const char*)base + (size_t)first * stride;
-    const uint32_t bytes = count * stride;
-    for (uint32_t off = (uint32_t)lane * 128u; off < bytes; off += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
-}
 
 template <int CAP>
 struct WarpLeafQueue {
@@ -395,12 +345,49 @@ struct WarpLeafQueue {
     int best_slot[32];
     int q_slot[CAP];                                                     // queued leaves: first triangle slot ...
     unsigned char q_lane[CAP];                                           // ... and the lane that owns the ray
+    unsigned char any[32];                                               // flush_leaf_queue<2>: the owner's ray is an any-hit ray
     int count;
 };
 static constexpr unsigned long long kNoHitKey = ((unsigned long long)0x7f7fffffu << 32) | 0x7fffffffull;   // t = FLT_MAX
 
-template <int MODE, typename Walker, typename Load, typename Done, typename Prefetch>
-CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Prefetch prefetch) {
+// The whole warp tests the queued leaves, one queue entry per lane, against the owners' rays (mirrored in the queue
+// struct) and combines the owners' best hits. MODE 0: closest hit; 1: any hit with t > 1e-5 && tmax - t > 1e-5;
+// 2: per ray, q.any[owner] says which (the tail path tracer mixes extend, probe and shadow rays in one warp).
+template <int MODE, typename Q>
+CRT_DEV void flush_leaf_queue(const SceneView& sc, Q& q, int q_count, int lane) {
+    for (int base = 0; base < q_count; base += 32) {
+        const int k = base + lane;
+        unsigned long long mykey = kNoHitKey;
+        int myslot = -1, owner = 0;
+        if (k < q_count) {
+            owner = q.q_lane[k];
+            int slot = q.q_slot[k];
+            const V3 ro = mk3(q.ox[owner], q.oy[owner], q.oz[owner]), rd = mk3(q.dx[owner], q.dy[owner], q.dz[owner]);
+            const float rtmax = q.tmax[owner];
+            const bool any = MODE == 1 || (MODE == 2 && q.any[owner]);
+            for (;; ++slot) {
+                V3 tv1, te1, te2;
+                const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
+                float t;
+                if (tri_test(tv1, te1, te2, ro, rd, &t) && t > kEps && (!any || rtmax - t > kEps)) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (fw & ~kLastBit);
+                    if (key < mykey) { mykey = key; myslot = slot; }
+                }
+                if (fw & kLastBit) break;
+            }
+            if (myslot >= 0) {
+                if (MODE != 1) atomicMin(&q.best[owner], mykey);
+                else q.best[owner] = mykey;                 // any blocker will do: one of the writers wins (64-bit store)
+            }
+        }
+        __syncwarp();
+        if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
+        __syncwarp();
+    }
+}
+
+template <int MODE, typename Walker, typename Load, typename Done>
+CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
     typedef WarpLeafQueue<Walker::kCap> Queue;
     __shared__ Queue s_wq[4];                              // launched with 128 threads per block
     Queue& q = s_wq[threadIdx.x >> 5];
@@ -429,34 +416,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
         __syncwarp();
         const int q_count = wk.queued(q);
         if (q_count >= Walker::kFlush || (walking == 0 && q_count > 0)) {
-            for (int base = 0; base < q_count; base += 32) {
-                const int k = base + lane;
-                unsigned long long mykey = kNoHitKey;
-                int myslot = -1, owner = 0;
-                if (k < q_count) {
-                    owner = q.q_lane[k];
-                    int slot = q.q_slot[k];
-                    const V3 ro = mk3(q.ox[owner], q.oy[owner], q.oz[owner]), rd = mk3(q.dx[owner], q.dy[owner], q.dz[owner]);
-                    const float rtmax = q.tmax[owner];
-                    for (;; ++slot) {
-                        V3 tv1, te1, te2;
-                        const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);
-                        float t;
-                        if (tri_test(tv1, te1, te2, ro, rd, &t) && t > kEps && (MODE == 0 || rtmax - t > kEps)) {
-                            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (fw & ~kLastBit);
-                            if (key < mykey) { mykey = key; myslot = slot; }
-                        }
-                        if (fw & kLastBit) break;
-                    }
-                    if (myslot >= 0) {
-                        if (MODE == 0) atomicMin(&q.best[owner], mykey);
-                        else q.best[owner] = mykey;                 // any blocker will do: one of the writers wins (64-bit store)
-                    }
-                }
-                __syncwarp();
-                if (myslot >= 0 && q.best[owner] == mykey) q.best_slot[owner] = myslot;
-                __syncwarp();
-            }
+            flush_leaf_queue<MODE>(sc, q, q_count, lane);
             wk.reset_queue(q, lane);
             pending = 0;
             if (have) {
@@ -482,7 +442,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
             const int n_idle = __popc(idle);
             if (!rf.drained() && (n_idle >= kRefillLanes || n_idle == 32)) {
                 uint32_t first = 0;
-                const uint32_t got = rf.take(fetch, n, lane, (uint32_t)n_idle, first, prefetch);
+                const uint32_t got = rf.take(fetch, n, lane, (uint32_t)n_idle, first);
                 const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
                 if (!have && rank < got) {
                     idx = first + rank;

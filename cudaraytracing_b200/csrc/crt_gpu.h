@@ -53,9 +53,20 @@ int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face
 // Uploads materials and lights, builds the BVH. Leaves the device selected.
 int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device, DeviceScene& ds, float* build_ms);
 
-// Ray batches (device pointers). rays: n * 2 float4 {o,tmax}{d,0}.
-int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
+// Ray batches. rays: n * 2 float4 {o,tmax}{d,0}. A RayBatcher holds what a batch call needs besides the scene - queue
+// counters, events, two streams and, for host buffers, chunk-sized device buffers and pinned staging - for the life of
+// the scene handle (round 1 paid a cudaMalloc / cudaFree / event create per call).
+struct RayBatcher;
+int ray_batcher_create(const DeviceScene& ds, RayBatcher** out);
+void ray_batcher_destroy(RayBatcher* b);
+// Device pointers on the scene's device.
+int trace_rays_device(RayBatcher* b, const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
                       cudaStream_t st, float* kernel_ms);
+// Host buffers: chunks of the batch go host -> device, through the kernel and back on two streams, so copy-in, trace and
+// copy-out of neighbouring chunks overlap. Page-locked caller buffers are used in place; pageable ones are staged through
+// pinned memory by host threads.
+int trace_rays_host(RayBatcher* b, const DeviceScene& ds, const float* rays, uint64_t n, int mode, float* t_out, int32_t* face_out,
+                    float* kernel_ms);
 
 int random_rays_device(const DeviceScene& ds, float4* d_rays, uint64_t n, uint64_t start, uint32_t key, int any_hit, cudaStream_t st);
 
@@ -79,7 +90,17 @@ int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wav
 void wavefront_destroy(Wavefront* w);
 int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
                      float tan_half, cudaStream_t st, crt_render_stats* stats);
+// The same run_view as a state machine, for one host thread driving several GPUs (crt_group): begin resets the frame,
+// step does the host side of one wavefront iteration (block == false: returns with *progressed == false instead of
+// waiting for the GPU), finish drains the stream and fills the statistics. The caller selects the device.
+int wavefront_begin(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
+                    float tan_half, cudaStream_t st);
+int wavefront_step(Wavefront* w, bool block, bool* done, bool* progressed);
+int wavefront_finish(Wavefront* w, crt_render_stats* stats);
 long long* wavefront_accum(Wavefront* w);
+// Device-to-device replica of a built scene (cudaMemcpyPeer of every table): what the other GPUs of a crt_group get
+// instead of a second parse + build. Leaves `device` selected.
+int clone_scene(const DeviceScene& src, int device, DeviceScene& dst);
 // fixed point -> linear float mean and tone-mapped RGB8 (reference Render.cuh:348,350), on the device
 int resolve_device(const long long* d_accum, uint32_t n_pixels, uint32_t spp, float* d_linear, uint8_t* d_rgb8, cudaStream_t st);
 

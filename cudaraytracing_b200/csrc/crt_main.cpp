@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
     std::string config = "config.json", out = "out.png", root = ".";
     std::string checkpoint;
     long spp = -1, seed = -1, width = -1, height = -1, chunk_spp = 64, stop_after = -1;
-    int estimator = -1, device = 0, builder = CRT_BUILDER_PLOC8;
+    int estimator = -1, device = 0, builder = CRT_BUILDER_PLOC8, gpus = 1;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -59,6 +59,7 @@ int main(int argc, char** argv) {
         else if (a == "--width") width = atol(next());
         else if (a == "--height") height = atol(next());
         else if (a == "--device") device = atoi(next());
+        else if (a == "--gpus") gpus = atoi(next());
         else if (a == "--estimator") { std::string e = next(); estimator = e == "mis" ? CRT_ESTIMATOR_MIS : CRT_ESTIMATOR_COMPAT; }
         else if (a == "--builder") { std::string e = next(); builder = e == "lbvh8" ? CRT_BUILDER_LBVH8 : e == "ploc" ? CRT_BUILDER_PLOC : e == "ploc8" ? CRT_BUILDER_PLOC8 : CRT_BUILDER_LBVH; }
         else if (a == "--checkpoint") checkpoint = next();
@@ -66,10 +67,12 @@ int main(int argc, char** argv) {
         else if (a == "--stop-after") stop_after = atol(next());
         else if (a == "--help" || a == "-h") {
             printf("usage: crt --config config.json [--root DIR] [--out image.png] [--spp N] [--seed S]\n"
-                   "           [--width W --height H] [--estimator compat|mis] [--builder lbvh|lbvh8|ploc|ploc8] [--device D]\n"
+                   "           [--width W --height H] [--estimator compat|mis] [--builder lbvh|lbvh8|ploc|ploc8] [--device D] [--gpus N]\n"
                    "           [--checkpoint FILE [--chunk-spp N] [--stop-after CHUNKS]]\n"
                    "  --checkpoint: progressive render in chunks of N samples per pixel (default 64); FILE is rewritten after\n"
-                   "                every chunk and, if it exists at start, the render resumes from it (bit-identical image).\n");
+                   "                every chunk and, if it exists at start, the render resumes from it (bit-identical image).\n"
+                   "  --gpus N:     devices D .. D+N-1 render shares of the samples (the built scene is copied device to device), one\n"
+                   "                NCCL reduce sums the accumulation buffers on device D; the image is the one a single GPU renders.\n");
             return 0;
         } else { fprintf(stderr, "crt: unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -97,6 +100,41 @@ int main(int argc, char** argv) {
     uint64_t n_tris = 0, n_nodes = 0; uint32_t n_mats = 0, n_lights = 0;
     crt_scene_counts(scene, &n_tris, &n_mats, &n_lights, &n_nodes);
 
+    float M[9];
+    crt_inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up, M);
+    const float fovy_rad = cfg.fov_y * (float)M_PI / 180.0f;
+    if (gpus > 1) {
+        // several GPUs behind one handle (crt_group): this thread drives all of them
+        if (!checkpoint.empty()) { fprintf(stderr, "crt: --checkpoint renders on one GPU (omit --gpus)\n"); return 2; }
+        std::vector<int> devs;
+        for (int k = 0; k < gpus; ++k) devs.push_back(device + k);
+        crt_group* group = nullptr;
+        double g0 = now_ms();
+        DIE_IF(crt_group_create(scene, cfg.width, cfg.height, devs.data(), (uint32_t)devs.size(), &group), "group_create");
+        DIE_IF(crt_group_set_params(group, cfg.spp, cfg.p_rr, cfg.light_sample_n, cfg.seed, (int)cfg.estimator), "group_set_params");
+        double g1 = now_ms();
+        DIE_IF(crt_group_run_view(group, cfg.eye_pos, M, fovy_rad), "group_run_view");
+        double g2 = now_ms();
+        DIE_IF(crt_group_save_png(group, out.c_str()), "group_save_png");
+        double g3 = now_ms();
+        float reduce_ms = 0, slowest = 0;
+        unsigned long long ext = 0, sh = 0, pr = 0;
+        for (int k = 0; k < gpus; ++k) {
+            crt_render_stats c;
+            crt_group_get_stats(group, (uint32_t)k, &c, &reduce_ms);
+            if (c.ms_total > slowest) slowest = c.ms_total;
+            ext += c.extend_rays; sh += c.shadow_rays; pr += c.probe_rays;
+        }
+        const double total_samples = (double)cfg.width * cfg.height * cfg.spp;
+        printf("{\"gpus\": %d, \"triangles\": %llu, \"nodes\": %llu, \"load_ms\": %.2f, \"bvh_build_gpu_ms\": %.3f, \"replicate_and_setup_ms\": %.2f, "
+               "\"render_ms_slowest_gpu\": %.3f, \"reduce_ms\": %.3f, \"render_wall_ms\": %.2f, \"png_ms\": %.2f, \"msamples_per_s\": %.2f, "
+               "\"extend_rays\": %llu, \"shadow_rays\": %llu, \"probe_rays\": %llu, \"out\": \"%s\"}\n",
+               gpus, (unsigned long long)n_tris, (unsigned long long)n_nodes, t1 - t0, build_ms, g1 - g0, slowest, reduce_ms, g2 - g1, g3 - g2,
+               total_samples / ((g2 - g1) * 1e3), ext, sh, pr, out.c_str());
+        crt_group_destroy(group);
+        crt_scene_destroy(scene);
+        return 0;
+    }
     crt_render* render = nullptr;
     DIE_IF(crt_render_create(scene, cfg.width, cfg.height, &render), "render_create");
     crt_render_set_spp(render, cfg.spp);
@@ -104,9 +142,6 @@ int main(int argc, char** argv) {
     crt_render_set_light_sample_n(render, cfg.light_sample_n);
     crt_render_set_seed(render, cfg.seed);
     DIE_IF(crt_render_set_estimator(render, (int)cfg.estimator), "set_estimator");
-    float M[9];
-    crt_inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up, M);
-    const float fovy_rad = cfg.fov_y * (float)M_PI / 180.0f;
     double t3 = now_ms();
     crt_render_stats st;
     uint64_t samples_rendered = (uint64_t)cfg.width * cfg.height * cfg.spp, resumed_from = 0;

@@ -28,6 +28,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <type_traits>
 #include <vector>
 
 namespace crt {
@@ -44,7 +46,40 @@ void DeviceScene::release() {
     n_tris = n_nodes = n_mats = n_lights = n_light_tris = 0;
 }
 
+int clone_scene(const DeviceScene& src, int device, DeviceScene& dst) {
+    CRT_CUDA(cudaSetDevice(device));
+    dst.release();
+    dst = src;                                                  // counts, flags, bounds; the pointers are replaced below
+    dst.device = device;
+    dst.nodes = dst.tri_geom = dst.tri_shade = dst.mats = dst.light_tris = nullptr;
+    dst.order = nullptr; dst.last = nullptr; dst.lights = nullptr; dst.light_cdf = nullptr;
+    auto copy = [&](auto*& d, const auto* s_ptr, size_t bytes) -> int {
+        if (!s_ptr || bytes == 0) return CRT_OK;
+        CRT_CUDA(cudaMalloc((void**)&d, bytes));
+        CRT_CUDA(cudaMemcpyPeer(d, device, s_ptr, src.device, bytes));
+        return CRT_OK;
+    };
+    int rc = CRT_OK;
+    const size_t node_bytes = sizeof(float4) * (src.wide ? 5 : 4) * (size_t)src.n_nodes;
+    if ((rc = copy(dst.nodes, src.nodes, node_bytes)) != CRT_OK) return rc;
+    if ((rc = copy(dst.tri_geom, src.tri_geom, sizeof(float4) * 3 * (size_t)src.n_tris)) != CRT_OK) return rc;
+    if ((rc = copy(dst.tri_shade, src.tri_shade, sizeof(float4) * (size_t)src.n_tris)) != CRT_OK) return rc;
+    if ((rc = copy(dst.order, src.order, sizeof(uint32_t) * (size_t)src.n_tris)) != CRT_OK) return rc;
+    if ((rc = copy(dst.last, src.last, (size_t)src.n_tris)) != CRT_OK) return rc;
+    if ((rc = copy(dst.mats, src.mats, sizeof(float4) * 4 * (size_t)src.n_mats)) != CRT_OK) return rc;
+    if ((rc = copy(dst.light_tris, src.light_tris, sizeof(float4) * 4 * (size_t)src.n_light_tris)) != CRT_OK) return rc;
+    if ((rc = copy(dst.lights, src.lights, sizeof(int4) * (size_t)src.n_lights)) != CRT_OK) return rc;
+    if ((rc = copy(dst.light_cdf, src.light_cdf, sizeof(float) * (size_t)src.n_light_tris)) != CRT_OK) return rc;
+    CRT_CUDA(cudaDeviceSynchronize());
+    return CRT_OK;
+}
+
 static inline float bits_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (uint32_t)strtoul(v, nullptr, 0);
+}
 
 int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device, DeviceScene& ds, float* build_ms) {
     CRT_CUDA(cudaSetDevice(device));
@@ -124,10 +159,10 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device
 // =============================================================================================
 // node-layout dispatch: WIDE = false: 64-byte child-pair nodes, true: 80-byte 8-wide compressed nodes
 // =============================================================================================
-template <int MODE, bool WIDE, typename Load, typename Done, typename Prefetch>
-CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done, Prefetch prefetch) {
-    if (WIDE) trace_persistent_queue<MODE, WideWalker>(sc, n, fetch, load, done, prefetch);
-    else trace_persistent_queue<MODE, PairWalker>(sc, n, fetch, load, done, prefetch);
+template <int MODE, bool WIDE, typename Load, typename Done>
+CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
+    if (WIDE) trace_persistent_queue<MODE, WideWalker>(sc, n, fetch, load, done);
+    else trace_persistent_queue<MODE, PairWalker>(sc, n, fetch, load, done);
 }
 template <int MODE, bool WIDE>
 CRT_DEV HitRec trace_one(const SceneView& sc, V3 o, V3 d, float tmax) {
@@ -152,8 +187,7 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_trace_batch(SceneView sc, con
         [&](uint32_t i, const HitRec& h) {
             if (t_out) t_out[i] = h.t;
             if (face_out) face_out[i] = h.face;
-        },
-        [&](uint32_t first, uint32_t count) { prefetch_l2(rays, first, count, 32u, threadIdx.x & 31); });
+        });
 }
 
 static int g_num_sms = 0;
@@ -167,42 +201,159 @@ static int num_sms() {
     return g_num_sms;
 }
 
-int trace_rays_device(const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
-                      cudaStream_t st, float* kernel_ms) {
-    uint32_t* fetch = nullptr;
-    CRT_CUDA(cudaMalloc(&fetch, sizeof(uint32_t)));
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
+// ---- batch context ------------------------------------------------------------------------------
+struct RayBatcher {
+    int device = 0;
+    int blocks = 0;
+    uint32_t* fetch = nullptr;                  // two queue counters, 128 bytes apart (one per pipeline slot)
+    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    // host-buffer path, allocated on first use
+    uint64_t chunk = 0;                         // rays per chunk
+    float4* d_rays[2] = {nullptr, nullptr};
+    float* d_t[2] = {nullptr, nullptr};
+    int* d_face[2] = {nullptr, nullptr};
+    float4* h_rays[2] = {nullptr, nullptr};     // pinned staging for pageable callers
+    float* h_t[2] = {nullptr, nullptr};
+    int* h_face[2] = {nullptr, nullptr};
+};
+
+int ray_batcher_create(const DeviceScene& ds, RayBatcher** out) {
+    RayBatcher* b = new RayBatcher();
+    b->device = ds.device;
+    *out = b;                                                  // destroyed by the caller on failure, too
+    CRT_CUDA(cudaMalloc(&b->fetch, 256));
+    for (int k = 0; k < 2; ++k) {
+        CRT_CUDA(cudaEventCreate(&b->ev_a[k]));
+        CRT_CUDA(cudaEventCreate(&b->ev_b[k]));
+        CRT_CUDA(cudaEventCreateWithFlags(&b->ev_done[k], cudaEventDisableTiming));
+        CRT_CUDA(cudaStreamCreateWithFlags(&b->st[k], cudaStreamNonBlocking));
+    }
     int occ = 0;
-    if (ds.wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0, true>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0, false>, 128, 0);
-    const int blocks = num_sms() * std::max(occ, 1);
+    if (ds.wide) CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0, true>, 128, 0));
+    else CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_batch<0, false>, 128, 0));
+    b->blocks = num_sms() * std::max(occ, 1);
+    return CRT_OK;
+}
+
+void ray_batcher_destroy(RayBatcher* b) {
+    if (!b) return;
+    cudaFree(b->fetch);
+    for (int k = 0; k < 2; ++k) {
+        if (b->ev_a[k]) cudaEventDestroy(b->ev_a[k]);
+        if (b->ev_b[k]) cudaEventDestroy(b->ev_b[k]);
+        if (b->ev_done[k]) cudaEventDestroy(b->ev_done[k]);
+        if (b->st[k]) cudaStreamDestroy(b->st[k]);
+        cudaFree(b->d_rays[k]); cudaFree(b->d_t[k]); cudaFree(b->d_face[k]);
+        if (b->h_rays[k]) cudaFreeHost(b->h_rays[k]);
+        if (b->h_t[k]) cudaFreeHost(b->h_t[k]);
+        if (b->h_face[k]) cudaFreeHost(b->h_face[k]);
+    }
+    delete b;
+}
+
+static void launch_trace_batch(const RayBatcher* b, const DeviceScene& ds, const float4* d_rays, uint32_t cnt, int mode, float* t_o, int* f_o,
+                               uint32_t* fetch, cudaStream_t st) {
+    cudaMemsetAsync(fetch, 0, sizeof(uint32_t), st);
+    if (mode == CRT_RAY_CLOSEST) {
+        if (ds.wide) k_trace_batch<0, true><<<b->blocks, 128, 0, st>>>(ds.view(), d_rays, cnt, t_o, f_o, fetch);
+        else k_trace_batch<0, false><<<b->blocks, 128, 0, st>>>(ds.view(), d_rays, cnt, t_o, f_o, fetch);
+    } else {
+        if (ds.wide) k_trace_batch<1, true><<<b->blocks, 128, 0, st>>>(ds.view(), d_rays, cnt, t_o, f_o, fetch);
+        else k_trace_batch<1, false><<<b->blocks, 128, 0, st>>>(ds.view(), d_rays, cnt, t_o, f_o, fetch);
+    }
+}
+
+int trace_rays_device(RayBatcher* b, const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
+                      cudaStream_t st, float* kernel_ms) {
     const uint64_t chunk = 1ull << 30;                   // queue indices are 32-bit
     float ms_total = 0;
-    cudaError_t e = cudaSuccess;
-    for (uint64_t off = 0; off < n && e == cudaSuccess; off += chunk) {
+    for (uint64_t off = 0; off < n; off += chunk) {
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, n - off);
-        cudaMemsetAsync(fetch, 0, sizeof(uint32_t), st);
-        cudaEventRecord(a, st);
-        float* t_o = d_t ? d_t + off : nullptr;
-        int* f_o = d_face ? d_face + off : nullptr;
-        if (mode == CRT_RAY_CLOSEST) {
-            if (ds.wide) k_trace_batch<0, true><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, t_o, f_o, fetch);
-            else k_trace_batch<0, false><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, t_o, f_o, fetch);
-        } else {
-            if (ds.wide) k_trace_batch<1, true><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, t_o, f_o, fetch);
-            else k_trace_batch<1, false><<<blocks, 128, 0, st>>>(ds.view(), d_rays + 2 * off, cnt, t_o, f_o, fetch);
-        }
-        cudaEventRecord(b, st);
-        e = cudaStreamSynchronize(st);
+        CRT_CUDA(cudaEventRecord(b->ev_a[0], st));
+        launch_trace_batch(b, ds, d_rays + 2 * off, cnt, mode, d_t ? d_t + off : nullptr, d_face ? d_face + off : nullptr, b->fetch, st);
+        CRT_CUDA(cudaGetLastError());
+        CRT_CUDA(cudaEventRecord(b->ev_b[0], st));
+        CRT_CUDA(cudaStreamSynchronize(st));
         float ms = 0;
-        if (e == cudaSuccess) { cudaEventElapsedTime(&ms, a, b); ms_total += ms; }
+        CRT_CUDA(cudaEventElapsedTime(&ms, b->ev_a[0], b->ev_b[0]));
+        ms_total += ms;
     }
-    cudaEventDestroy(a); cudaEventDestroy(b);
-    cudaFree(fetch);
-    if (e != cudaSuccess) return cuda_fail(e, "k_trace_batch");
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "k_trace_batch launch");
+    if (kernel_ms) *kernel_ms = ms_total;
+    return CRT_OK;
+}
+
+static bool is_page_locked(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// memcpy on all host threads (a pageable 128 MB chunk at one thread's ~10 GB/s would be slower than the PCIe link)
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    unsigned T = std::thread::hardware_concurrency();
+    T = std::max(1u, std::min(T, 16u));
+    if (bytes < (8u << 20) || T == 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / T) + 4095) & ~(size_t)4095;
+    for (unsigned k = 1; k < T; ++k) {
+        const size_t o = per * k;
+        if (o >= bytes) break;
+        th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, std::min(per, bytes - o)); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto& t : th) t.join();
+}
+
+int trace_rays_host(RayBatcher* b, const DeviceScene& ds, const float* rays, uint64_t n, int mode, float* t_out, int32_t* face_out,
+                    float* kernel_ms) {
+    if (b->chunk == 0) {
+        uint64_t chunk = env_u32("CRT_BATCH_CHUNK", 4u << 20);          // 4 Mi rays: 128 MB in, 32 MB out per chunk
+        chunk = std::max<uint64_t>(1024, std::min<uint64_t>(chunk, 1ull << 28));
+        for (int k = 0; k < 2; ++k) {
+            CRT_CUDA(cudaMalloc(&b->d_rays[k], sizeof(float4) * 2 * chunk));
+            CRT_CUDA(cudaMalloc(&b->d_t[k], sizeof(float) * chunk));
+            CRT_CUDA(cudaMalloc(&b->d_face[k], sizeof(int) * chunk));
+        }
+        b->chunk = chunk;
+    }
+    const bool in_place_in = is_page_locked(rays), in_place_t = is_page_locked(t_out), in_place_f = is_page_locked(face_out);
+    const uint64_t C = b->chunk;
+    for (int k = 0; k < 2; ++k) {
+        if (!in_place_in && !b->h_rays[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_rays[k], sizeof(float4) * 2 * C, cudaHostAllocDefault));
+        if (t_out && !in_place_t && !b->h_t[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_t[k], sizeof(float) * C, cudaHostAllocDefault));
+        if (face_out && !in_place_f && !b->h_face[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_face[k], sizeof(int) * C, cudaHostAllocDefault));
+    }
+    const uint64_t n_chunks = (n + C - 1) / C;
+    float ms_total = 0;
+    auto retire = [&](uint64_t k) -> int {                // chunk k has left the GPU: kernel time, staged results to the caller
+        const int s = (int)(k & 1);
+        const uint64_t off = k * C, cnt = std::min<uint64_t>(C, n - off);
+        CRT_CUDA(cudaEventSynchronize(b->ev_done[s]));
+        float ms = 0;
+        CRT_CUDA(cudaEventElapsedTime(&ms, b->ev_a[s], b->ev_b[s]));
+        ms_total += ms;
+        if (t_out && !in_place_t) parallel_memcpy(t_out + off, b->h_t[s], sizeof(float) * cnt);
+        if (face_out && !in_place_f) parallel_memcpy(face_out + off, b->h_face[s], sizeof(int) * cnt);
+        return CRT_OK;
+    };
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const int s = (int)(k & 1);
+        const uint64_t off = k * C, cnt = std::min<uint64_t>(C, n - off);
+        if (k >= 2) { int rc = retire(k - 2); if (rc != CRT_OK) return rc; }      // the slot's buffers are free again
+        const float* src = rays + 8 * off;
+        if (!in_place_in) { parallel_memcpy(b->h_rays[s], src, sizeof(float) * 8 * cnt); src = (const float*)b->h_rays[s]; }
+        CRT_CUDA(cudaMemcpyAsync(b->d_rays[s], src, sizeof(float) * 8 * cnt, cudaMemcpyHostToDevice, b->st[s]));
+        CRT_CUDA(cudaEventRecord(b->ev_a[s], b->st[s]));
+        launch_trace_batch(b, ds, b->d_rays[s], (uint32_t)cnt, mode, b->d_t[s], b->d_face[s], b->fetch + 32 * s, b->st[s]);
+        CRT_CUDA(cudaGetLastError());
+        CRT_CUDA(cudaEventRecord(b->ev_b[s], b->st[s]));
+        if (t_out) CRT_CUDA(cudaMemcpyAsync(in_place_t ? t_out + off : b->h_t[s], b->d_t[s], sizeof(float) * cnt, cudaMemcpyDeviceToHost, b->st[s]));
+        if (face_out) CRT_CUDA(cudaMemcpyAsync(in_place_f ? face_out + off : b->h_face[s], b->d_face[s], sizeof(int) * cnt, cudaMemcpyDeviceToHost, b->st[s]));
+        CRT_CUDA(cudaEventRecord(b->ev_done[s], b->st[s]));
+    }
+    for (uint64_t k = n_chunks >= 2 ? n_chunks - 2 : 0; k < n_chunks; ++k) { int rc = retire(k); if (rc != CRT_OK) return rc; }
     if (kernel_ms) *kernel_ms = ms_total;
     return CRT_OK;
 }
@@ -282,9 +433,33 @@ struct RenderParamsDev {
 };
 
 static constexpr uint32_t kFlagProbe = 0x100u;
-static constexpr uint32_t kTailDefault = 1u << 17;   // paths alive when k_tail takes over (CRT_TAIL overrides, 0 = never)
+static constexpr uint32_t kTailDefault = 1u << 19;   // paths alive when k_tail takes over (CRT_TAIL overrides, 0 = never)
+
+struct WfRun {                      // the run_view in flight on a Wavefront (wavefront_begin / step / finish)
+    bool active = false;
+    const DeviceScene* ds = nullptr;
+    RenderSettings rs;
+    RenderParamsDev p;
+    SceneView sv;
+    cudaStream_t st = nullptr;
+    bool wide = false, mis = false, overlap = false, timeline = false;
+    uint32_t tail_max = 0, it = 0;
+    uint64_t launches = 0;
+    unsigned long long w_begin = 0;
+    float ms_stage[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t se[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<std::pair<const char*, cudaEvent_t>> tl;      // CRT_TIMELINE
+    void mark(const char* what, cudaStream_t s) {
+        if (!timeline) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tl.push_back({what, e});
+    }
+};
 
 struct Wavefront {
+    WfRun run;
     uint32_t width = 0, height = 0;
     uint32_t pool = 0;             // path slots per queue
     uint32_t shadow_cap = 0;
@@ -387,11 +562,7 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_extend(SceneView sc, Counters
     trace_queue<0, WIDE>(
         sc, c->n_cur, &c->fetch_extend,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
-        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; },
-        [&](uint32_t first, uint32_t count) {
-            prefetch_l2(q_o, first, count, 16u, threadIdx.x & 31);
-            prefetch_l2(q_d, first, count, 16u, threadIdx.x & 31);
-        });
+        [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });
 }
 
 // SPECULAR probe rays (reference Render.cuh:303): traced only when the continuation ray hit.
@@ -408,8 +579,7 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_probe(SceneView sc, Counters*
             o = mk3(pr_o[i]); d = mk3(pr_d[i]); tmax = FLT_MAX; traced++;
             return true;
         },
-        [&](uint32_t k, const HitRec& h) { pr_hit[list[k]] = h.slot; },
-        [&](uint32_t first, uint32_t count) { prefetch_l2(list, first, count, 4u, threadIdx.x & 31); });
+        [&](uint32_t k, const HitRec& h) { pr_hit[list[k]] = h.slot; });
     const int lane = threadIdx.x & 31;
     for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
     if (lane == 0 && traced) atomicAdd(&c->stat_probe, traced);
@@ -734,62 +904,242 @@ __global__ void __launch_bounds__(128, EST == CRT_ESTIMATOR_COMPAT ? CRT_SHADE_M
     }
 }
 
-// Tail of a frame: once no new camera paths remain and few paths are still alive, every remaining
-// path is run to its end by one lane (extend -> shade -> shadow in place), instead of paying five
-// launches per bounce for ever smaller wavefronts. Same per-vertex statement as above, same Philox
-// keys and the same order-independent accumulation, so the image does not depend on where the
-// switch happens.
+// Tail of a frame: once no new camera paths remain and at most tail_max paths are alive, ONE persistent kernel runs
+// them to their ends, instead of five launches per bounce for ever smaller wavefronts (a launch with 2-3 rays per lane
+// lasts as long as its longest ray: the second and third bounce of an 800x600 frame cost more than the first,
+// profiles/r02_s08.md). It is the leaf-queue traversal of trace_persistent_queue with three kinds of rays in flight in one
+// warp - the extend ray of a path, shadow rays, SPECULAR probe rays - and a source of rays in front of the global path
+// queue: a lane whose extend ray hit shades the vertex (same per-vertex statement, same Philox keys, same
+// order-independent accumulation as k_shade, so the image does not depend on where the switch happens), pushes the
+// shadow / probe rays onto the warp's stash in shared memory and parks the continuation; idle lanes take stash entries
+// first (every lane, when the stash runs high), then their parked continuation, then a new path. Shadow rays are thereby
+// off a path's critical chain, and a lane is never without work while the warp has any.
+#ifndef CRT_TERM_HIGH
+#define CRT_TERM_HIGH 16
+#endif
+#ifndef CRT_TAIL_MINB
+#define CRT_TAIL_MINB 4
+#endif
+static constexpr int kTermCap = 80;                  // shadow / probe rays waiting per warp; beyond it a ray is traced in place
+static constexpr int kTermHigh = CRT_TERM_HIGH;                 // at this many, parked continuations wait and every idle lane takes from the stash
+#ifndef CRT_SHADE_BATCH
+#define CRT_SHADE_BATCH 8                            // lanes with a vertex to shade that make the warp shade now (else after kShadeWait turns)
+#endif
+static constexpr int kShadeBatch = CRT_SHADE_BATCH;
+static constexpr int kShadeWait = 2;
+struct TermStash {
+    float4 a[kTermCap];                              // origin, tmax
+    float4 b[kTermCap];                              // direction, kind (1 shadow, 2 probe)
+    float4 c[kTermCap];                              // contribution (shadow) / weight (probe), pixel
+    int count;
+};
+enum { kPayT = 0, kPayPixel = 3, kPaySample = 4, kPayMeta = 5, kPayPdf = 6, kPayPd = 7, kPayPw = 10, kPayO = 13, kPayD = 16, kPayWords = 19 };
+
 template <int EST, bool WIDE>
-__global__ void __launch_bounds__(128) k_tail(SceneView sc, Counters* c, RenderParamsDev p, const float4* __restrict__ q_o,
-                                              const float4* __restrict__ q_d, const float4* __restrict__ q_T,
-                                              const float* __restrict__ q_pdf, const float4* __restrict__ pr_o, const float4* __restrict__ pr_d,
-                                              const float4* __restrict__ pr_w, long long* __restrict__ accum) {
+__global__ void __launch_bounds__(128, CRT_TAIL_MINB) k_tail(SceneView sc, Counters* c, RenderParamsDev p, const float4* __restrict__ q_o,
+                                                 const float4* __restrict__ q_d, const float4* __restrict__ q_T,
+                                                 const float* __restrict__ q_pdf, const float4* __restrict__ pr_d,
+                                                 const float4* __restrict__ pr_w, long long* __restrict__ accum) {
     const uint32_t n = c->tail_n;
     if (n == 0) return;
+    typedef typename std::conditional<WIDE, WideWalker, PairWalker>::type Walker;
+    typedef WarpLeafQueue<Walker::kCap> Queue;
+    __shared__ Queue s_wq[4];
+    __shared__ TermStash s_ts[4];
+    __shared__ float s_pay[kPayWords][128];           // the lane's path: throughput, pixel, sample, meta, pdf, pending probe, parked ray
+    __shared__ float4 s_term[128];                    // the terminal ray the lane traces: contribution / weight, pixel
+    Queue& q = s_wq[threadIdx.x >> 5];
+    TermStash& ts = s_ts[threadIdx.x >> 5];
+    const unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, tid = threadIdx.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    typename Walker::Entry stack[Walker::kLocal];
+    Walker wk;
+    wk.init();
+    V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
+    float tlimit = 0.0f, sh_t = 0.0f;
+    int pending = 0, kind = 0, sh_slot = -1, shade_wait = 0;
+    bool have = false, zray = false, parked = false, needs_shade = false;
     unsigned long long n_ext = 0, n_sh = 0, n_pr = 0;
+    RayFetch rf;
+    rf.init(n);
+    if (lane == 0) { q.count = 0; ts.count = 0; }
+    __syncwarp();
+    auto arm = [&](V3 ro, V3 rd, float tmax, int k) {          // this lane starts tracing a ray of kind k
+        o = ro;
+        inv = box_inv3(rd);
+        zray = has_parallel_axis(inv);
+        kind = k;
+        tlimit = k == 1 ? tmax : FLT_MAX;
+        q.ox[lane] = ro.x; q.oy[lane] = ro.y; q.oz[lane] = ro.z;
+        q.dx[lane] = rd.x; q.dy[lane] = rd.y; q.dz[lane] = rd.z;
+        q.tmax[lane] = tmax;
+        q.any[lane] = k == 1;
+        q.best[lane] = kNoHitKey;
+        q.best_slot[lane] = -1;
+        pending = 0;
+        wk.start(sc.n_nodes != 0, inv);
+        have = true;
+    };
+    auto push_term = [&](V3 ro, float tmax, V3 rd, int k, V3 w, uint32_t pixel) {
+        const int pos = atomicAdd(&ts.count, 1);
+        if (pos < kTermCap) {
+            ts.a[pos] = make_float4(ro.x, ro.y, ro.z, tmax);
+            ts.b[pos] = make_float4(rd.x, rd.y, rd.z, __int_as_float(k));
+            ts.c[pos] = make_float4(w.x, w.y, w.z, __uint_as_float(pixel));
+            return;
+        }
+        atomicSub(&ts.count, 1);                                 // stash full: trace it here (sequential rule, rare)
+        if (k == 1) {
+            const HitRec h = trace_one<1, WIDE>(sc, ro, rd, tmax);
+            n_sh++;
+            if (h.slot < 0) accum_add(accum, pixel, w);
+        } else {
+            const HitRec h = trace_one<0, WIDE>(sc, ro, rd, FLT_MAX);
+            n_pr++;
+            probe_resolve(sc, h.slot, w, pixel, accum);
+        }
+    };
     for (;;) {
-        const uint32_t i = atomicAdd(&c->fetch_tail, 1u);
-        if (i >= n) break;
-        const float4 qo = q_o[i], qd = q_d[i], qT = q_T[i];
-        PathState ps;
-        ps.o = mk3(qo); ps.d = mk3(qd); ps.T = mk3(qT);
-        ps.pixel = __float_as_uint(qo.w); ps.sample = __float_as_uint(qd.w); ps.meta = __float_as_uint(qT.w);
-        ps.pdf = EST == CRT_ESTIMATOR_MIS ? q_pdf[i] : 0.0f;
-        ProbeState pr;
-        pr.o = pr.d = pr.w = mk3(0.0f, 0.0f, 0.0f);
-        if (EST == CRT_ESTIMATOR_COMPAT && (ps.meta & kFlagProbe)) { pr.o = mk3(pr_o[i]); pr.d = mk3(pr_d[i]); pr.w = mk3(pr_w[i]); }
-        for (;;) {
-            const HitRec h = trace_one<0, WIDE>(sc, ps.o, ps.d, FLT_MAX);
-            n_ext++;
-            if (h.slot < 0) break;
-            if (EST == CRT_ESTIMATOR_COMPAT && (ps.meta & kFlagProbe)) {
-                const HitRec ph = trace_one<0, WIDE>(sc, pr.o, pr.d, FLT_MAX);
-                n_pr++;
-                probe_resolve(sc, ph.slot, pr.w, ps.pixel, accum);
+        // A. node steps; leaves go to the queue
+        wk.steps(sc, q, stack, o, inv, tlimit * 1.0001f, zray, lane, lt_mask, pending);
+        // B. flush the leaf queue
+        const unsigned walking = __ballot_sync(kFull, wk.walking());
+        __syncwarp();
+        const int q_count = wk.queued(q);
+        if (q_count >= Walker::kFlush || (walking == 0 && q_count > 0)) {
+            flush_leaf_queue<2>(sc, q, q_count, lane);
+            wk.reset_queue(q, lane);
+            pending = 0;
+            if (have) {
+                const unsigned long long b = q.best[lane];
+                if (kind != 1) tlimit = __uint_as_float((uint32_t)(b >> 32));
+                else if (b != kNoHitKey) wk.stop();
             }
-            PathState nx;
-            ProbeState npr;
-            const uint32_t pixel = ps.pixel;
-            auto shadow = [&](bool needs_trace, V3 pos, float tmax, V3 dir, V3 contrib) {
-                if (!needs_trace) return;
-                const HitRec b = trace_one<1, WIDE>(sc, pos, dir, tmax);
+            __syncwarp();
+        }
+        // C. finished rays
+        if (have && !wk.walking() && pending == 0) {
+            const unsigned long long b = q.best[lane];
+            const bool hit = b != kNoHitKey;
+            have = false;
+            if (kind == 1) {
                 n_sh++;
-                if (b.slot < 0) accum_add(accum, pixel, contrib);
-            };
-            bool alive;
-            if (EST == CRT_ESTIMATOR_MIS) alive = shade_vertex_mis(sc, p, ps, h.t, h.slot, accum, shadow, nx);
-            else alive = shade_vertex_compat(sc, p, ps, h.t, h.slot, accum, shadow, nx, npr);
-            if (!alive) break;
-            ps = nx;
-            if (EST == CRT_ESTIMATOR_COMPAT && (nx.meta & kFlagProbe)) pr = npr;
+                if (!hit) { const float4 cc = s_term[tid]; accum_add(accum, __float_as_uint(cc.w), mk3(cc)); }
+            } else if (kind == 2) {
+                n_pr++;
+                const float4 cc = s_term[tid];
+                probe_resolve(sc, hit ? q.best_slot[lane] : -1, mk3(cc), __float_as_uint(cc.w), accum);
+            } else {
+                n_ext++;
+                if (hit) { needs_shade = true; sh_t = __uint_as_float((uint32_t)(b >> 32)); sh_slot = q.best_slot[lane]; }
+            }
+        }
+        // C2. vertices: shaded when enough lanes have one (the statement is long: a lane or two at a time would cost the
+        // warp as many instructions as a full one), or when they have waited kShadeWait turns
+        {
+            const unsigned ns = __ballot_sync(kFull, needs_shade);
+            if (ns) {
+                // ... or when a quarter of the paths this warp still has are waiting (late in the frame a warp holds a handful)
+                const int live = __popc(__ballot_sync(kFull, needs_shade || parked || (have && kind == 0)));
+                if (__popc(ns) >= kShadeBatch || 4 * __popc(ns) >= live || shade_wait >= kShadeWait) {
+                    shade_wait = 0;
+                    if (needs_shade) {
+                        needs_shade = false;
+                        PathState ps;
+                        ps.o = mk3(q.ox[lane], q.oy[lane], q.oz[lane]);
+                        ps.d = mk3(q.dx[lane], q.dy[lane], q.dz[lane]);
+                        ps.T = mk3(s_pay[kPayT][tid], s_pay[kPayT + 1][tid], s_pay[kPayT + 2][tid]);
+                        ps.pixel = __float_as_uint(s_pay[kPayPixel][tid]);
+                        ps.sample = __float_as_uint(s_pay[kPaySample][tid]);
+                        ps.meta = __float_as_uint(s_pay[kPayMeta][tid]);
+                        ps.pdf = s_pay[kPayPdf][tid];
+                        const uint32_t pixel = ps.pixel;
+                        if (EST == CRT_ESTIMATOR_COMPAT && (ps.meta & kFlagProbe))     // the pending probe of the previous vertex, Render.cuh:303
+                            push_term(ps.o, FLT_MAX, mk3(s_pay[kPayPd][tid], s_pay[kPayPd + 1][tid], s_pay[kPayPd + 2][tid]), 2,
+                                      mk3(s_pay[kPayPw][tid], s_pay[kPayPw + 1][tid], s_pay[kPayPw + 2][tid]), pixel);
+                        auto shadow = [&](bool needs_trace, V3 pos, float tmax, V3 dir, V3 contrib) {
+                            if (needs_trace) push_term(pos, tmax, dir, 1, contrib, pixel);
+                        };
+                        PathState nx;
+                        ProbeState npr;
+                        bool alive;
+                        if (EST == CRT_ESTIMATOR_MIS) alive = shade_vertex_mis(sc, p, ps, sh_t, sh_slot, accum, shadow, nx);
+                        else alive = shade_vertex_compat(sc, p, ps, sh_t, sh_slot, accum, shadow, nx, npr);
+                        if (alive) {
+                            s_pay[kPayT][tid] = nx.T.x; s_pay[kPayT + 1][tid] = nx.T.y; s_pay[kPayT + 2][tid] = nx.T.z;
+                            s_pay[kPayMeta][tid] = __uint_as_float(nx.meta);
+                            if (EST == CRT_ESTIMATOR_MIS) s_pay[kPayPdf][tid] = nx.pdf;
+                            if (EST == CRT_ESTIMATOR_COMPAT && (nx.meta & kFlagProbe)) {
+                                s_pay[kPayPd][tid] = npr.d.x; s_pay[kPayPd + 1][tid] = npr.d.y; s_pay[kPayPd + 2][tid] = npr.d.z;
+                                s_pay[kPayPw][tid] = npr.w.x; s_pay[kPayPw + 1][tid] = npr.w.y; s_pay[kPayPw + 2][tid] = npr.w.z;
+                            }
+                            s_pay[kPayO][tid] = nx.o.x; s_pay[kPayO + 1][tid] = nx.o.y; s_pay[kPayO + 2][tid] = nx.o.z;
+                            s_pay[kPayD][tid] = nx.d.x; s_pay[kPayD + 1][tid] = nx.d.y; s_pay[kPayD + 2][tid] = nx.d.z;
+                            parked = true;
+                        }
+                    }
+                } else {
+                    ++shade_wait;
+                }
+            }
+        }
+        // D. idle lanes: a stash entry, else the parked continuation, else a new path
+        __syncwarp();
+        const int t_cnt = ts.count;
+        const bool idle_me = !have && !needs_shade;
+        const unsigned idle = __ballot_sync(kFull, idle_me);
+        if (idle) {
+            bool got = false;
+            const bool want_t = idle_me && (!parked || t_cnt >= kTermHigh);
+            const unsigned wt = __ballot_sync(kFull, want_t);
+            const int take_t = min(__popc(wt), t_cnt);
+            if (want_t && __popc(wt & lt_mask) < take_t) {
+                const int e = t_cnt - 1 - __popc(wt & lt_mask);
+                const float4 a = ts.a[e], b = ts.b[e];
+                s_term[tid] = ts.c[e];
+                arm(mk3(a), mk3(b), a.w, __float_as_int(b.w));
+                got = true;
+            }
+            __syncwarp();
+            if (lane == 0 && take_t) ts.count = t_cnt - take_t;
+            if (idle_me && !got && parked) {
+                parked = false;
+                arm(mk3(s_pay[kPayO][tid], s_pay[kPayO + 1][tid], s_pay[kPayO + 2][tid]),
+                    mk3(s_pay[kPayD][tid], s_pay[kPayD + 1][tid], s_pay[kPayD + 2][tid]), FLT_MAX, 0);
+                got = true;
+            }
+            const bool fresh_me = idle_me && !got;
+            const unsigned fresh = __ballot_sync(kFull, fresh_me);
+            if (fresh && !rf.drained()) {
+                uint32_t first = 0;
+                const uint32_t got_n = rf.take(&c->fetch_tail, n, lane, (uint32_t)__popc(fresh), first);
+                const uint32_t rank = (uint32_t)__popc(fresh & lt_mask);
+                if (fresh_me && rank < got_n) {
+                    const uint32_t i = first + rank;
+                    const float4 qo = q_o[i], qd = q_d[i], qT = q_T[i];
+                    s_pay[kPayT][tid] = qT.x; s_pay[kPayT + 1][tid] = qT.y; s_pay[kPayT + 2][tid] = qT.z;
+                    s_pay[kPayPixel][tid] = qo.w; s_pay[kPaySample][tid] = qd.w; s_pay[kPayMeta][tid] = qT.w;
+                    s_pay[kPayPdf][tid] = EST == CRT_ESTIMATOR_MIS ? q_pdf[i] : 0.0f;
+                    if (EST == CRT_ESTIMATOR_COMPAT && (__float_as_uint(qT.w) & kFlagProbe)) {
+                        const float4 pd = pr_d[i], pw = pr_w[i];
+                        s_pay[kPayPd][tid] = pd.x; s_pay[kPayPd + 1][tid] = pd.y; s_pay[kPayPd + 2][tid] = pd.z;
+                        s_pay[kPayPw][tid] = pw.x; s_pay[kPayPw + 1][tid] = pw.y; s_pay[kPayPw + 2][tid] = pw.z;
+                    }
+                    arm(mk3(qo), mk3(qd), FLT_MAX, 0);
+                }
+            }
+            __syncwarp();
+            // nothing in flight, nothing parked or waiting to be shaded, nothing stashed, no path left in the queue
+            if (!__any_sync(kFull, have || parked || needs_shade) && ts.count == 0 && rf.drained()) break;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        n_ext += __shfl_down_sync(0xffffffffu, n_ext, o);
-        n_sh += __shfl_down_sync(0xffffffffu, n_sh, o);
-        n_pr += __shfl_down_sync(0xffffffffu, n_pr, o);
+    for (int off = 16; off > 0; off >>= 1) {
+        n_ext += __shfl_down_sync(kFull, n_ext, off);
+        n_sh += __shfl_down_sync(kFull, n_sh, off);
+        n_pr += __shfl_down_sync(kFull, n_pr, off);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (n_ext) atomicAdd(&c->stat_extend, n_ext);
         if (n_sh) atomicAdd(&c->stat_shadow, n_sh);
         if (n_pr) atomicAdd(&c->stat_probe, n_pr);
@@ -814,11 +1164,6 @@ __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters
         },
         [&](uint32_t i, const HitRec& h) {
             if (h.slot < 0) { const float4 cc = s_contrib[threadIdx.x]; accum_add(accum, __float_as_uint(cc.w), mk3(cc)); }
-        },
-        [&](uint32_t first, uint32_t count) {
-            prefetch_l2(sh_o, first, count, 16u, threadIdx.x & 31);
-            prefetch_l2(sh_d, first, count, 16u, threadIdx.x & 31);
-            prefetch_l2(sh_c, first, count, 16u, threadIdx.x & 31);
         });
 }
 
@@ -845,12 +1190,6 @@ int resolve_device(const long long* d_accum, uint32_t n_pixels, uint32_t spp, fl
 // =============================================================================================
 // host driver
 // =============================================================================================
-static uint32_t env_u32(const char* name, uint32_t dflt) {
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    return (uint32_t)strtoul(v, nullptr, 0);
-}
-
 #ifdef CRT_EXP_SORT
 #include "experiments/exp_sort.cuh"   // ray-ordering experiment, not part of the product build
 #endif
@@ -947,8 +1286,13 @@ void wavefront_destroy(Wavefront* w) {
 
 long long* wavefront_accum(Wavefront* w) { return w->accum; }
 
-int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
-                     float tan_half, cudaStream_t st, crt_render_stats* stats) {
+// A run_view is a small state machine - begin (reset + first settings), step (the host side of ONE wavefront iteration,
+// optionally without blocking), finish (drain + statistics) - so that one host thread can drive the renders of several
+// GPUs at once (crt_group, crt_api.cu); wavefront_render below is the blocking single-GPU composition.
+int wavefront_begin(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
+                    float tan_half, cudaStream_t st) {
+    WfRun& r = w->run;
+    if (r.active) { set_error("run_view: a render is already in flight on this handle"); return CRT_ERR_STATE; }
     if (rs.estimator != CRT_ESTIMATOR_COMPAT && rs.estimator != CRT_ESTIMATOR_MIS) { set_error("unknown estimator"); return CRT_ERR_INVALID; }
     const bool mis = rs.estimator == CRT_ESTIMATOR_MIS;
     const size_t npix = (size_t)w->width * w->height;
@@ -957,7 +1301,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     const unsigned long long w_end = rs.range_set ? std::min(rs.work_end, work_all) : work_all;
     int rc = ensure_pool(w, ds, rs, w_end > w_begin ? w_end - w_begin : 0);
     if (rc != CRT_OK) return rc;
-    RenderParamsDev p;
+    RenderParamsDev& p = r.p;
     memcpy(p.eye, eye, sizeof(p.eye));
     memcpy(p.M, M, sizeof(p.M));
     p.tan_half = tan_half;
@@ -967,7 +1311,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     p.w_begin = w_begin;
     p.tile_px = p.tile_s0 = p.tile_S = 0;
     {
-        const uint32_t tile_px = env_u32("CRT_TILE_PX", 1u << 21);    // 48 MB of accumulation buffer per tile
+        const uint32_t tile_px = env_u32("CRT_TILE_PX", 1u << 20);    // 24 MB of accumulation buffer per tile (4K: 2^22 2465, 2^21 2658, 2^20 2724, 2^19 2743 Msamples/s, r02_s08)
         if (tile_px && npix > tile_px && w_end > w_begin && w_begin % npix == 0 && w_end % npix == 0) {
             p.tile_px = tile_px;
             p.tile_s0 = (uint32_t)(w_begin / npix);
@@ -983,32 +1327,66 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
     CRT_CUDA(cudaEventRecord(w->ev_begin, st));
     if (!rs.accumulate) CRT_CUDA(cudaMemsetAsync(w->accum, 0, sizeof(long long) * 3 * npix, st));
     CRT_CUDA(cudaMemcpyAsync(w->counters, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-    const SceneView sv = ds.view();
-    const bool wide = ds.wide;
-    uint64_t launches = 0;
-    float ms_stage[5] = {0, 0, 0, 0, 0};
-    cudaEvent_t se[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    const uint32_t tail_max = rs.stage_timing ? 0u : env_u32("CRT_TAIL", kTailDefault);
-    if (rs.stage_timing) for (auto& e : se) cudaEventCreate(&e);
+    r.ds = &ds; r.rs = rs; r.st = st; r.mis = mis; r.w_begin = w_begin;
+    r.sv = ds.view();
+    r.wide = ds.wide;
+    r.launches = 0;
+    for (float& m : r.ms_stage) m = 0;
+    r.tail_max = rs.stage_timing ? 0u : env_u32("CRT_TAIL", kTailDefault);
+    if (rs.stage_timing) for (auto& e : r.se) cudaEventCreate(&e);
     // CRT_OVERLAP (default on): k_shadow of iteration k runs on a second stream beside k_prepare, k_generate and k_extend
     // of iteration k + 1 (it only adds to the accumulation buffer; its counters are indexed by iteration parity), so the
     // drain of one persistent kernel is filled by the start of the next. k_shade(k + 1) waits for it (one shadow queue).
-    const bool overlap = !rs.stage_timing && env_u32("CRT_OVERLAP", 1) != 0;
-    if (overlap && !w->st_shadow) {
+    r.overlap = !rs.stage_timing && env_u32("CRT_OVERLAP", 1) != 0 && env_u32("CRT_TIMELINE", 0) == 0;
+    if (r.overlap && !w->st_shadow) {
         CRT_CUDA(cudaStreamCreateWithFlags(&w->st_shadow, cudaStreamNonBlocking));
         CRT_CUDA(cudaEventCreateWithFlags(&w->ev_shaded, cudaEventDisableTiming));
         CRT_CUDA(cudaEventCreateWithFlags(&w->ev_shadowed, cudaEventDisableTiming));
     }
-    uint32_t it = 0;
-    for (;; ++it) {
+    // CRT_TIMELINE=1 (profiling aid): an event behind every launch of the frame, printed to stderr at the end - the
+    // real schedule (tail kernel and host polling included), one stream
+    r.timeline = env_u32("CRT_TIMELINE", 0) != 0 && !rs.stage_timing;
+    r.tl.clear();
+    r.mark("begin", st);
+    r.it = 0;
+    r.active = true;
+    return CRT_OK;
+}
+
+// The host keeps two iterations in flight: iteration `it` is enqueued once iteration it - 2 has finished and did not report
+// the end of the frame. block == false: returns with *progressed == false instead of waiting for that event.
+int wavefront_step(Wavefront* w, bool block, bool* done, bool* progressed) {
+    WfRun& r = w->run;
+    const DeviceScene& ds = *r.ds;
+    const RenderSettings& rs = r.rs;
+    const RenderParamsDev& p = r.p;
+    const SceneView& sv = r.sv;
+    cudaStream_t st = r.st;
+    const bool wide = r.wide, mis = r.mis, overlap = r.overlap;
+    const uint32_t tail_max = r.tail_max, it = r.it;
+    uint64_t& launches = r.launches;
+    float* ms_stage = r.ms_stage;
+    cudaEvent_t* se = r.se;
+    auto mark = [&](const char* what, cudaStream_t s) { r.mark(what, s); };
+    (void)ds;
+    *done = false;
+    if (progressed) *progressed = false;
+    {
         if (it >= 2) {
-            CRT_CUDA(cudaEventSynchronize(w->ev[(it - 2) & 3]));
-            if (w->status_host->done) break;
+            if (block) CRT_CUDA(cudaEventSynchronize(w->ev[(it - 2) & 3]));
+            else {
+                cudaError_t q = cudaEventQuery(w->ev[(it - 2) & 3]);
+                if (q == cudaErrorNotReady) return CRT_OK;
+                if (q != cudaSuccess) return cuda_fail(q, "cudaEventQuery");
+            }
+            if (w->status_host->done) { *done = true; if (progressed) *progressed = true; return CRT_OK; }
         }
         const int cur = it & 1, nxt = cur ^ 1;
         k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, tail_max, w->status_dev, cur);
+        mark("prepare", st);
         if (rs.stage_timing) cudaEventRecord(se[0], st);
         k_generate<<<w->grid_shade, 256, 0, st>>>(w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], mis ? w->q_pdf[cur] : nullptr);
+        mark("generate", st);
         if (rs.stage_timing) cudaEventRecord(se[1], st);
         if (wide) k_extend<true><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->q_o[cur], w->q_d[cur], w->hit_t, w->hit_slot);
         else k_extend<false><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->q_o[cur], w->q_d[cur], w->hit_t, w->hit_slot);
@@ -1018,6 +1396,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
             else k_probe<false><<<w->grid_trace, 128, 0, st>>>(sv, w->counters, w->pr_list[cur], w->pr_o[cur], w->pr_d[cur], w->hit_slot, w->pr_hit);
             launches++;
         }
+        mark("extend", st);
         if (rs.stage_timing) cudaEventRecord(se[2], st);
         if (overlap && it > 0) CRT_CUDA(cudaStreamWaitEvent(st, w->ev_shadowed, 0));      // k_shadow(it - 1) still reads the shadow queue
         if (mis)
@@ -1033,6 +1412,7 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
 #ifdef CRT_EXP_SORT
         exp_sort(ds, w->counters, 1, w->sh_o, w->sh_d, w->sh_c, w->shadow_cap, st);
 #endif
+        mark("shade", st);
         if (rs.stage_timing) cudaEventRecord(se[3], st);
         cudaStream_t ss = st;
         if (overlap) {
@@ -1043,16 +1423,18 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         if (wide) k_shadow<true><<<w->grid_trace, 128, 0, ss>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
         else k_shadow<false><<<w->grid_trace, 128, 0, ss>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
         if (overlap) CRT_CUDA(cudaEventRecord(w->ev_shadowed, ss));
+        mark("shadow", st);
         if (rs.stage_timing) cudaEventRecord(se[4], st);
 #ifdef CRT_EXP_SORT
         exp_sort(ds, w->counters, 0, w->q_o[nxt], w->q_d[nxt], w->q_T[nxt], w->pool, st);
 #endif
 #define CRT_TAIL_LAUNCH(EST, W)                                                                                              \
-    k_tail<EST, W><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur], w->pr_o[cur], \
-                                                 w->pr_d[cur], w->pr_w[cur], w->accum)
+    k_tail<EST, W><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur], w->pr_d[cur], \
+                                                 w->pr_w[cur], w->accum)
         if (mis) { if (wide) CRT_TAIL_LAUNCH(CRT_ESTIMATOR_MIS, true); else CRT_TAIL_LAUNCH(CRT_ESTIMATOR_MIS, false); }
         else { if (wide) CRT_TAIL_LAUNCH(CRT_ESTIMATOR_COMPAT, true); else CRT_TAIL_LAUNCH(CRT_ESTIMATOR_COMPAT, false); }
 #undef CRT_TAIL_LAUNCH
+        mark("tail", st);
         launches += 3;
         if (rs.stage_timing) {
             cudaEventRecord(se[5], st);
@@ -1062,10 +1444,38 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         CRT_CUDA(cudaEventRecord(w->ev[it & 3], st));
         CRT_CUDA(cudaGetLastError());
     }
+    r.it = it + 1;
+    if (progressed) *progressed = true;
+    return CRT_OK;
+}
+
+int wavefront_finish(Wavefront* w, crt_render_stats* stats) {
+    WfRun& r = w->run;
+    const RenderSettings& rs = r.rs;
+    cudaStream_t st = r.st;
+    const bool overlap = r.overlap, timeline = r.timeline;
+    const uint32_t it = r.it;
+    const unsigned long long w_begin = r.w_begin;
+    const uint64_t launches = r.launches;
+    float* ms_stage = r.ms_stage;
+    cudaEvent_t* se = r.se;
+    auto& tl = r.tl;
+    Counters h;
+    r.active = false;
     if (overlap && it > 0) CRT_CUDA(cudaStreamWaitEvent(st, w->ev_shadowed, 0));
     CRT_CUDA(cudaEventRecord(w->ev_end, st));
     CRT_CUDA(cudaStreamSynchronize(st));
-    if (rs.stage_timing) for (auto& e : se) cudaEventDestroy(e);
+    if (rs.stage_timing) for (int k = 0; k < 6; ++k) cudaEventDestroy(se[k]);
+    if (timeline) {
+        float t0 = 0;
+        for (size_t k = 1; k < tl.size(); ++k) {
+            float ms = 0, at = 0;
+            cudaEventElapsedTime(&ms, tl[k - 1].second, tl[k].second);
+            cudaEventElapsedTime(&at, tl[0].second, tl[k].second);
+            fprintf(stderr, "timeline %8.1f us  +%7.1f us  %s\n", at * 1e3f, ms * 1e3f, tl[k].first);
+        }
+        for (auto& e : tl) cudaEventDestroy(e.second);
+    }
     if (stats) {
         CRT_CUDA(cudaMemcpy(&h, w->counters, sizeof(h), cudaMemcpyDeviceToHost));
         memset(stats, 0, sizeof(*stats));
@@ -1080,6 +1490,17 @@ int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& 
         stats->ms_tail = ms_stage[4];
     }
     return CRT_OK;
+}
+
+int wavefront_render(Wavefront* w, const DeviceScene& ds, const RenderSettings& rs, const float eye[3], const float M[9],
+                     float tan_half, cudaStream_t st, crt_render_stats* stats) {
+    int rc = wavefront_begin(w, ds, rs, eye, M, tan_half, st);
+    if (rc != CRT_OK) return rc;
+    for (bool done = false; !done;) {
+        rc = wavefront_step(w, true, &done, nullptr);
+        if (rc != CRT_OK) { w->run.active = false; return rc; }
+    }
+    return wavefront_finish(w, stats);
 }
 
 }  // namespace crt

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CRT_ABI_VERSION 1
+#define CRT_ABI_VERSION 2
 
 typedef enum crt_status {
     CRT_OK = 0,
@@ -223,6 +223,27 @@ int crt_render_get_stats(crt_render* r, crt_render_stats* out);
 int crt_render_set_stage_timing(crt_render* r, int on);
 /* Render::free, include/Render.cuh:477-487 */
 int crt_render_destroy(crt_render* r);
+
+/* ---- several GPUs of one box behind one handle ------------------------------------------- */
+/* The reference renders on device 0 only (src/main.cu:99-100). A crt_group is Render::Render + run_view for N GPUs driven
+ * by the calling thread: the scene `s` must be built on devices[0]; every other device gets a
+ * device-to-device replica of the built scene (no second parse or build), GPU g renders a contiguous share of the sample-major
+ * work index space (whole samples when spp >= N, pixel ranges of a sample otherwise) on its own stream, the int64
+ * accumulation buffers are summed onto devices[0] with one ncclReduce (the NCCL library is loaded when a group of more than
+ * one GPU is created: libnccl.so.2, or the file CRT_NCCL_LIB names) and resolved there. The buffer, and therefore the frame,
+ * is bit-identical for every N. Not thread-safe; the scene must outlive the group. */
+typedef struct crt_group crt_group;
+int crt_group_create(crt_scene* s, uint32_t width, uint32_t height, const int* devices, uint32_t n_devices, crt_group** out);
+/* Render::set_spp / set_P_RR / set_light_sample_n (include/Render.cuh:543-556) + seed and estimator, for every GPU of the group */
+int crt_group_set_params(crt_group* g, uint32_t spp, float p_rr, uint32_t light_sample_n, uint32_t seed, int estimator);
+/* Render::run_view (include/Render.cuh:435-475). Blocking; the reduced buffer is left on devices[0]. */
+int crt_group_run_view(crt_group* g, const float eye[3], const float inv_view[9], float fovy_rad);
+int crt_group_get_accum_i64(crt_group* g, int64_t* out);
+int crt_group_get_rgb8(crt_group* g, uint8_t* out);
+int crt_group_save_png(crt_group* g, const char* path);
+/* Statistics of GPU `index` (0 .. n_devices-1) for the last run_view; reduce_ms (optional) = CUDA-event time of the ncclReduce. */
+int crt_group_get_stats(crt_group* g, uint32_t index, crt_render_stats* out, float* reduce_ms);
+int crt_group_destroy(crt_group* g);
 
 /* PNG writer used by save_png, exposed for the host tools: rgb8 is width*height*3, top row first. 8-bit RGB, filter 0,
  * scanline bands of about 1 MB deflated on all host threads; the file depends on the image only. */

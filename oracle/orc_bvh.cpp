@@ -721,13 +721,15 @@ Hit wide8_intersect(const Scene& s, const Wide8BVH& b, const Ray& r, int mode, T
         if (!(fay <= FLT_MAX)) fay = 0.0f;
         if (!(faz <= FLT_MAX)) faz = 0.0f;
         // plane distance t = q b + a evaluated as fma(32768 + q, b, a - 32768 b): the GPU gets 32768 + q from one PRMT
-        // (crt_wide.cuh wide_biased); pad = 2^-21 max|a| + 2^-7 max|b| covers the roundings (the folded bias: 2^-9 |b|)
-        float fbx = fabsf(bx), fby = fabsf(by), fbz = fabsf(bz);
-        if (!(fbx <= FLT_MAX)) fbx = 0.0f;
-        if (!(fby <= FLT_MAX)) fby = 0.0f;
-        if (!(fbz <= FLT_MAX)) fbz = 0.0f;
-        const float pad = fmaf(fmaxf(fmaxf(fbx, fby), fbz), 0.0078125f, fmaxf(fmaxf(fax, fay), faz) * 4.76837158203125e-07f);
+        // (crt_wide.cuh wide_biased). The folded bias costs one more rounding, 2^-9 |b| on the distances of ITS axis:
+        // near planes are taken e = 2^-7 |b| earlier, far planes later; pad = 2^-21 max|a| as before.
+        const float pad = fmaxf(fmaxf(fax, fay), faz) * 4.76837158203125e-07f;     // 2^-21
+        float ex = fabsf(bx) * 0.0078125f, ey = fabsf(by) * 0.0078125f, ez = fabsf(bz) * 0.0078125f;
+        if (!(ex <= FLT_MAX)) ex = 0.0f;
+        if (!(ey <= FLT_MAX)) ey = 0.0f;
+        if (!(ez <= FLT_MAX)) ez = 0.0f;
         const float a2x = fmaf(-32768.0f, bx, ax), a2y = fmaf(-32768.0f, by, ay), a2z = fmaf(-32768.0f, bz, az);
+        const float anx = a2x - ex, any_ = a2y - ey, anz = a2z - ez, afx = a2x + ex, afy = a2y + ey, afz = a2z + ez;
         const float lim = tlimit * 1.0001f;
         const uint8_t* bytes = (const uint8_t*)nd.w;
         const uint8_t* meta = bytes + 24;
@@ -740,9 +742,9 @@ Hit wide8_intersect(const Scene& s, const Wide8BVH& b, const Ray& r, int mode, T
         uint32_t node_hits = 0, leaf_hits = 0;                  // priority space
         for (uint32_t c = 0; c < 8; ++c) {
             if (meta[c] == 0) continue;
-            const float tnx = fmaf(32768.0f + (float)qnx[c], bx, a2x), tfx = fmaf(32768.0f + (float)qfx[c], bx, a2x);
-            const float tny = fmaf(32768.0f + (float)qny[c], by, a2y), tfy = fmaf(32768.0f + (float)qfy[c], by, a2y);
-            const float tnz = fmaf(32768.0f + (float)qnz[c], bz, a2z), tfz = fmaf(32768.0f + (float)qfz[c], bz, a2z);
+            const float tnx = fmaf(32768.0f + (float)qnx[c], bx, anx), tfx = fmaf(32768.0f + (float)qfx[c], bx, afx);
+            const float tny = fmaf(32768.0f + (float)qny[c], by, any_), tfy = fmaf(32768.0f + (float)qfy[c], by, afy);
+            const float tnz = fmaf(32768.0f + (float)qnz[c], bz, anz), tfz = fmaf(32768.0f + (float)qfz[c], bz, afz);
             const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, lim));
             if (tmin <= fmaf(tmax, kSlabSlack, pad)) {

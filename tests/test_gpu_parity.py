@@ -499,3 +499,49 @@ def test_error_paths_on_gpu(gpu):
     R0 = gpu.Render(e0, 4, 4)
     R0.run_view([0, 0, 0], np.eye(3, dtype=np.float32).reshape(9), 0.5)
     assert not R0.get_accum_i64().any()
+
+
+def test_c3_size_frame_equals_the_oracle(gpu, orc, scene_files, monkeypatch):
+    """The benchmarked configuration at its own size: cornell-box 3840x2160, builder ploc8, 2^25 paths in flight (the pool
+    a C3 frame runs with), camera paths started tile by tile (whole samples, frame larger than a tile) - two samples per
+    pixel of it, every value of the 199 MB fixed-point buffer equal to the oracle's."""
+    monkeypatch.setenv("CRT_POOL", str(1 << 25))
+    cfg = gpu.load_config(scene_files["cornell-box"]["cfg_path"])
+    a = gpu.Scene().add_obj(scene_files["cornell-box"]["obj"], scene_files["cornell-box"]["dir"])
+    a.set_BVH(cfg.bvh_thresh_n, builder=3)
+    b = orc.Scene().add_obj(scene_files["cornell-box"]["obj"], scene_files["cornell-box"]["dir"])
+    b.build_new_bvh(cfg.bvh_thresh_n, 2)
+    b.build_wide8(cfg.bvh_thresh_n, 3)
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    W, H, spp = 3840, 2160, 2
+    R = gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n)
+    R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+    acc, st = R.get_accum_i64(), R.stats()
+    oacc, ost = b.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 0, spp, cfg.P_RR, cfg.light_sample_n, wide=True)
+    assert np.array_equal(acc, oacc), "%d values differ" % int((acc != oacc).sum())
+    assert (st["extend_rays"], st["shadow_rays"]) == (ost["extend_rays"], ost["shadow_rays"]) and st["samples"] == W * H * spp
+    # a band of rows of one sample (a work range that is not whole samples: sample-major order) adds up with the rest
+    R.set_work_range(1000 * W, 1064 * W); R.run_view(cfg.eye_pos, M, cfg.fovy_rad); band = R.get_accum_i64()
+    assert band.reshape(H, W, 3)[:1000].any() == False and band.reshape(H, W, 3)[1064:].any() == False and band.any()
+    R.set_work_range(0, 1000 * W); R.run_view(cfg.eye_pos, M, cfg.fovy_rad); band += R.get_accum_i64()
+    R.set_work_range(1064 * W, W * H * spp); R.run_view(cfg.eye_pos, M, cfg.fovy_rad); band += R.get_accum_i64()
+    assert np.array_equal(band, oacc)
+
+
+@pytest.mark.parametrize("tile_px", ["0", "1000", "4096", "47999", "48000"])
+def test_tile_order_does_not_change_the_buffer(gpu, orc, scene_files, monkeypatch, tile_px):
+    """k_generate may start the work items of whole-sample ranges tile by tile (CRT_TILE_PX pixels per tile, last tile
+    ragged): any order gives the same integer buffer."""
+    monkeypatch.setenv("CRT_TILE_PX", tile_px)
+    monkeypatch.setenv("CRT_POOL", "16384")
+    cfg, a, b = _pair(gpu, orc, scene_files, "veach-mis")
+    M = gpu.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
+    W, H, spp = 240, 200, 3
+    R = gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n)
+    R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+    oacc, ost = b.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 0, spp, cfg.P_RR, cfg.light_sample_n)
+    assert np.array_equal(R.get_accum_i64(), oacc) and R.stats()["extend_rays"] == ost["extend_rays"]
+    R.set_sample_range(1, 3)
+    R.run_view(cfg.eye_pos, M, cfg.fovy_rad)
+    oacc, _ = b.render(cfg.eye_pos, M, float(cfg.fovy_rad), W, H, 1, 3, cfg.P_RR, cfg.light_sample_n)
+    assert np.array_equal(R.get_accum_i64(), oacc)

@@ -128,3 +128,70 @@ def test_c4_full_size_properties(gpu):
     R.set_sample_range(1, 4); R.run_view(c["eye"], M, math.radians(c["fov_y"])); part = part + R.get_accum_i64()
     assert np.array_equal(full, part) and full.any()
     print("C4 full: %d triangles, %d nodes, GPU build %.1f ms" % (n, len(nodes), ms))
+
+
+def test_c4_full_size_rays_equal_the_oracle(gpu, orc):
+    """The full 10M-triangle scene, builder ploc8 (the bench default): 200k of the C5 rays, closest-hit (t bits, face id)
+    and any-hit decisions, against the oracle's traversal of its own CPU build of the same tree; and a crop of the C4
+    frame (work range of the sample-major index space) against the oracle's buffer rows."""
+    import torch
+    from tools import synthetic as sy
+    verts, mat, obj, mats = sy.c4_scene(sy.C4_FULL_N)
+    a = gpu.Scene().add_triangles(verts, mat, obj, mats)
+    a.set_BVH(2, builder=3)
+    b = orc.Scene().add_arrays(verts, mat.astype(np.int32), obj.astype(np.int32), mats)
+    b.build_new_bvh(2, 2)
+    b.build_wide8(2, 3)
+    n = 200000
+    for any_hit in (False, True):
+        d_rays = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+        a.random_rays_device(d_rays.data_ptr(), n, start=0, key=0xC5, any_hit=any_hit)
+        d_t, d_f = torch.empty(n, dtype=torch.float32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+        mode = gpu.RAY_ANY if any_hit else gpu.RAY_CLOSEST
+        a.trace_rays_device(d_rays.data_ptr(), n, mode, d_t.data_ptr(), d_f.data_ptr())
+        rays, t, f = d_rays.cpu().numpy(), d_t.cpu().numpy(), d_f.cpu().numpy()
+        if any_hit:
+            assert b.check_any_hits(rays, t, f) and 0.3 < (f >= 0).mean() < 0.9
+        else:
+            ot, of = b.trace(rays, which=4, mode=0)
+            assert np.array_equal(f, of) and np.array_equal(t.view(np.uint32), ot.view(np.uint32)) and (f >= 0).mean() > 0.5
+            ht, hf, _ = a.trace_rays(rays, gpu.RAY_CLOSEST)            # the host-buffer entry point (chunked pipeline) gives the same
+            assert np.array_equal(hf, of) and np.array_equal(ht.view(np.uint32), ot.view(np.uint32))
+    c = sy.C4_CAMERA
+    M = gpu.inverse_view_matrix(c["eye"], c["lookat"], c["up"])
+    W, H = 480, 270
+    R = gpu.Render(a, W, H, 2, c["P_RR"], c["light_sample_n"])
+    R.run_view(c["eye"], M, math.radians(c["fov_y"]))
+    oacc, ost = b.render(c["eye"], M, math.radians(c["fov_y"]), W, H, 0, 2, c["P_RR"], c["light_sample_n"], wide=True)
+    assert np.array_equal(R.get_accum_i64(), oacc) and oacc.any()
+
+
+def test_host_buffer_batches_are_chunked_and_exact(gpu, orc, monkeypatch):
+    """crt_trace_rays with host buffers runs in chunks on two streams (CRT_BATCH_CHUNK rays each): many small chunks, a
+    ragged last one, pageable and page-locked caller buffers all give the device-buffer result."""
+    import torch
+    from tools import synthetic as sy
+    monkeypatch.setenv("CRT_BATCH_CHUNK", "4096")
+    verts, mat, obj, mats = sy.c4_scene(65)
+    a = gpu.Scene().add_triangles(verts, mat, obj, mats)
+    a.set_BVH(2, builder=3)
+    n = 4096 * 5 + 123
+    d_rays = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    a.random_rays_device(d_rays.data_ptr(), n, start=7, key=0xC5, any_hit=True)
+    d_t, d_f = torch.empty(n, dtype=torch.float32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+    rays = d_rays.cpu().numpy()
+    for mode in (gpu.RAY_CLOSEST, gpu.RAY_ANY):
+        a.trace_rays_device(d_rays.data_ptr(), n, mode, d_t.data_ptr(), d_f.data_ptr())
+        want_t, want_f = d_t.cpu().numpy(), d_f.cpu().numpy()
+        t, f, ms = a.trace_rays(rays, mode)                               # pageable in, pageable out
+        assert ms > 0 and np.array_equal(f >= 0, want_f >= 0)
+        if mode == gpu.RAY_CLOSEST:
+            assert np.array_equal(f, want_f) and np.array_equal(t.view(np.uint32), want_t.view(np.uint32))
+        pin_rays = torch.from_numpy(rays).pin_memory()
+        pin_t, pin_f = torch.empty(n, dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory()
+        t2, f2, _ = a.trace_rays(pin_rays.numpy(), mode, out=(pin_t.numpy(), pin_f.numpy()))     # page-locked: DMA in place
+        assert np.array_equal(f2 >= 0, want_f >= 0)
+        if mode == gpu.RAY_CLOSEST:
+            assert np.array_equal(f2, want_f) and np.array_equal(t2.view(np.uint32), want_t.view(np.uint32))
+    t, f, _ = a.trace_rays(rays[:0], gpu.RAY_CLOSEST)
+    assert len(t) == 0

@@ -19,7 +19,7 @@ def test_cabi_exports_every_declared_symbol(crt):
     L = C.CDLL(crt.lib_path())
     for n in names:
         assert hasattr(L, n), "libcrt.so does not export " + n
-    assert L.crt_abi_version() == 1
+    assert L.crt_abi_version() == 2          # 2: crt_group (several GPUs behind one handle)
 
 
 def test_no_gpu_means_loud_failure_not_fallback(crt):

@@ -70,6 +70,32 @@ def c4_scene(n=C4_FULL_N, seed=0x5EED):
     return verts, mat, obj, mats
 
 
+def _sincos_2pi_vec(u):
+    """Vectorised sincos_2pi (crt_device.cuh) for large n: fmaf is emulated in float64 (exact product, the sum rounded
+    twice), so a direction may differ from the device's in the last bit on rare inputs. Used for the timing baselines
+    of the reference arm only; the parity tests use the exact scalar statement (n <= 200000)."""
+    f32 = np.float32
+    def fma(a, b, c):
+        return (a.astype(np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(f32)
+    u = u.astype(f32)
+    q = fma(u, f32(4.0), f32(0.5)).astype(np.int32)
+    x = ((u - q.astype(f32) * f32(0.25)) * f32(6.2831855)).astype(f32)
+    x2 = (x * x).astype(f32)
+    ps = fma(x2, f32(2.7557319e-06), f32(-1.9841270e-04))
+    ps = fma(ps, x2, f32(8.3333333e-03))
+    ps = fma(ps, x2, f32(-1.6666667e-01))
+    ss = fma((x * x2).astype(f32), ps, x)
+    pc = fma(x2, f32(-2.7557319e-07), f32(2.4801587e-05))
+    pc = fma(pc, x2, f32(-1.3888889e-03))
+    pc = fma(pc, x2, f32(4.1666667e-02))
+    pc = fma(pc, x2, f32(-0.5))
+    cc = fma(pc, x2, f32(1.0))
+    k = q & 3
+    s = np.where(k == 0, ss, np.where(k == 1, cc, np.where(k == 2, -ss, -cc)))
+    c = np.where(k == 0, cc, np.where(k == 1, -ss, np.where(k == 2, -cc, ss)))
+    return np.stack([s, c], axis=1).astype(f32)
+
+
 def random_rays(lo, hi, n, key=0xC5, any_hit=False, start=0):
     """numpy statement of crt_random_rays_device: n x 8 float32 {o, tmax, d, 0}."""
     idx = np.arange(start, start + n, dtype=np.uint64)
@@ -83,10 +109,11 @@ def random_rays(lo, hi, n, key=0xC5, any_hit=False, start=0):
         r[:, k] = lo[k] + (hi[k] - lo[k]) * u01(a[k])
     z = np.float32(1.0) - np.float32(2.0) * u01(a[3])
     rad = np.sqrt(np.maximum(np.float32(0.0), np.float32(1.0) - z * z)).astype(np.float32)
-    from oracle import orc
-    sc = np.array([orc.sincos_2pi(float(u)) for u in u01(b[0])], np.float32) if n <= 200000 else None
-    if sc is None:
-        raise ValueError("random_rays: numpy statement is for small n")
+    if n <= 200000:
+        from oracle import orc
+        sc = np.array([orc.sincos_2pi(float(u)) for u in u01(b[0])], np.float32)
+    else:
+        sc = _sincos_2pi_vec(u01(b[0]))
     r[:, 4], r[:, 5], r[:, 6] = rad * sc[:, 1], rad * sc[:, 0], z
     diag = np.float32(np.sqrt(np.sum((hi - lo).astype(np.float64) ** 2)))
     r[:, 3] = u01(b[1]) * diag if any_hit else np.finfo(np.float32).max
