@@ -57,7 +57,7 @@ assert BVH8_NODE.itemsize == 80
 
 
 def lib_path():
-    # CRT_LIB: development override used by tools/variant_bench.py to compare kernel variants
+    # CRT_LIB: development override (tools/build_variant.sh) to compare kernel variants in one GPU session
     return os.environ.get("CRT_LIB") or os.path.join(_HERE, "libcrt.so")
 
 

@@ -48,6 +48,13 @@ CRT_DEV V3 normalize(V3 a) {
     return a;
 }
 CRT_DEV float length(V3 a) { return sqrtf(dot(a, a)); }
+// Shading only: one IEEE division and three products instead of three divisions (a division is ~9 instructions; the compat
+// vertex had 38 of them, a third of k_shade's instructions, profiles/r02_s15.md). Statement: oracle/orc_math.h normalize_rcp.
+CRT_DEV V3 normalize_rcp(V3 a) {
+    float n = dot(a, a);
+    if (n > 0.0f) return a * (1.0f / sqrtf(n));
+    return a;
+}
 
 // ---- Philox4x32-10 (Salmon et al., SC'11). Replaces curand XORWOW + clock() seed
 // (reference Global.h:52-55,106-109; Render.cuh:340-341).
@@ -144,7 +151,7 @@ struct SceneView {
     const float4* __restrict__ nodes;       // 4 x 16 B per node (crt_bvh_node)
     const float4* __restrict__ tri_geom;    // 3 x 16 B per slot: (v1, face|last) (e1, mat) (e2, 0)
     const float4* __restrict__ tri_shade;   // 1 x 16 B per slot: (normal, mat)
-    const float4* __restrict__ mats;        // 4 x 16 B per material, see MatRec
+    const float4* __restrict__ mats;        // 5 x 16 B per material: (kd, ns) (ke, flags) (probe lobe) (ks, pdf) (kd / pi)
     const float4* __restrict__ light_tris;  // 4 x 16 B per light triangle: (v1,ke.r) (v2,ke.g) (v3,ke.b) (n, 0)
     const int4* __restrict__ lights;        // per light object: (first light tri, count, area bits, 0)
     const float* __restrict__ light_cdf;    // mis estimator: CDF over light_tris, P ~ area * luminance(Ke)

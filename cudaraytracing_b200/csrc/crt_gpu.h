@@ -30,7 +30,7 @@ struct DeviceScene {
     float4* tri_shade = nullptr;    // n_tris, BVH slot order
     uint32_t* order = nullptr;      // slot -> face id
     uint8_t* last = nullptr;        // slot -> leaf terminator
-    float4* mats = nullptr;         // n_mats * 4
+    float4* mats = nullptr;         // n_mats * 5
     float4* light_tris = nullptr;   // n_light_tris * 4
     int4* lights = nullptr;         // n_lights
     float* light_cdf = nullptr;     // n_light_tris (mis estimator)

@@ -66,7 +66,7 @@ int clone_scene(const DeviceScene& src, int device, DeviceScene& dst) {
     if ((rc = copy(dst.tri_shade, src.tri_shade, sizeof(float4) * (size_t)src.n_tris)) != CRT_OK) return rc;
     if ((rc = copy(dst.order, src.order, sizeof(uint32_t) * (size_t)src.n_tris)) != CRT_OK) return rc;
     if ((rc = copy(dst.last, src.last, (size_t)src.n_tris)) != CRT_OK) return rc;
-    if ((rc = copy(dst.mats, src.mats, sizeof(float4) * 4 * (size_t)src.n_mats)) != CRT_OK) return rc;
+    if ((rc = copy(dst.mats, src.mats, sizeof(float4) * 5 * (size_t)src.n_mats)) != CRT_OK) return rc;
     if ((rc = copy(dst.light_tris, src.light_tris, sizeof(float4) * 4 * (size_t)src.n_light_tris)) != CRT_OK) return rc;
     if ((rc = copy(dst.lights, src.lights, sizeof(int4) * (size_t)src.n_lights)) != CRT_OK) return rc;
     if ((rc = copy(dst.light_cdf, src.light_cdf, sizeof(float) * (size_t)src.n_light_tris)) != CRT_OK) return rc;
@@ -87,17 +87,19 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device
     ds.device = device;
     const size_t n = hs.n_tris();
     if (n > 0x7fffffffu / 4) { set_error("scene too large (more than 2^29 triangles)"); return CRT_ERR_INVALID; }
-    // materials: (kd, ns) (ke, flags) (probe_dtheta, probe_dphi, probe_shin, 0) (ks, mis light-sampling density per area)
-    std::vector<float4> mats(hs.mats.size() * 4);
+    // materials: (kd, ns) (ke, flags) (probe_dtheta, probe_dphi, probe_shin, 0) (ks, mis light-sampling density per area) (kd / pi, 0)
+    std::vector<float4> mats(hs.mats.size() * 5);
     ds.has_specular = false;
     for (size_t m = 0; m < hs.mats.size(); ++m) {
         const HostMaterial& hm = hs.mats[m];
         uint32_t flags = (hm.has_emit ? 1u : 0u) | (hm.mode == 1 ? 2u : 0u);
         if (hm.mode == 1 && !hm.has_emit) ds.has_specular = true;
-        mats[4 * m + 0] = make_float4(hm.kd[0], hm.kd[1], hm.kd[2], hm.ns);
-        mats[4 * m + 1] = make_float4(hm.ke[0], hm.ke[1], hm.ke[2], bits_f(flags));
-        mats[4 * m + 2] = make_float4(hm.probe_dtheta, hm.probe_dphi, hm.probe_shin, 0.0f);
-        mats[4 * m + 3] = make_float4(hm.ks[0], hm.ks[1], hm.ks[2], hm.pdf_area);
+        const float kPiF = 3.14159265358979323846f;
+        mats[5 * m + 0] = make_float4(hm.kd[0], hm.kd[1], hm.kd[2], hm.ns);
+        mats[5 * m + 1] = make_float4(hm.ke[0], hm.ke[1], hm.ke[2], bits_f(flags));
+        mats[5 * m + 2] = make_float4(hm.probe_dtheta, hm.probe_dphi, hm.probe_shin, 0.0f);
+        mats[5 * m + 3] = make_float4(hm.ks[0], hm.ks[1], hm.ks[2], hm.pdf_area);
+        mats[5 * m + 4] = make_float4(hm.kd[0] / kPiF, hm.kd[1] / kPiF, hm.kd[2] / kPiF, 0.0f);     // kd / pi (Render.cuh:259), one IEEE division each
     }
     // lights (DeviceLights.cuh:63-87): object table + flat triangle table
     std::vector<int4> lights;
@@ -420,6 +422,7 @@ struct RenderParamsDev {
     uint32_t width, height;
     unsigned long long n_pixels;
     uint32_t s_begin;
+    float two_pi_over_p_rr;                     // 2 pi / P_RR, divided once on the host (Render.cuh:288-293)
     // Order in which the work items of this run_view are started (any order gives the same buffer). tile_px > 0: the
     // range is whole samples [tile_s0, tile_s0 + tile_S) and is walked tile by tile - all its samples of pixels
     // [0, tile_px), then of the next tile_px pixels ... - so that the part of the accumulation buffer the paths in flight
@@ -647,7 +650,7 @@ CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, 
     const float lsn_f = (float)p.light_sample_n;
     const float4 sh = __ldg(sc.tri_shade + slot);
     const uint32_t mat = __float_as_uint(sh.w);
-    const float4 m0 = __ldg(sc.mats + 4 * mat + 0), m1 = __ldg(sc.mats + 4 * mat + 1);
+    const float4 m0 = __ldg(sc.mats + 5 * mat + 0), m1 = __ldg(sc.mats + 5 * mat + 1);
     const uint32_t mflags = __float_as_uint(m1.w);
     if (mflags & 1u) {                                          // emissive vertex, :210,249-255
         if (bounce == 0) accum_add(accum, pixel, mk3(m1));
@@ -656,7 +659,7 @@ CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, 
     const V3 o = ps.o, d = ps.d, T = ps.T;
     const V3 pos = o + t * d;                                   // DeviceTriangle.cuh:50
     const V3 nrm = mk3(sh);
-    const V3 f_r = mk3(m0) / kPi;                               // :259
+    const V3 f_r = mk3(__ldg(sc.mats + 5 * mat + 4));           // kd / pi, :259 (divided once per material on the host)
     const V3 Tf = cmul(T, f_r);
     // next-event estimation, :262-286
     for (int li = 0; li < sc.n_lights; ++li) {
@@ -671,12 +674,12 @@ CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, 
             float gamma = (1.0f - alpha) - beta;
             V3 lp = (alpha * mk3(a) + beta * mk3(b)) + gamma * mk3(cc);
             V3 dist = lp - pos;
-            V3 dir = normalize(dist);
+            V3 dir = normalize(dist);                           // the reference's operation sequence: its shadow test is rounding-dependent
             float d1 = length(dist);
             float d2 = d1 * d1;
             float cos1 = fmaxf(0.0f, dot(dir, nrm));
             float cos2 = fmaxf(0.0f, -dot(dir, mk3(ln)));
-            V3 contrib = cmul(mk3(a.w, b.w, cc.w), Tf) * cos1 * cos2 * area / d2 / lsn_f;     // :274-283
+            V3 contrib = cmul(mk3(a.w, b.w, cc.w), Tf) * (((cos1 * cos2) * area) / d2 / lsn_f);     // :274-283
             bool live = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);
             float t_to_light = dist.x / dir.x;                  // :272
             bool needs_trace = live && (t_to_light == t_to_light);
@@ -687,14 +690,14 @@ CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, 
     if (bounce == (uint32_t)(p.max_vertices - 1)) return false;  // bounce stack full, :210
     const uint4 q = draw(pixel, sample, bounce, 0, p.seed);
     if (u01(q.x) > p.p_rr) return false;                         // :216-221
-    V3 wdir = normalize(normalize(sample_hemisphere(nrm, u01(q.y), u01(q.z))));   // :225-227 + Ray ctor
+    V3 wdir = normalize_rcp(normalize_rcp(sample_hemisphere(nrm, u01(q.y), u01(q.z))));   // :225-227 + Ray ctor
     uint32_t nmeta = bounce + 1u;
     if (mflags & 2u) {                                          // SPECULAR probe, :294-303
-        const float4 m2 = __ldg(sc.mats + 4 * mat + 2);
-        V3 in = normalize(d);
+        const float4 m2 = __ldg(sc.mats + 5 * mat + 2);
+        V3 in = normalize_rcp(d);
         V3 out = in - (2.0f * dot(in, nrm)) * nrm;
         uint4 e = draw(pixel, sample, bounce, 1, p.seed);
-        V3 pd = normalize(normalize(sample_probe_lobe(out, m2.x, m2.y, u01(e.x), u01(e.y))));
+        V3 pd = normalize_rcp(normalize_rcp(sample_probe_lobe(out, m2.x, m2.y, u01(e.x), u01(e.y))));
         float pc = fmaxf(0.0f, dot(pd, nrm));
         npr.o = pos;
         npr.d = pd;
@@ -704,7 +707,7 @@ CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, 
     float cosn = fmaxf(0.0f, dot(wdir, nrm));
     nx.o = pos;
     nx.d = wdir;
-    nx.T = Tf * cosn * kTwoPi / p.p_rr;                         // :288-293
+    nx.T = Tf * (cosn * p.two_pi_over_p_rr);                    // :288-293
     nx.pixel = pixel; nx.sample = sample; nx.meta = nmeta;
     return true;
 }
@@ -720,8 +723,7 @@ CRT_DEV int pick_light(const float* __restrict__ cdf, int n, float u) {
     }
     return lo;
 }
-CRT_DEV void phong_eval(V3 kd, V3 ks, float ns, float pd, bool has_spec, float cos_s, float ca, V3* f, float* pdf) {
-    const V3 fd = kd / kPi;
+CRT_DEV void phong_eval(V3 fd /* kd / pi */, V3 ks, float ns, float pd, bool has_spec, float cos_s, float ca, V3* f, float* pdf) {
     const float pdf_d = cos_s / kPi;
     if (has_spec) {
         const float pw = det_pow(ca, ns);
@@ -741,7 +743,7 @@ CRT_DEV bool shade_vertex_mis(const SceneView& sc, const RenderParamsDev& p, con
     const float lsn_f = (float)p.light_sample_n;
     const float4 sh = __ldg(sc.tri_shade + slot);
     const uint32_t mat = __float_as_uint(sh.w);
-    const float4 m0 = __ldg(sc.mats + 4 * mat + 0), m1 = __ldg(sc.mats + 4 * mat + 1), m3 = __ldg(sc.mats + 4 * mat + 3);
+    const float4 m0 = __ldg(sc.mats + 5 * mat + 0), m1 = __ldg(sc.mats + 5 * mat + 1), m3 = __ldg(sc.mats + 5 * mat + 3);
     const V3 n = mk3(sh), d = ps.d, T = ps.T;
     const float dn = dot(n, d);
     if (__float_as_uint(m1.w) & 1u) {                            // emitter: seen from its front side only
@@ -762,8 +764,8 @@ CRT_DEV bool shade_vertex_mis(const SceneView& sc, const RenderParamsDev& p, con
     const float off = 1.0e-4f * (1.0f + fmaxf(fmaxf(fabsf(pos.x), fabsf(pos.y)), fabsf(pos.z)));
     const V3 org = pos + off * ns;
     const float cos_o = dot(ns, wo);
-    const V3 refl = normalize((2.0f * cos_o) * ns - wo);
-    const V3 kd = mk3(m0), ks = mk3(m3);
+    const V3 refl = normalize_rcp((2.0f * cos_o) * ns - wo);
+    const V3 kd = mk3(m0), ks = mk3(m3), kd_pi = mk3(__ldg(sc.mats + 5 * mat + 4));
     const float mns = m0.w;
     const float lkd = lumf(kd), lks = lumf(ks);
     const float lsum = lkd + lks;
@@ -782,7 +784,7 @@ CRT_DEV bool shade_vertex_mis(const SceneView& sc, const RenderParamsDev& p, con
         const V3 dist = lp - org;
         const float d2 = dot(dist, dist);
         const float d1 = sqrtf(d2);
-        const V3 wi = dist / d1;
+        const V3 wi = dist * (1.0f / d1);
         const float cos_s = dot(ns, wi);
         const float cos_l = -dot(mk3(ln), wi);
         bool needs_trace = cos_s > 0.0f && cos_l > 0.0f;
@@ -791,7 +793,7 @@ CRT_DEV bool shade_vertex_mis(const SceneView& sc, const RenderParamsDev& p, con
             const float ca = fmaxf(0.0f, dot(refl, wi));
             V3 f;
             float pb;
-            phong_eval(kd, ks, mns, pd, has_spec, cos_s, ca, &f, &pb);
+            phong_eval(kd_pi, ks, mns, pd, has_spec, cos_s, ca, &f, &pb);
             const float pl = ln.w * d2 / cos_l;
             const float pls = lsn_f * pl;
             const float w = (pls * pls) / fmaf(pls, pls, pb * pb);
@@ -816,13 +818,13 @@ CRT_DEV bool shade_vertex_mis(const SceneView& sc, const RenderParamsDev& p, con
         const float sa0 = sqrtf(fmaxf(0.0f, 1.0f - ca0 * ca0));
         wi = to_world(mk3(sa0 * cs, sa0 * sn, ca0), refl);
     }
-    wi = normalize(wi);
+    wi = normalize_rcp(wi);
     const float cos_s = dot(ns, wi);
     if (!(cos_s > 0.0f)) return false;
     const float ca = fmaxf(0.0f, dot(refl, wi));
     V3 f;
     float pb;
-    phong_eval(kd, ks, mns, pd, has_spec, cos_s, ca, &f, &pb);
+    phong_eval(kd_pi, ks, mns, pd, has_spec, cos_s, ca, &f, &pb);
     if (!(pb > 0.0f)) return false;
     nx.o = org;
     nx.d = wi;
@@ -836,7 +838,7 @@ CRT_DEV bool shade_vertex_mis(const SceneView& sc, const RenderParamsDev& p, con
 CRT_DEV void probe_resolve(const SceneView& sc, int probe_slot, V3 w, uint32_t pixel, long long* __restrict__ accum) {
     if (probe_slot < 0) return;
     const uint32_t pm = __float_as_uint(__ldg(sc.tri_shade + probe_slot).w);
-    const float4 m1 = __ldg(sc.mats + 4 * pm + 1);
+    const float4 m1 = __ldg(sc.mats + 5 * pm + 1);
     if (__float_as_uint(m1.w) & 1u) accum_add(accum, pixel, cmul(w, mk3(m1)));
 }
 
@@ -981,25 +983,14 @@ __global__ void __launch_bounds__(128, CRT_TAIL_MINB) k_tail(SceneView sc, Count
         wk.start(sc.n_nodes != 0, inv);
         have = true;
     };
+    // room for every push is reserved before a lane shades (C2), so the stash cannot overflow
     auto push_term = [&](V3 ro, float tmax, V3 rd, int k, V3 w, uint32_t pixel) {
         const int pos = atomicAdd(&ts.count, 1);
-        if (pos < kTermCap) {
-            ts.a[pos] = make_float4(ro.x, ro.y, ro.z, tmax);
-            ts.b[pos] = make_float4(rd.x, rd.y, rd.z, __int_as_float(k));
-            ts.c[pos] = make_float4(w.x, w.y, w.z, __uint_as_float(pixel));
-            return;
-        }
-        atomicSub(&ts.count, 1);                                 // stash full: trace it here (sequential rule, rare)
-        if (k == 1) {
-            const HitRec h = trace_one<1, WIDE>(sc, ro, rd, tmax);
-            n_sh++;
-            if (h.slot < 0) accum_add(accum, pixel, w);
-        } else {
-            const HitRec h = trace_one<0, WIDE>(sc, ro, rd, FLT_MAX);
-            n_pr++;
-            probe_resolve(sc, h.slot, w, pixel, accum);
-        }
+        ts.a[pos] = make_float4(ro.x, ro.y, ro.z, tmax);
+        ts.b[pos] = make_float4(rd.x, rd.y, rd.z, __int_as_float(k));
+        ts.c[pos] = make_float4(w.x, w.y, w.z, __uint_as_float(pixel));
     };
+    const int per_vertex = sc.n_lights * p.light_sample_n + 1;       // shadow rays + the probe a vertex can push (EST mis: light_sample_n + 0)
     for (;;) {
         // A. node steps; leaves go to the queue
         wk.steps(sc, q, stack, o, inv, tlimit * 1.0001f, zray, lane, lt_mask, pending);
@@ -1032,23 +1023,29 @@ __global__ void __launch_bounds__(128, CRT_TAIL_MINB) k_tail(SceneView sc, Count
                 probe_resolve(sc, hit ? q.best_slot[lane] : -1, mk3(cc), __float_as_uint(cc.w), accum);
             } else {
                 n_ext++;
-                if (hit) { needs_shade = true; sh_t = __uint_as_float((uint32_t)(b >> 32)); sh_slot = q.best_slot[lane]; }
+                if (hit) {                                        // the ray is kept for the shading turn: the lane may trace stash entries meanwhile
+                    needs_shade = true; sh_t = __uint_as_float((uint32_t)(b >> 32)); sh_slot = q.best_slot[lane];
+                    s_pay[kPayO][tid] = q.ox[lane]; s_pay[kPayO + 1][tid] = q.oy[lane]; s_pay[kPayO + 2][tid] = q.oz[lane];
+                    s_pay[kPayD][tid] = q.dx[lane]; s_pay[kPayD + 1][tid] = q.dy[lane]; s_pay[kPayD + 2][tid] = q.dz[lane];
+                }
             }
         }
         // C2. vertices: shaded when enough lanes have one (the statement is long: a lane or two at a time would cost the
         // warp as many instructions as a full one), or when they have waited kShadeWait turns
         {
-            const unsigned ns = __ballot_sync(kFull, needs_shade);
+            const unsigned ns = __ballot_sync(kFull, needs_shade && !have);
             if (ns) {
                 // ... or when a quarter of the paths this warp still has are waiting (late in the frame a warp holds a handful)
                 const int live = __popc(__ballot_sync(kFull, needs_shade || parked || (have && kind == 0)));
-                if (__popc(ns) >= kShadeBatch || 4 * __popc(ns) >= live || shade_wait >= kShadeWait) {
+                // as many lanes shade as the stash has room for all they can push; the others wait (and trace stash entries meanwhile)
+                const int allowed = (kTermCap - ts.count) / per_vertex;
+                if (allowed > 0 && (__popc(ns) >= kShadeBatch || 4 * __popc(ns) >= live || shade_wait >= kShadeWait)) {
                     shade_wait = 0;
-                    if (needs_shade) {
+                    if (needs_shade && !have && __popc(ns & lt_mask) < allowed) {
                         needs_shade = false;
                         PathState ps;
-                        ps.o = mk3(q.ox[lane], q.oy[lane], q.oz[lane]);
-                        ps.d = mk3(q.dx[lane], q.dy[lane], q.dz[lane]);
+                        ps.o = mk3(s_pay[kPayO][tid], s_pay[kPayO + 1][tid], s_pay[kPayO + 2][tid]);
+                        ps.d = mk3(s_pay[kPayD][tid], s_pay[kPayD + 1][tid], s_pay[kPayD + 2][tid]);
                         ps.T = mk3(s_pay[kPayT][tid], s_pay[kPayT + 1][tid], s_pay[kPayT + 2][tid]);
                         ps.pixel = __float_as_uint(s_pay[kPayPixel][tid]);
                         ps.sample = __float_as_uint(s_pay[kPaySample][tid]);
@@ -1088,10 +1085,10 @@ __global__ void __launch_bounds__(128, CRT_TAIL_MINB) k_tail(SceneView sc, Count
         __syncwarp();
         const int t_cnt = ts.count;
         const bool idle_me = !have && !needs_shade;
-        const unsigned idle = __ballot_sync(kFull, idle_me);
+        const unsigned idle = __ballot_sync(kFull, !have);
         if (idle) {
             bool got = false;
-            const bool want_t = idle_me && (!parked || t_cnt >= kTermHigh);
+            const bool want_t = !have && (needs_shade || !parked || t_cnt >= kTermHigh);
             const unsigned wt = __ballot_sync(kFull, want_t);
             const int take_t = min(__popc(wt), t_cnt);
             if (want_t && __popc(wt & lt_mask) < take_t) {
@@ -1190,10 +1187,6 @@ int resolve_device(const long long* d_accum, uint32_t n_pixels, uint32_t spp, fl
 // =============================================================================================
 // host driver
 // =============================================================================================
-#ifdef CRT_EXP_SORT
-#include "experiments/exp_sort.cuh"   // ray-ordering experiment, not part of the product build
-#endif
-
 int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wavefront** out) {
     Wavefront* w = new Wavefront();
     w->width = width; w->height = height;
@@ -1306,6 +1299,7 @@ int wavefront_begin(Wavefront* w, const DeviceScene& ds, const RenderSettings& r
     memcpy(p.M, M, sizeof(p.M));
     p.tan_half = tan_half;
     p.width = w->width; p.height = w->height; p.n_pixels = npix;
+    p.two_pi_over_p_rr = kTwoPi / rs.p_rr;
     p.s_begin = 0; p.p_rr = rs.p_rr; p.light_sample_n = (int)rs.light_sample_n; p.seed = rs.seed;
     p.max_vertices = 64;                                           // BOUNCE_STACK_SIZE, Global.h:18
     p.w_begin = w_begin;
@@ -1333,6 +1327,9 @@ int wavefront_begin(Wavefront* w, const DeviceScene& ds, const RenderSettings& r
     r.launches = 0;
     for (float& m : r.ms_stage) m = 0;
     r.tail_max = rs.stage_timing ? 0u : env_u32("CRT_TAIL", kTailDefault);
+    // the tail path tracer reserves stash room for every ray a vertex can push; a scene whose vertices push more than half the
+    // stash (lights x light_sample_n + 1) finishes with wavefront iterations instead
+    if ((uint64_t)std::max<uint32_t>(ds.n_lights, 1) * rs.light_sample_n + 1 > (uint64_t)kTermCap / 2) r.tail_max = 0;
     if (rs.stage_timing) for (auto& e : r.se) cudaEventCreate(&e);
     // CRT_OVERLAP (default on): k_shadow of iteration k runs on a second stream beside k_prepare, k_generate and k_extend
     // of iteration k + 1 (it only adds to the accumulation buffer; its counters are indexed by iteration parity), so the
@@ -1409,9 +1406,6 @@ int wavefront_step(Wavefront* w, bool block, bool* done, bool* progressed) {
                                                                           w->q_pdf[nxt], w->hit_t, w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt],
                                                                           w->q_d[nxt], w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
                                                                           w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
-#ifdef CRT_EXP_SORT
-        exp_sort(ds, w->counters, 1, w->sh_o, w->sh_d, w->sh_c, w->shadow_cap, st);
-#endif
         mark("shade", st);
         if (rs.stage_timing) cudaEventRecord(se[3], st);
         cudaStream_t ss = st;
@@ -1425,9 +1419,6 @@ int wavefront_step(Wavefront* w, bool block, bool* done, bool* progressed) {
         if (overlap) CRT_CUDA(cudaEventRecord(w->ev_shadowed, ss));
         mark("shadow", st);
         if (rs.stage_timing) cudaEventRecord(se[4], st);
-#ifdef CRT_EXP_SORT
-        exp_sort(ds, w->counters, 0, w->q_o[nxt], w->q_d[nxt], w->q_T[nxt], w->pool, st);
-#endif
 #define CRT_TAIL_LAUNCH(EST, W)                                                                                              \
     k_tail<EST, W><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur], w->pr_d[cur], \
                                                  w->pr_w[cur], w->accum)

@@ -45,6 +45,13 @@ static inline V3 normalize(V3 a) {
     return a;
 }
 static inline float length(V3 a) { return sqrtf(dot(a, a)); }
+// Shading only (crt_device.cuh normalize_rcp): one division and three products instead of three divisions. The camera rays
+// and everything pinned against the reference's host code keep normalize().
+static inline V3 normalize_rcp(V3 a) {
+    float n = dot(a, a);
+    if (n > 0.0f) return a * (1.0f / sqrtf(n));
+    return a;
+}
 // Inverse direction for the box tests of the new traversal rules: 1/d, NaN for a component that is exactly zero, so
 // that this axis never culls (NaN plane distances drop out of fminf / fmaxf). With 1/0 = inf a ray lying in a box plane
 // made the pair-node slab empty (min(0 * inf, +inf) = +inf) and boxes were dropped whose triangles pass the triangle

@@ -163,13 +163,17 @@ static void path_compat(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sam
                 float gamma = (1.0f - alpha) - beta;
                 V3 lp = (alpha * lt.v1 + beta * lt.v2) + gamma * lt.v3;
                 V3 dist = lp - pos;
+                // dir, t_to_light and the shadow ray's direction keep the reference's operation sequence (three divisions each):
+                // its shadow test compares t_to_light - t with an absolute 1e-5 at t ~ 400 (Render.cuh:19-27,272), so how often the
+                // light occludes its own samples depends on these roundings (with dist * (1 / d1) the converged cornell-box image
+                // left the stated RMSE, r02_s16)
                 V3 dir = normalize(dist);
                 float d1 = length(dist);
                 float d2 = d1 * d1;
                 float cos1 = fmaxf(0.0f, dot(dir, n));
                 float cos2 = fmaxf(0.0f, -dot(dir, lt.normal));
                 const Material& lm = s.mats[lt.mat];
-                V3 contrib = cmul(lm.ke, Tf) * cos1 * cos2 * L.area / d2 / lsn_f;   // :274-283
+                V3 contrib = cmul(lm.ke, Tf) * (((cos1 * cos2) * L.area) / d2 / lsn_f);   // :274-283, the scalar factor first
                 // a sample that cannot contribute needs no visibility test (the reference traces it anyway)
                 if (contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f) continue;
                 float t_to_light = dist.x / dir.x;                        // :272
@@ -185,12 +189,12 @@ static void path_compat(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sam
         if (bnc == p.max_vertices - 1) break;                             // bounce stack full, :210
         U4 q = draw(pixel, sample, (uint32_t)bnc, 0, p.seed);
         if (u01(q.x) > p.p_rr) break;                                     // :216-221
-        V3 wdir = normalize(normalize(sample_hemisphere(n, u01(q.y), u01(q.z))));   // :225-227 + Ray ctor
+        V3 wdir = normalize_rcp(normalize_rcp(sample_hemisphere(n, u01(q.y), u01(q.z))));   // :225-227 + Ray ctor
         if (m.mode == SPECULAR) {                                         // :294-303
-            V3 in = normalize(ray.d);
+            V3 in = normalize_rcp(ray.d);
             V3 out = in - (2.0f * dot(in, n)) * n;
             U4 e = draw(pixel, sample, (uint32_t)bnc, 1, p.seed);
-            V3 pd = normalize(normalize(sample_probe_lobe(out, m.probe_dtheta, m.probe_dphi, u01(e.x), u01(e.y))));
+            V3 pd = normalize_rcp(normalize_rcp(sample_probe_lobe(out, m.probe_dtheta, m.probe_dphi, u01(e.x), u01(e.y))));
             probe_ray = Ray{pos, pd, FLT_MAX};
             float pc = fmaxf(0.0f, dot(pd, n));
             // :306-312 : (0.5*log10(Ns)+1) * Ke (x) kd * cos * 2pi/8, carried with the path throughput
@@ -198,7 +202,7 @@ static void path_compat(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sam
             have_probe = true;
         }
         float cosn = fmaxf(0.0f, dot(wdir, n));
-        T = Tf * cosn * kTwoPi / p.p_rr;                                  // :288-293
+        T = Tf * (cosn * (kTwoPi / p.p_rr));                              // :288-293, the scalar factor first
         ray = Ray{pos, wdir, FLT_MAX};
     }
 }
@@ -278,7 +282,7 @@ static void path_mis(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sample
         float off = 1.0e-4f * (1.0f + fmaxf(fmaxf(fabsf(pos.x), fabsf(pos.y)), fabsf(pos.z)));
         V3 org = pos + off * ns;
         float cos_o = dot(ns, wo);
-        V3 refl = normalize((2.0f * cos_o) * ns - wo);
+        V3 refl = normalize_rcp((2.0f * cos_o) * ns - wo);
         float lkd = lumf(m.kd), lks = lumf(m.ks);
         float lsum = lkd + lks;
         if (!(lsum > 0.0f)) break;
@@ -296,7 +300,7 @@ static void path_mis(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sample
             V3 dist = lp - org;
             float d2 = dot(dist, dist);
             float d1 = sqrtf(d2);
-            V3 wi = dist / d1;
+            V3 wi = dist * (1.0f / d1);
             float cos_s = dot(ns, wi);
             float cos_l = -dot(lt.normal, wi);
             if (!(cos_s > 0.0f && cos_l > 0.0f)) continue;
@@ -333,7 +337,7 @@ static void path_mis(const Ctx& c, uint32_t pixel, int i, int j, uint32_t sample
             float sa0 = sqrtf(fmaxf(0.0f, 1.0f - ca0 * ca0));
             wi = to_world(V3{sa0 * cs, sa0 * sn, ca0}, refl);
         }
-        wi = normalize(wi);
+        wi = normalize_rcp(wi);
         float cos_s = dot(ns, wi);
         if (!(cos_s > 0.0f)) break;
         float ca = fmaxf(0.0f, dot(refl, wi));
