@@ -735,7 +735,22 @@ int crt_group_create(crt_scene* s, uint32_t width, uint32_t height, const int* d
         CRT_CUDA(cudaMalloc(&g->d_rgb8, 3 * (size_t)width * height));
         CRT_CUDA(cudaEventCreate(&g->ev_r0));
         CRT_CUDA(cudaEventCreate(&g->ev_r1));
-        if (n_devices > 1) CRT_NCCL(g_nccl.CommInitAll(g->comms.data(), (int)n_devices, devices));
+        if (n_devices > 1) {
+            CRT_NCCL(g_nccl.CommInitAll(g->comms.data(), (int)n_devices, devices));
+            // the first collective of a communicator sets up its connections (~0.2 s): spent here on the 24 bytes of pixel 0,
+            // not inside the first frame (the buffers are cleared at the start of every run_view)
+            CRT_NCCL(g_nccl.GroupStart());
+            for (uint32_t k = 0; k < n_devices; ++k) {
+                long long* acc = wavefront_accum(g->wf[k]);
+                CRT_NCCL(g_nccl.Reduce(acc, acc, 3, ncclInt64, ncclSum, 0, g->comms[k], g->streams[k]));
+            }
+            CRT_NCCL(g_nccl.GroupEnd());
+            for (uint32_t k = 0; k < n_devices; ++k) {
+                CRT_CUDA(cudaSetDevice(devices[k]));
+                CRT_CUDA(cudaStreamSynchronize(g->streams[k]));
+            }
+            CRT_CUDA(cudaSetDevice(devices[0]));
+        }
         return CRT_OK;
     };
     int rc = build();

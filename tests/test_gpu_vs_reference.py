@@ -23,16 +23,22 @@ def _box(img, k):
     return img[:h - h % k, :w - w % k].reshape(h // k, k, w // k, k, c).astype(np.float64).mean(axis=(1, 3))
 
 
-@pytest.mark.parametrize("name,rmse_max,rmse_box_max", [("cornell-box", 9.0, 3.0), ("veach-mis", 9.0, 3.0)])
-def test_converged_image_vs_reference_kernel(crt, ref_mod, scene_files, name, rmse_max, rmse_box_max):
+@pytest.mark.parametrize("name,rmse_max,rmse_box_max,ratio_tol", [("cornell-box", 8.5, 2.8, 0.015), ("veach-mis", 2.6, 0.45, 0.005)])
+def test_converged_image_vs_reference_kernel(crt, ref_mod, scene_files, name, rmse_max, rmse_box_max, ratio_tol):
     """North-star check 3: the converged `compat` image against a high-spp render of the reference's own
     view_render_kernel. Both are Monte-Carlo estimates with independent noise (the reference seeds with
     clock()), compared on the tone-mapped RGB8 frame, the only thing the reference exposes (Render.cuh:350).
-    Stated thresholds, in 8-bit code values: per-pixel RMSE <= 9 (noise of two independent 2048-spp renders
-    of an estimator with fireflies), RMSE after an 8x8 box filter <= 3 (what is left is systematic: the
-    reference's shadow test compares t_to_light - hit.t with an absolute 1e-5 at t ~ 400, Render.cuh:19-27,
-    so the light falsely occludes a rounding-dependent ~10 % of its own samples, and nvcc's FMA contraction
-    of the reference differs from the canonical arithmetic used here), mean brightness within 3 %."""
+    Thresholds in 8-bit code values at 2048 spp, from the spp ladder in profiles/r02_converged.md (256 ... 16384 spp,
+    both sides, with the noise floor from two of our own renders and two of the reference's):
+      veach-mis   per-pixel RMSE 2.85 (1024 spp) -> 1.44 (4096), 8x8-box RMSE 0.35 -> 0.19: pure noise, it keeps falling
+                  with spp down to 0.11 at 16384 where two of our own renders differ by 0.10; mean ratio 1.0005-1.0009;
+      cornell-box per-pixel RMSE 9.3 -> 5.9, 8x8-box RMSE 2.50 -> 2.39 -> 2.34: a bias floor of ~2.3 code values that does
+                  not fall with spp (noise floor 0.41 at 16384), mean ratio 1.004. It sits on the directly lit surfaces
+                  (RMS of the box residual 3.26 there, 1.13 elsewhere): the reference's shadow test compares
+                  t_to_light - hit.t with an absolute 1e-5 at t ~ 400 (Render.cuh:19-27,272), so the light's own
+                  triangles occlude a rounding-dependent share of its samples - 26 % on average, 12-56 % depending on
+                  where the shaded point is, with this repo's arithmetic - and nvcc's FMA contraction of the reference
+                  shifts that pattern by a few per cent of the direct light."""
     f = scene_files[name]
     cfg = crt.load_config(f["cfg_path"])
     W, H, spp = 240, 180, 2048
@@ -55,7 +61,7 @@ def test_converged_image_vs_reference_kernel(crt, ref_mod, scene_files, name, rm
     os.makedirs("gpurun_out", exist_ok=True)
     crt.write_png("gpurun_out/conv_%s_ours.png" % name, img)
     crt.write_png("gpurun_out/conv_%s_ref.png" % name, ref_img)
-    assert rmse <= rmse_max and rmse_box <= rmse_box_max and abs(ratio - 1.0) <= 0.03
+    assert rmse <= rmse_max and rmse_box <= rmse_box_max and abs(ratio - 1.0) <= ratio_tol
 
 
 @pytest.mark.parametrize("name", ["cornell-box", "veach-mis"])

@@ -17,7 +17,7 @@ def main():
         d = os.path.dirname(cfg_path)
         for b in builders:
             S = crt.Scene().add_obj(os.path.join(d, cfg.OBJ_paths[0][0]), d)
-            S.set_BVH(cfg.bvh_thresh_n, builder=B[b])
+            S.set_BVH(int(os.environ.get("QB_THRESH", cfg.bvh_thresh_n)), builder=B[b])
             M = crt.inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up)
             for est in (0, 1):
                 R = crt.Render(S, W, H, spp, cfg.P_RR, cfg.light_sample_n)
