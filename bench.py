@@ -190,10 +190,10 @@ def dist_env():
 # CPU baseline (oracle port) — bounded sample of the same workload; also yields the per-ray
 # node / triangle visit counts the roofline uses (counted by the oracle on the same BVH and rule).
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline_leg(cfg, budget_samples=float(os.environ.get("CRT_CPU_BUDGET", "4.0e7")), estimator=0):
+def cpu_baseline_leg(cfg, budget_samples=float(os.environ.get("CRT_CPU_BUDGET", "4.0e7")), estimator=0, oracle_scene=None):
     from oracle import orc
     import numpy as np
-    S = cfg.build_oracle(orc)
+    S = oracle_scene or cfg.build_oracle(orc)
     M = orc.inverse_view_matrix(cfg.eye, cfg.lookat, cfg.up)
     # bounded sample: the full frame at reduced resolution (same camera, same per-ray statistics), 1..spp samples
     scale = 1
@@ -279,7 +279,7 @@ class Ctx:
             self.torch.distributed.destroy_process_group()
 
 
-def render_workload(ctx, name, steps, warmup, estimator=0, headline=False, clocks=False):
+def render_workload(ctx, name, steps, warmup, estimator=0, headline=False, clocks=False, prebuilt=None):
     """One render workload (C1-C4) at ctx.world GPUs: device-timed value, e2e through the public API with host buffers,
     hashes of the reduced buffer and of the frame, per-kernel roofline (rank 0)."""
     import hashlib
@@ -287,9 +287,12 @@ def render_workload(ctx, name, steps, warmup, estimator=0, headline=False, clock
     import cudaraytracing_b200 as crt
     from cudaraytracing_b200 import distributed as cd
     torch = ctx.torch
-    cfg = Workload(name)
+    if prebuilt:                                              # (Workload, scene, build_ms): the C4 frame reuses the scene C5 has built
+        cfg, scene, build_ms = prebuilt[:3]
+    else:
+        cfg = Workload(name)
+        scene, build_ms = cfg.build_scene(crt, ctx.local)
     npix = cfg.width * cfg.height
-    scene, build_ms = cfg.build_scene(crt, ctx.local)
     M = crt.inverse_view_matrix(cfg.eye, cfg.lookat, cfg.up)
     render = crt.Render(scene, cfg.width, cfg.height, cfg.spp, cfg.P_RR, cfg.light_sample_n)
     render.set_seed(0)
@@ -351,7 +354,8 @@ def render_workload(ctx, name, steps, warmup, estimator=0, headline=False, clock
             out["clocks"] = clk
         # per-kernel roofline pass (stage timing on, bounded spp): CUDA events around every stage of this workload
         peaks, peak_kind = load_peaks()
-        cpu_base, per_ray = cpu_baseline_leg(cfg, estimator=estimator) if headline else cpu_baseline_leg(cfg, budget_samples=2.0e6, estimator=estimator)
+        cpu_base, per_ray = cpu_baseline_leg(cfg, estimator=estimator, oracle_scene=prebuilt[3] if prebuilt and len(prebuilt) > 3 else None) if headline \
+            else cpu_baseline_leg(cfg, budget_samples=2.0e6, estimator=estimator, oracle_scene=prebuilt[3] if prebuilt and len(prebuilt) > 3 else None)
         render.clear_range()
         spp_probe = min(cfg.spp, 16)
         render.set_spp(spp_probe)
@@ -415,7 +419,7 @@ def ours(args):
         subs["c1"] = render_workload(ctx, "c1", k, 3)
         subs["c2"] = render_workload(ctx, "c2", k, 3)
         subs["c2_mis"] = render_workload(ctx, "c2", k, 3, estimator=1)
-        subs["c5"] = c5_workload(ctx, max(1, min(args.steps, 3)), 3)
+        subs["c5"], subs["c4"] = c5_workload(ctx, max(1, min(args.steps, 3)), 3, with_c4=True)
     if ctx.rank == 0:
         out = {"metric": "Msamples/s", "value": main["value"], "unit": "Msamples/s", "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -682,7 +686,7 @@ def reference(args):
     print(json.dumps(out), flush=True)
 
 
-def c5_workload(ctx, steps, warmup, n_total=None):
+def c5_workload(ctx, steps, warmup, n_total=None, with_c4=False):
     """C5: 100M incoherent rays against the 10M-triangle BVH; closest-hit and any-hit Mrays/s with the rays resident in HBM, and
     the same through crt_trace_rays with HOST buffers (rays H2D, hits D2H inside the timed call). Rays are independent: they
     are sharded over the ranks, no collective."""
@@ -783,8 +787,15 @@ def c5_workload(ctx, steps, warmup, n_total=None):
             "cpu_baseline": {"value": round(len(sample) / cpu_dt / 1e6, 3), "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "%d of the same rays, oracle traversal, %.1f s" % (len(sample), cpu_dt)},
             "bvh_build_gpu_ms": round(build_ms, 3)}
-    del rays, t_out, f_out, scene
-    return out
+    del rays, t_out, f_out
+    c4 = None
+    if with_c4:
+        # C4: the 1920x1080 spp 64 frame of the same 10M-triangle scene (no second build of scene or oracle tree)
+        c4cfg = Workload("c4")
+        c4cfg._arrays = cfg._arrays
+        c4 = render_workload(ctx, "c4", max(1, min(steps, 3)), 2, prebuilt=(c4cfg, scene, build_ms) + ((O,) if ctx.rank == 0 else ()))
+    del scene
+    return (out, c4) if with_c4 else out
 
 
 def ours_c5(args):

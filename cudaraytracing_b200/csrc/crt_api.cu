@@ -14,6 +14,7 @@ struct crt_scene {
     HostScene host;
     DeviceScene dev;
     RayBatcher* batcher = nullptr;
+    uint32_t scene_hash = 0;            // identity of the built scene (checkpoints), 0 = not built
     bool built = false;
     uint32_t thresh_n = 0;
 };
@@ -38,7 +39,7 @@ struct CheckpointHeader {
     char magic[8];
     uint32_t width, height, spp, seed, estimator, light_sample_n;
     float p_rr;
-    uint32_t reserved;
+    uint32_t scene_hash;          // crt_scene::scene_hash of the scene the buffer was rendered from (0 in files written before round 2)
     uint64_t work_done;
     float eye[3], M[9], fovy;
     uint32_t pad;
@@ -188,9 +189,23 @@ int crt_scene_build_bvh(crt_scene* s, uint32_t thresh_n, int builder, int device
     int n = crt_device_count();
     if (n <= 0) { set_error("crt_scene_build_bvh: no CUDA device (there is no CPU fallback)"); return CRT_ERR_CUDA; }
     CHECK_ARG(device >= 0 && device < n, "crt_scene_build_bvh: device out of range");
+    if (s->batcher) { ray_batcher_destroy(s->batcher); s->batcher = nullptr; }       // its buffers belong to the previous build's device
     int rc = upload_scene(s->host, thresh_n, builder, device, s->dev, build_ms);
     s->built = rc == CRT_OK;
     s->thresh_n = thresh_n;
+    if (rc != CRT_OK) { s->dev.release(); return rc; }                               // nothing half-uploaded stays behind
+    // identity of the scene for checkpoints: triangle count, leaf rule and an FNV-1a of the vertex and material tables
+    {
+        uint64_t h = fnv1a64(s->host.verts.data(), s->host.verts.size() * sizeof(float) / 8 * 8);
+        for (const HostMaterial& m : s->host.mats) {
+            uint32_t w[10];
+            memcpy(w, m.kd, 12); memcpy(w + 3, m.ks, 12); memcpy(w + 6, m.ke, 12); memcpy(w + 9, &m.ns, 4);
+            for (uint32_t x : w) { h ^= x; h *= 1099511628211ull; }
+        }
+        h ^= (uint64_t)s->host.n_tris() * 0x9E3779B97F4A7C15ull;
+        s->scene_hash = (uint32_t)(h ^ (h >> 32));
+        if (s->scene_hash == 0) s->scene_hash = 1;
+    }
     return rc;
     });
 }
@@ -478,6 +493,7 @@ int crt_render_clear_accum(crt_render* r) {
 int crt_render_save_checkpoint(crt_render* r, const char* path, uint64_t work_done) {
     return guarded("crt_render_save_checkpoint", [&]() -> int {
     CHECK_ARG(r && path, "crt_render_save_checkpoint: null argument");
+    CHECK_ARG(work_done <= (uint64_t)r->rs.width * r->rs.height * r->rs.spp, "crt_render_save_checkpoint: work_done exceeds width * height * spp");
     if (!r->cam_set) { set_error("crt_render_save_checkpoint: nothing rendered yet"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(r->scene->dev.device));
     const size_t n = 3 * (size_t)r->rs.width * r->rs.height;
@@ -488,6 +504,7 @@ int crt_render_save_checkpoint(crt_render* r, const char* path, uint64_t work_do
     memcpy(h.magic, kCkptMagic, 8);
     h.width = r->rs.width; h.height = r->rs.height; h.spp = r->rs.spp; h.seed = r->rs.seed; h.estimator = (uint32_t)r->rs.estimator;
     h.light_sample_n = r->rs.light_sample_n; h.p_rr = r->rs.p_rr; h.work_done = work_done;
+    h.scene_hash = r->scene->scene_hash;
     memcpy(h.eye, r->cam_eye, sizeof(h.eye)); memcpy(h.M, r->cam_M, sizeof(h.M)); h.fovy = r->cam_fovy;
     h.payload_bytes = sizeof(int64_t) * n;
     h.payload_fnv1a = fnv1a64(buf.data(), h.payload_bytes);
@@ -518,6 +535,11 @@ int crt_render_load_checkpoint(crt_render* r, const char* path, uint64_t* work_d
         set_error("crt_render_load_checkpoint: the checkpoint was written with different render settings "
                   "(width, height, spp, seed, estimator, P_RR, light_sample_n must match)");
         rc = CRT_ERR_STATE;
+    } else if (h.scene_hash != 0 && h.scene_hash != r->scene->scene_hash) {
+        set_error("crt_render_load_checkpoint: the checkpoint was rendered from a different scene");
+        rc = CRT_ERR_STATE;
+    } else if (h.work_done > (uint64_t)r->rs.width * r->rs.height * r->rs.spp) {
+        set_error("crt_render_load_checkpoint: work_done exceeds width * height * spp"); rc = CRT_ERR_IO;
     } else if (h.payload_bytes != sizeof(int64_t) * n) {
         set_error("crt_render_load_checkpoint: payload size does not match the image size"); rc = CRT_ERR_IO;
     } else {
@@ -739,6 +761,10 @@ int crt_group_create(crt_scene* s, uint32_t width, uint32_t height, const int* d
             CRT_NCCL(g_nccl.CommInitAll(g->comms.data(), (int)n_devices, devices));
             // the first collective of a communicator sets up its connections (~0.2 s): spent here on the 24 bytes of pixel 0,
             // not inside the first frame (the buffers are cleared at the start of every run_view)
+            for (uint32_t k = 0; k < n_devices; ++k) {
+                CRT_CUDA(cudaSetDevice(devices[k]));
+                CRT_CUDA(cudaMemsetAsync(wavefront_accum(g->wf[k]), 0, 3 * sizeof(long long), g->streams[k]));
+            }
             CRT_NCCL(g_nccl.GroupStart());
             for (uint32_t k = 0; k < n_devices; ++k) {
                 long long* acc = wavefront_accum(g->wf[k]);

@@ -372,6 +372,8 @@ CRT_DEV void flush_leaf_queue(const SceneView& sc, Q& q, int q_count, int lane) 
             const V3 ro = mk3(q.ox[owner], q.oy[owner], q.oz[owner]), rd = mk3(q.dx[owner], q.dy[owner], q.dz[owner]);
             const float rtmax = q.tmax[owner];
             const bool any = MODE == 1 || (MODE == 2 && q.any[owner]);
+            // (Loading the first two triangles of a leaf together, to save the dependent second round trip of a two-triangle
+            //  leaf, was measured: cornell-box 93.2 -> 96.3 ms per 1080p spp-128 frame, C5 6.10 -> 5.42 Grays/s, r02_s18.)
             for (;; ++slot) {
                 V3 tv1, te1, te2;
                 const uint32_t fw = load_tri(sc.tri_geom, slot, tv1, te1, te2);

@@ -11,12 +11,6 @@
 #include "crt_gpu.h"
 #include "crt_wide.cuh"
 
-// 1: the queue counters every warp adds to sit in 128-byte lines of their own. With n_cur / n_next / n_shadow / fetch_* in
-// one 32-byte sector the compat shade stage took 24.7 - 34.1 ms for the same work depending on the box (1080p spp 128,
-// profiles/r01_s35.md); apart it takes 24.7 ms.
-#ifndef CRT_COUNTER_LINES
-#define CRT_COUNTER_LINES 1
-#endif
 // __launch_bounds__ min blocks/SM of the traversal kernels. 8 caps the wide-node kernels at 64 registers (no spills; the
 // compiler's own choice is 77-79 = 6 blocks): cornell-box +3 %, C5 (HBM-latency bound) 4793 -> 5394 Mrays/s (r01_s27).
 #ifndef CRT_MINB
@@ -391,6 +385,7 @@ int random_rays_device(const DeviceScene& ds, float4* d_rays, uint64_t n, uint64
 // =============================================================================================
 // wavefront state
 // =============================================================================================
+static constexpr int kShadowRegions = 8;
 struct Counters {
     unsigned long long work_next, work_end, gen_work0;
     unsigned long long stat_extend, stat_shadow, stat_probe;
@@ -399,19 +394,20 @@ struct Counters {
     uint32_t iterations;
     uint32_t tail_n, fetch_tail;       // paths handed to k_tail by the last k_prepare (0: none)
     uint32_t fetch_probe;
-#if CRT_COUNTER_LINES
-    // the words every warp of a kernel adds to, each alone in a 128-byte line (same-address atomics serialise in one L2
-    // slice; n_next and n_shadow shared a 32-byte sector, and so did the fetch counters)
+    // the words every warp of a kernel adds to, each alone in a 128-byte line: same-address atomics serialise in one L2 slice
+    // (with n_next and n_shadow in one 32-byte sector the shade stage took 24.7 - 34.1 ms for the same work depending on the
+    // box, profiles/r01_s35.md).
     alignas(128) uint32_t n_next;
-    alignas(128) uint32_t n_shadow[2];          // by iteration parity: k_shadow of iteration k overlaps k_prepare .. k_extend of k + 1
+    // The shadow queue is cut into kShadowRegions regions with a counter each (a warp of k_shade appends to region
+    // global-warp-id % kShadowRegions): two appends per vertex and warp on ONE counter were ~1 atomic per ns, the rate one
+    // address takes - once the vertex arithmetic had lost a third of its instructions, k_shade waited on exactly that
+    // (24.7 % of its stall samples, box-dependent 19 - 30 ms per 1080p spp-128 frame, profiles/r02_s20.md).
+    // [parity][region]: k_shadow of iteration k overlaps k_prepare .. k_extend of k + 1.
+    struct alignas(128) Line { uint32_t v; };
+    Line n_shadow[2][kShadowRegions];
     alignas(128) uint32_t fetch_extend;
     alignas(128) uint32_t fetch_shadow[2];
     alignas(128) uint32_t pad_;
-#else
-    uint32_t n_next;
-    uint32_t n_shadow[2], fetch_shadow[2];      // by iteration parity: k_shadow of iteration k overlaps k_prepare .. k_extend of k + 1
-    uint32_t fetch_extend;
-#endif
 };
 struct HostStatus { volatile uint32_t done; volatile uint32_t n_cur; volatile unsigned long long work_next; };
 
@@ -465,7 +461,7 @@ struct Wavefront {
     WfRun run;
     uint32_t width = 0, height = 0;
     uint32_t pool = 0;             // path slots per queue
-    uint32_t shadow_cap = 0;
+    uint32_t shadow_cap = 0, region_cap = 0;      // shadow queue: kShadowRegions regions of region_cap rays
     bool has_probe = false;
     float4 *q_o[2] = {nullptr, nullptr}, *q_d[2] = {nullptr, nullptr}, *q_T[2] = {nullptr, nullptr};
     float* q_pdf[2] = {nullptr, nullptr};      // mis: density of the BSDF sample that produced the ray
@@ -490,12 +486,14 @@ struct Wavefront {
 // kernels
 // =============================================================================================
 __global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostStatus* status, int par) {
-    c->stat_shadow += c->n_shadow[par];          // the shadow rays of iteration k - 2, traced long ago
+    for (int r = 0; r < kShadowRegions; ++r) {    // the shadow rays of iteration k - 2, traced long ago
+        c->stat_shadow += c->n_shadow[par][r].v;
+        c->n_shadow[par][r].v = 0;
+    }
     uint32_t n_cur = c->n_next;
     uint32_t n_probe = c->n_probe_next;
     c->n_next = 0;
     c->n_probe_next = 0;
-    c->n_shadow[par] = 0;
     unsigned long long remaining = c->work_end - c->work_next;
     uint32_t room = pool - n_cur;
     uint32_t n_new = remaining < (unsigned long long)room ? (uint32_t)remaining : room;
@@ -865,8 +863,9 @@ __global__ void __launch_bounds__(128, EST == CRT_ESTIMATOR_COMPAT ? CRT_SHADE_M
                                                       float4* __restrict__ pr_o_next, float4* __restrict__ pr_d_next,
                                                       float4* __restrict__ pr_w_next, uint32_t* __restrict__ pr_list_next,
                                                       float4* __restrict__ sh_o, float4* __restrict__ sh_d,
-                                                      float4* __restrict__ sh_c, long long* __restrict__ accum, int par) {
+                                                      float4* __restrict__ sh_c, long long* __restrict__ accum, int par, uint32_t region_cap) {
     const uint32_t n = c->n_cur;
+    const uint32_t region = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % (uint32_t)kShadowRegions;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 qo = q_o[i], qd = q_d[i], qT = q_T[i];
         PathState ps;
@@ -880,8 +879,9 @@ __global__ void __launch_bounds__(128, EST == CRT_ESTIMATOR_COMPAT ? CRT_SHADE_M
         ProbeState npr;
         const uint32_t pixel = ps.pixel;
         auto shadow = [&](bool needs_trace, V3 pos, float tmax, V3 dir, V3 contrib) {
-            int k = warp_append(&c->n_shadow[par], needs_trace);
+            int k = warp_append(&c->n_shadow[par][region].v, needs_trace);
             if (k >= 0) {
+                k += (int)(region * region_cap);
                 sh_o[k] = make_float4(pos.x, pos.y, pos.z, tmax);
                 sh_d[k] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pixel));
                 sh_c[k] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
@@ -1147,14 +1147,33 @@ __global__ void __launch_bounds__(128, CRT_TAIL_MINB) k_tail(SceneView sc, Count
 template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_shadow(SceneView sc, Counters* c, const float4* __restrict__ sh_o,
                                                 const float4* __restrict__ sh_d, const float4* __restrict__ sh_c,
-                                                long long* __restrict__ accum, int par) {
+                                                long long* __restrict__ accum, int par, uint32_t region_cap) {
     // the contribution and pixel of the ray a lane owns wait in shared memory (loaded with the ray, one DRAM round trip
     // instead of a second one when the ray finishes: 3.7 % of this kernel's stall samples, profiles/r01_s20.md)
     __shared__ float4 s_contrib[128];
+    // The regions are read interleaved in runs of 32: indices 32 b .. 32 b + 31 are entries 32 (b / 8) .. of region b % 8, so
+    // that a warp's refill reads consecutive records of one region and the queue is still walked roughly in the order the
+    // paths were shaded in. The regions hold nearly the same number of rays (each takes an eighth of the warps); an index past
+    // the end of its region is a slot without a ray.
+    __shared__ uint32_t s_cnt[kShadowRegions];
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) {
+        uint32_t mx = 0;
+        for (int r = 0; r < kShadowRegions; ++r) { s_cnt[r] = c->n_shadow[par][r].v; mx = max(mx, s_cnt[r]); }
+        s_n = ((mx + 31u) & ~31u) * (uint32_t)kShadowRegions;
+    }
+    __syncthreads();
     trace_queue<1, WIDE>(
-        sc, c->n_shadow[par], &c->fetch_shadow[par],
+        sc, s_n, &c->fetch_shadow[par],
         [&](uint32_t i, V3& o, V3& d, float& tmax) {
-            const float4 a = sh_o[i], b = sh_d[i], cc = sh_c[i];
+            const uint32_t blk = i >> 5, r = blk % (uint32_t)kShadowRegions, e = ((blk / (uint32_t)kShadowRegions) << 5) | (i & 31u);
+            if (e >= s_cnt[r]) {                                        // no ray here: nothing to trace, nothing to add
+                o = mk3(0.0f, 0.0f, 0.0f); d = mk3(0.0f, 0.0f, 1.0f); tmax = 0.0f;
+                s_contrib[threadIdx.x] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                return false;
+            }
+            const size_t k = (size_t)r * region_cap + e;
+            const float4 a = sh_o[k], b = sh_d[k], cc = sh_c[k];
             o = mk3(a); tmax = a.w; d = mk3(b);
             s_contrib[threadIdx.x] = make_float4(cc.x, cc.y, cc.z, b.w);
             return true;
@@ -1189,6 +1208,7 @@ int resolve_device(const long long* d_accum, uint32_t n_pixels, uint32_t spp, fl
 // =============================================================================================
 int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wavefront** out) {
     Wavefront* w = new Wavefront();
+    *out = w;                                        // the caller destroys it when an allocation below fails
     w->width = width; w->height = height;
     w->has_probe = ds.has_specular;
     const size_t npix = (size_t)width * height;
@@ -1207,7 +1227,6 @@ int wavefront_create(const DeviceScene& ds, uint32_t width, uint32_t height, Wav
     if (ds.wide) CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_tail<CRT_ESTIMATOR_MIS, true>), 128, 0));
     else CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_tail<CRT_ESTIMATOR_MIS, false>), 128, 0));
     w->grid_tail = num_sms() * std::max(occ, 1);
-    *out = w;
     return CRT_OK;
 }
 
@@ -1224,9 +1243,15 @@ static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings
     uint64_t per_vertex = (uint64_t)std::max<uint32_t>(ds.n_lights, 1) * std::max<uint32_t>(rs.light_sample_n, 1);
     const uint64_t shadow_budget = 1ull << 26;        // 64 Mi shadow rays in flight at most (3 GiB)
     while (pool > 4096 && (uint64_t)pool * per_vertex > shadow_budget) pool >>= 1;
-    uint64_t shadow_cap = (uint64_t)pool * per_vertex;
+    // a region takes the shadow rays of the warps with global id % kShadowRegions == r: at most this many paths each
+    const uint64_t warps = (uint64_t)w->grid_shade * 4;
+    const uint64_t region_paths = ((uint64_t)pool + warps * 32 - 1) / (warps * 32) * 32 * ((warps + kShadowRegions - 1) / kShadowRegions);
+    const uint64_t region_cap = std::min<uint64_t>(region_paths, pool) * per_vertex;
+    uint64_t shadow_cap = region_cap * kShadowRegions;
     if (shadow_cap > 0xffffffffull) { set_error("light_sample_n x lights too large"); return CRT_ERR_INVALID; }
     if (w->pool == pool && w->shadow_cap >= shadow_cap) return CRT_OK;
+    w->pool = 0;                                     // nothing is valid until every allocation below has succeeded
+    w->shadow_cap = 0;
     for (int b = 0; b < 2; ++b) {
         cudaFree(w->q_o[b]); cudaFree(w->q_d[b]); cudaFree(w->q_T[b]); cudaFree(w->q_pdf[b]);
         cudaFree(w->pr_o[b]); cudaFree(w->pr_d[b]); cudaFree(w->pr_w[b]); cudaFree(w->pr_list[b]);
@@ -1255,6 +1280,7 @@ static int ensure_pool(Wavefront* w, const DeviceScene& ds, const RenderSettings
     CRT_CUDA(cudaMalloc(&w->sh_c, sizeof(float4) * shadow_cap));
     w->pool = pool;
     w->shadow_cap = (uint32_t)shadow_cap;
+    w->region_cap = (uint32_t)region_cap;
     return CRT_OK;
 }
 
@@ -1381,6 +1407,16 @@ int wavefront_step(Wavefront* w, bool block, bool* done, bool* progressed) {
         const int cur = it & 1, nxt = cur ^ 1;
         k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, tail_max, w->status_dev, cur);
         mark("prepare", st);
+        // The tail path tracer goes first: when k_prepare hands the remaining paths to it, the other kernels of this iteration are
+        // empty, and it needs nothing from k_shadow of the previous iteration (still running on the second stream), which k_shade
+        // below has to wait for. On the shipped frames that shadow launch is 0.2 ms the tail now runs beside.
+#define CRT_TAIL_LAUNCH(EST, W)                                                                                              \
+    k_tail<EST, W><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur], w->pr_d[cur], \
+                                                 w->pr_w[cur], w->accum)
+        if (mis) { if (wide) CRT_TAIL_LAUNCH(CRT_ESTIMATOR_MIS, true); else CRT_TAIL_LAUNCH(CRT_ESTIMATOR_MIS, false); }
+        else { if (wide) CRT_TAIL_LAUNCH(CRT_ESTIMATOR_COMPAT, true); else CRT_TAIL_LAUNCH(CRT_ESTIMATOR_COMPAT, false); }
+#undef CRT_TAIL_LAUNCH
+        mark("tail", st);
         if (rs.stage_timing) cudaEventRecord(se[0], st);
         k_generate<<<w->grid_shade, 256, 0, st>>>(w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], mis ? w->q_pdf[cur] : nullptr);
         mark("generate", st);
@@ -1400,12 +1436,12 @@ int wavefront_step(Wavefront* w, bool block, bool* done, bool* progressed) {
             k_shade<CRT_ESTIMATOR_MIS><<<w->grid_shade, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
                                                                        w->q_pdf[nxt], w->hit_t, w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt],
                                                                        w->q_d[nxt], w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
-                                                                       w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
+                                                                       w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum, cur, w->region_cap);
         else
             k_shade<CRT_ESTIMATOR_COMPAT><<<w->grid_shade, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur],
                                                                           w->q_pdf[nxt], w->hit_t, w->hit_slot, w->pr_w[cur], w->pr_hit, w->q_o[nxt],
                                                                           w->q_d[nxt], w->q_T[nxt], w->pr_o[nxt], w->pr_d[nxt], w->pr_w[nxt],
-                                                                          w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
+                                                                          w->pr_list[nxt], w->sh_o, w->sh_d, w->sh_c, w->accum, cur, w->region_cap);
         mark("shade", st);
         if (rs.stage_timing) cudaEventRecord(se[3], st);
         cudaStream_t ss = st;
@@ -1414,18 +1450,11 @@ int wavefront_step(Wavefront* w, bool block, bool* done, bool* progressed) {
             CRT_CUDA(cudaStreamWaitEvent(w->st_shadow, w->ev_shaded, 0));
             ss = w->st_shadow;
         }
-        if (wide) k_shadow<true><<<w->grid_trace, 128, 0, ss>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
-        else k_shadow<false><<<w->grid_trace, 128, 0, ss>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum, cur);
+        if (wide) k_shadow<true><<<w->grid_trace, 128, 0, ss>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum, cur, w->region_cap);
+        else k_shadow<false><<<w->grid_trace, 128, 0, ss>>>(sv, w->counters, w->sh_o, w->sh_d, w->sh_c, w->accum, cur, w->region_cap);
         if (overlap) CRT_CUDA(cudaEventRecord(w->ev_shadowed, ss));
         mark("shadow", st);
         if (rs.stage_timing) cudaEventRecord(se[4], st);
-#define CRT_TAIL_LAUNCH(EST, W)                                                                                              \
-    k_tail<EST, W><<<w->grid_tail, 128, 0, st>>>(sv, w->counters, p, w->q_o[cur], w->q_d[cur], w->q_T[cur], w->q_pdf[cur], w->pr_d[cur], \
-                                                 w->pr_w[cur], w->accum)
-        if (mis) { if (wide) CRT_TAIL_LAUNCH(CRT_ESTIMATOR_MIS, true); else CRT_TAIL_LAUNCH(CRT_ESTIMATOR_MIS, false); }
-        else { if (wide) CRT_TAIL_LAUNCH(CRT_ESTIMATOR_COMPAT, true); else CRT_TAIL_LAUNCH(CRT_ESTIMATOR_COMPAT, false); }
-#undef CRT_TAIL_LAUNCH
-        mark("tail", st);
         launches += 3;
         if (rs.stage_timing) {
             cudaEventRecord(se[5], st);
@@ -1472,7 +1501,9 @@ int wavefront_finish(Wavefront* w, crt_render_stats* stats) {
         memset(stats, 0, sizeof(*stats));
         stats->samples = h.work_end - w_begin;
         stats->extend_rays = h.stat_extend;
-        stats->shadow_rays = h.stat_shadow + h.n_shadow[0] + h.n_shadow[1];
+        stats->shadow_rays = h.stat_shadow;
+        for (int par = 0; par < 2; ++par)
+            for (int r = 0; r < kShadowRegions; ++r) stats->shadow_rays += h.n_shadow[par][r].v;
         stats->probe_rays = h.stat_probe;
         stats->iterations = h.iterations;
         stats->kernel_launches = launches;

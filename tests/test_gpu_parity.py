@@ -421,6 +421,14 @@ def test_progressive_chunks_and_checkpoint_resume(gpu, scene_files, tmp_path):
         with pytest.raises(gpu.CrtError) as e:
             gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n).load_checkpoint(bad)
         assert e.value.code == -2
+    # refused: a render of another scene (the header carries the scene's identity), a work_done beyond the frame
+    other = gpu.Scene().add_obj(scene_files["cornell-box"]["obj"], scene_files["cornell-box"]["dir"])
+    other.set_BVH(2)
+    with pytest.raises(gpu.CrtError) as e:
+        gpu.Render(other, W, H, spp, cfg.P_RR, cfg.light_sample_n).load_checkpoint(ck)
+    assert e.value.code == -5 and "different scene" in str(e.value)
+    with pytest.raises(gpu.CrtError):
+        r2.save_checkpoint(str(tmp_path / "over.ckpt"), W * H * spp + 1)
     with pytest.raises(gpu.CrtError) as e:
         gpu.Render(a, W, H, spp, cfg.P_RR, cfg.light_sample_n).save_checkpoint(ck, 0)      # nothing rendered yet
     assert e.value.code == -5
