@@ -391,6 +391,7 @@ struct Counters {
     unsigned long long stat_extend, stat_shadow, stat_probe;
     uint32_t n_cur, n_probe_cur, n_probe_next;
     uint32_t gen_base, gen_count;
+    uint32_t gen_tile, gen_jj0;        // tile order: tile and offset inside it of the first work item k_generate starts (k_prepare)
     uint32_t iterations;
     uint32_t tail_n, fetch_tail;       // paths handed to k_tail by the last k_prepare (0: none)
     uint32_t fetch_probe;
@@ -424,6 +425,7 @@ struct RenderParamsDev {
     // [0, tile_px), then of the next tile_px pixels ... - so that the part of the accumulation buffer the paths in flight
     // add to (24 B per pixel) stays L2-resident on frames whose whole buffer is not (4K: 199 MB against 126 MB of L2).
     uint32_t tile_px, tile_s0, tile_S;
+    uint32_t tile_fast;                         // per_tile = tile_px * tile_S fits 31 bits and is >= the pool: k_generate's 32-bit path
     unsigned long long w_begin;
     float p_rr;
     int light_sample_n;
@@ -444,7 +446,7 @@ struct WfRun {                      // the run_view in flight on a Wavefront (wa
     bool wide = false, mis = false, overlap = false, timeline = false;
     uint32_t tail_max = 0, it = 0;
     uint64_t launches = 0;
-    unsigned long long w_begin = 0;
+    unsigned long long w_begin = 0, per_tile32 = 0;       // per_tile32: work items per tile when k_generate takes its 32-bit path, else 0
     float ms_stage[5] = {0, 0, 0, 0, 0};
     cudaEvent_t se[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<std::pair<const char*, cudaEvent_t>> tl;      // CRT_TIMELINE
@@ -485,7 +487,8 @@ struct Wavefront {
 // =============================================================================================
 // kernels
 // =============================================================================================
-__global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostStatus* status, int par) {
+__global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostStatus* status, int par, unsigned long long per_tile,
+                          unsigned long long w_begin) {
     for (int r = 0; r < kShadowRegions; ++r) {    // the shadow rays of iteration k - 2, traced long ago
         c->stat_shadow += c->n_shadow[par][r].v;
         c->n_shadow[par][r].v = 0;
@@ -500,6 +503,11 @@ __global__ void k_prepare(Counters* c, uint32_t pool, uint32_t tail_max, HostSta
     c->gen_base = n_cur;
     c->gen_count = n_new;
     c->gen_work0 = c->work_next;
+    if (per_tile) {                    // the one 64-bit division of the tile order, here instead of three per generated path
+        const unsigned long long j = c->work_next - w_begin;
+        c->gen_tile = (uint32_t)(j / per_tile);
+        c->gen_jj0 = (uint32_t)(j - (unsigned long long)c->gen_tile * per_tile);
+    }
     n_cur += n_new;
     c->work_next += n_new;
     c->fetch_extend = c->fetch_shadow[par] = c->fetch_probe = c->fetch_tail = 0;
@@ -528,7 +536,16 @@ __global__ void __launch_bounds__(256) k_generate(const Counters* __restrict__ c
         // (an 8x4-tile order of the pixels inside a sample, alone or in blocks of 4-16 tiles, changes nothing measurable:
         //  profiles/r01_s21.md - the camera rays are a third of the extend rays and the cheapest ones)
         uint32_t pixel, sample;
-        if (p.tile_px) {
+        if (p.tile_fast) {
+            // 32-bit arithmetic: k_prepare has located the first work item; a launch spans at most two tiles (per_tile >= pool)
+            const uint32_t per_tile = p.tile_px * p.tile_S;
+            uint32_t t = c->gen_tile, jj = c->gen_jj0 + k;
+            if (jj >= per_tile) { jj -= per_tile; ++t; }
+            const uint32_t first = t * p.tile_px;
+            const uint32_t px = (uint32_t)min((unsigned long long)p.tile_px, p.n_pixels - first);
+            sample = p.tile_s0 + jj / px;
+            pixel = first + jj % px;
+        } else if (p.tile_px) {
             const unsigned long long j = w - p.w_begin, per_tile = (unsigned long long)p.tile_px * p.tile_S;
             const uint32_t t = (uint32_t)(j / per_tile);
             const unsigned long long jj = j - (unsigned long long)t * per_tile;
@@ -1329,7 +1346,7 @@ int wavefront_begin(Wavefront* w, const DeviceScene& ds, const RenderSettings& r
     p.s_begin = 0; p.p_rr = rs.p_rr; p.light_sample_n = (int)rs.light_sample_n; p.seed = rs.seed;
     p.max_vertices = 64;                                           // BOUNCE_STACK_SIZE, Global.h:18
     p.w_begin = w_begin;
-    p.tile_px = p.tile_s0 = p.tile_S = 0;
+    p.tile_px = p.tile_s0 = p.tile_S = p.tile_fast = 0;
     {
         const uint32_t tile_px = env_u32("CRT_TILE_PX", 1u << 20);    // 24 MB of accumulation buffer per tile (4K: 2^22 2465, 2^21 2658, 2^20 2724, 2^19 2743 Msamples/s, r02_s08)
         if (tile_px && npix > tile_px && w_end > w_begin && w_begin % npix == 0 && w_end % npix == 0) {
@@ -1337,6 +1354,11 @@ int wavefront_begin(Wavefront* w, const DeviceScene& ds, const RenderSettings& r
             p.tile_s0 = (uint32_t)(w_begin / npix);
             p.tile_S = (uint32_t)((w_end - w_begin) / npix);
         }
+    }
+    {
+        const unsigned long long per_tile = (unsigned long long)p.tile_px * p.tile_S;
+        p.tile_fast = (per_tile >= w->pool && per_tile < (1ull << 31)) ? 1u : 0u;
+        r.per_tile32 = p.tile_fast ? per_tile : 0ull;
     }
     Counters h;
     memset(&h, 0, sizeof(h));
@@ -1405,7 +1427,7 @@ int wavefront_step(Wavefront* w, bool block, bool* done, bool* progressed) {
             if (w->status_host->done) { *done = true; if (progressed) *progressed = true; return CRT_OK; }
         }
         const int cur = it & 1, nxt = cur ^ 1;
-        k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, tail_max, w->status_dev, cur);
+        k_prepare<<<1, 1, 0, st>>>(w->counters, w->pool, tail_max, w->status_dev, cur, r.per_tile32, r.w_begin);
         mark("prepare", st);
         // The tail path tracer goes first: when k_prepare hands the remaining paths to it, the other kernels of this iteration are
         // empty, and it needs nothing from k_shadow of the previous iteration (still running on the second stream), which k_shade

@@ -54,6 +54,9 @@ for r in rr[2:]:
     try:
         key = name.replace("void ", "").replace("crt::", "").split("<")[0]
         dur = val(r, "gpu__time_duration.sum")
+        if key in facts and facts[key]["duration_ms"] >= round(dur * 1e3, 4):
+            out.append("")
+            continue                                      # several captures of one kernel: the longest launch is the one kept
         facts[key] = {
             "issue_frac": round(float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]) / 100, 4),
             "lane_efficiency": round(float(r[idx["smsp__thread_inst_executed_per_inst_executed.ratio"]]) / 32, 4),
