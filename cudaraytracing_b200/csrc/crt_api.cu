@@ -685,6 +685,7 @@ int nccl_fail(ncclResult_t r, const char* what) {
     } while (0)
 }  // namespace
 
+static constexpr int kGroupBands = 8;
 struct crt_group {
     crt_scene* scene = nullptr;
     uint32_t width = 0, height = 0;
@@ -696,6 +697,9 @@ struct crt_group {
     std::vector<crt_render_stats> stats;
     RenderSettings rs;
     cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;
+    cudaEvent_t ev_band[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st_resolve = nullptr;          // devices[0]: resolves band c while band c + 1 is being reduced
+    bool resolved = false;                      // d_linear / d_rgb8 hold the resolved frame of the last run_view
     float reduce_ms = 0;
     float* d_linear = nullptr;
     uint8_t* d_rgb8 = nullptr;
@@ -717,6 +721,8 @@ int crt_group_destroy(crt_group* g) {
     if (!g->devices.empty()) cudaSetDevice(g->devices[0]);
     if (g->ev_r0) cudaEventDestroy(g->ev_r0);
     if (g->ev_r1) cudaEventDestroy(g->ev_r1);
+    for (cudaEvent_t e : g->ev_band) if (e) cudaEventDestroy(e);
+    if (g->st_resolve) cudaStreamDestroy(g->st_resolve);
     cudaFree(g->d_linear);
     cudaFree(g->d_rgb8);
     delete g;
@@ -757,6 +763,8 @@ int crt_group_create(crt_scene* s, uint32_t width, uint32_t height, const int* d
         CRT_CUDA(cudaMalloc(&g->d_rgb8, 3 * (size_t)width * height));
         CRT_CUDA(cudaEventCreate(&g->ev_r0));
         CRT_CUDA(cudaEventCreate(&g->ev_r1));
+        for (cudaEvent_t& e : g->ev_band) CRT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CRT_CUDA(cudaStreamCreateWithFlags(&g->st_resolve, cudaStreamNonBlocking));
         if (n_devices > 1) {
             CRT_NCCL(g_nccl.CommInitAll(g->comms.data(), (int)n_devices, devices));
             // the first collective of a communicator sets up its connections (~0.2 s): spent here on the 24 bytes of pixel 0,
@@ -830,25 +838,40 @@ int crt_group_run_view(crt_group* g, const float eye[3], const float inv_view[9]
         int rc = wavefront_finish(g->wf[k], &g->stats[k]);
         if (rc != CRT_OK) return rc;
     }
-    // ONE collective: sum of the int64 buffers onto devices[0] (integer addition: the same buffer for every G)
+    // The collective: sum of the int64 buffers onto devices[0] (integer addition: the same buffer for every G), issued in bands
+    // of pixel rows so that the resolve of band c (fixed point -> linear -> tone map, on a second stream of devices[0]) runs
+    // beside the reduce of band c + 1 (chunked, overlapped reduce; the reference has no accumulation buffer).
     g->reduce_ms = 0;
+    g->resolved = false;
     if (G > 1) {
+        const unsigned long long band_px = std::max<unsigned long long>((npix + kGroupBands - 1) / kGroupBands, 1ull << 16);
         CRT_CUDA(cudaSetDevice(g->devices[0]));
         CRT_CUDA(cudaEventRecord(g->ev_r0, g->streams[0]));
-        CRT_NCCL(g_nccl.GroupStart());
-        for (size_t k = 0; k < G; ++k) {
-            long long* acc = wavefront_accum(g->wf[k]);
-            CRT_NCCL(g_nccl.Reduce(acc, acc, (size_t)(3 * npix), ncclInt64, ncclSum, 0, g->comms[k], g->streams[k]));
+        int band = 0;
+        for (unsigned long long px0 = 0; px0 < npix; px0 += band_px, ++band) {
+            const unsigned long long cnt_px = std::min(band_px, npix - px0);
+            CRT_NCCL(g_nccl.GroupStart());
+            for (size_t k = 0; k < G; ++k) {
+                long long* acc = wavefront_accum(g->wf[k]) + 3 * px0;
+                CRT_NCCL(g_nccl.Reduce(acc, acc, (size_t)(3 * cnt_px), ncclInt64, ncclSum, 0, g->comms[k], g->streams[k]));
+            }
+            CRT_NCCL(g_nccl.GroupEnd());
+            CRT_CUDA(cudaSetDevice(g->devices[0]));
+            CRT_CUDA(cudaEventRecord(g->ev_band[band % kGroupBands], g->streams[0]));
+            CRT_CUDA(cudaStreamWaitEvent(g->st_resolve, g->ev_band[band % kGroupBands], 0));
+            int rc = resolve_device(wavefront_accum(g->wf[0]) + 3 * px0, (uint32_t)cnt_px, g->rs.spp, g->d_linear + 3 * px0, g->d_rgb8 + 3 * px0,
+                                    g->st_resolve);
+            if (rc != CRT_OK) return rc;
         }
-        CRT_NCCL(g_nccl.GroupEnd());
-        CRT_CUDA(cudaSetDevice(g->devices[0]));
         CRT_CUDA(cudaEventRecord(g->ev_r1, g->streams[0]));
         for (size_t k = 0; k < G; ++k) {
             CRT_CUDA(cudaSetDevice(g->devices[k]));
             CRT_CUDA(cudaStreamSynchronize(g->streams[k]));
         }
         CRT_CUDA(cudaSetDevice(g->devices[0]));
+        CRT_CUDA(cudaStreamSynchronize(g->st_resolve));
         CRT_CUDA(cudaEventElapsedTime(&g->reduce_ms, g->ev_r0, g->ev_r1));
+        g->resolved = true;
     }
     g->rendered = true;
     return CRT_OK;
@@ -866,8 +889,10 @@ int crt_group_get_rgb8(crt_group* g, uint8_t* out) {
     CHECK_ARG(g && out, "crt_group_get_rgb8: null argument");
     CRT_CUDA(cudaSetDevice(g->devices[0]));
     const uint32_t npix = g->width * g->height;
-    int rc = resolve_device(wavefront_accum(g->wf[0]), npix, g->rs.spp, g->d_linear, g->d_rgb8, g->streams[0]);
-    if (rc != CRT_OK) return rc;
+    if (!g->resolved) {                          // one GPU: no collective, resolved here
+        int rc = resolve_device(wavefront_accum(g->wf[0]), npix, g->rs.spp, g->d_linear, g->d_rgb8, g->streams[0]);
+        if (rc != CRT_OK) return rc;
+    }
     CRT_CUDA(cudaMemcpyAsync(out, g->d_rgb8, 3 * (size_t)npix, cudaMemcpyDeviceToHost, g->streams[0]));
     CRT_CUDA(cudaStreamSynchronize(g->streams[0]));
     return CRT_OK;
