@@ -41,10 +41,24 @@ CRT_DEV float dot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x))
 CRT_DEV V3 cross(V3 a, V3 b) {
     return mk3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
+// a / b for b > 0 (or b = +inf) where a is often exactly zero - a clamped cosine, a coordinate in the plane of the light. The
+// compiler's IEEE division rejects a zero numerator in its fast path (FCHK) and calls a 31-instruction subroutine for the whole
+// warp; in k_shade that was 17 % of the instructions (profiles/r02_div_zero.md). The quotient is a itself (the zero keeps its sign),
+// so the division is given a harmless numerator and the result selected: same value, no call.
+CRT_DEV float div_by_pos(float a, float b) {
+    const bool z = a == 0.0f;
+    float n = z ? 1.0f : a;
+    asm("" : "+f"(n));          // or the compiler folds the two selects back into a / b
+    const float q = n / b;
+    return z ? a : q;
+}
 // Eigen normalized(): v / sqrt(v.v) when v.v > 0 (reference include/Eigen/src/Core/Dot.h:121-131)
 CRT_DEV V3 normalize(V3 a) {
     float n = dot(a, a);
-    if (n > 0.0f) return a / sqrtf(n);
+    if (n > 0.0f) {
+        const float s = sqrtf(n);
+        return mk3(div_by_pos(a.x, s), div_by_pos(a.y, s), div_by_pos(a.z, s));
+    }
     return a;
 }
 CRT_DEV float length(V3 a) { return sqrtf(dot(a, a)); }
@@ -329,7 +343,10 @@ static constexpr int kRefillLanes = CRT_REFILL_LANES;
 // included, so the round trip is waited for on the spot anyway), and a static round-robin deal of 128-ray chunks with a
 // dynamic tail and L2 prefetch of the next chunk: k_extend 15 % slower, k_shadow 9 % slower at 1080p. The returned value of
 // this atomic is the largest single stall of k_shadow only when the accumulation buffer misses L2 (4K frames: its RED
-// traffic to DRAM queues in front of it); the tile order of k_generate removes that.
+// traffic to DRAM queues in front of it); the tile order of k_generate removes that. Also measured and removed (r02_s27,
+// profiles/r02_late_levers.md): a reservation of 32 indices issued under elect.sync (which ptxas leaves un-aggregated) just
+// before the leaf flush and read just after it, so that the flush covers the round trip - k_extend 8 % slower, C5 7 % slower:
+// the register the value waits in and the bookkeeping of two open reservations cost more than the hidden latency returns.
 struct RayFetch {
     bool exhausted = false;
     CRT_DEV void init(uint32_t n) { exhausted = n == 0; }

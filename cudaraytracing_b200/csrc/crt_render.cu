@@ -694,7 +694,9 @@ CRT_DEV bool shade_vertex_compat(const SceneView& sc, const RenderParamsDev& p, 
             float d2 = d1 * d1;
             float cos1 = fmaxf(0.0f, dot(dir, nrm));
             float cos2 = fmaxf(0.0f, -dot(dir, mk3(ln)));
-            V3 contrib = cmul(mk3(a.w, b.w, cc.w), Tf) * (((cos1 * cos2) * area) / d2 / lsn_f);     // :274-283
+            const float geom = (cos1 * cos2) * area;            // zero for every sample on a surface that faces away: no slow division
+            const float fac = d2 > 0.0f ? div_by_pos(div_by_pos(geom, d2), lsn_f) : geom / d2 / lsn_f;
+            V3 contrib = cmul(mk3(a.w, b.w, cc.w), Tf) * fac;   // :274-283
             bool live = !(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f);
             float t_to_light = dist.x / dir.x;                  // :272
             bool needs_trace = live && (t_to_light == t_to_light);

@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, session 25: the node step with packed FFMA2 (two children per FMA instruction; default) against scalar FFMAs (noffma2)
+mkdir -p gpurun_out
+for rep in 1 2; do
+for v in variants/libcrt_noffma2.so libcrt.so; do
+  echo "== $v"
+  env CRT_LIB=$PWD/cudaraytracing_b200/$v QB_W=3840 QB_H=2160 QB_SPP=48 QB_SCENES=cornell-box timeout 300 python tools/quick_bench.py ploc8
+  env CRT_LIB=$PWD/cudaraytracing_b200/$v QB_W=800 QB_H=600 QB_SPP=4 QB_NO_BATCH=1 QB_SCENES=veach-mis timeout 300 python tools/quick_bench.py ploc8
+done
+done 2>&1 | tee gpurun_out/r02_s25.log
+( timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_wide.py -m gpu -x -q 2>&1 | tail -3 ) | tee -a gpurun_out/r02_s25.log
