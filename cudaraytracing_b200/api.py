@@ -113,6 +113,7 @@ def load_library():
         "crt_render_get_accum_i64": [vp, vp],
         "crt_render_get_accum": [vp, vp],
         "crt_render_get_rgb8": [vp, vp],
+        "crt_render_get_rgb8_device": [vp, vp],
         "crt_render_save_png": [vp, C.c_char_p],
         "crt_render_get_stats": [vp, C.POINTER(_Stats)],
         "crt_render_destroy": [vp],
@@ -403,6 +404,11 @@ class Render:
         _check(self.L.crt_render_get_rgb8(self.h, _p(out)))
         return out
 
+    def frame_to_device(self, device_ptr):
+        """The display path of Render::run_view(..., cuda_pbo_resource) (include/Render.cuh:446-469): the RGB8 frame written
+        into a device buffer of width*height*3 bytes the caller owns (a mapped GL pixel buffer object, a torch tensor ...)."""
+        _check(self.L.crt_render_get_rgb8_device(self.h, C.c_void_p(device_ptr)))
+
     def save_frame_buffer(self, path):
         _check(self.L.crt_render_save_png(self.h, path.encode()))
 
@@ -410,6 +416,25 @@ class Render:
         s = _Stats()
         _check(self.L.crt_render_get_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+
+def _prefer_bundled_nccl():
+    """The library loads NCCL by name (`libnccl.so.2`, or CRT_NCCL_LIB) when a group of several GPUs is created. In a Python process
+    that also imports torch, both must map the SAME file: torch's CUDA library is linked against the NCCL wheel next to it, and a
+    different libnccl.so.2 loaded first (the system one) makes `import torch` fail on a missing symbol. So, unless the caller chose
+    a file, name the wheel's library when there is one."""
+    if os.environ.get("CRT_NCCL_LIB"):
+        return
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["CRT_NCCL_LIB"] = cand
+            return
 
 
 class RenderGroup:
@@ -424,6 +449,7 @@ class RenderGroup:
         self.devices = [int(d) for d in devices]
         self.h = C.c_void_p()
         arr = (C.c_int * len(self.devices))(*self.devices)
+        _prefer_bundled_nccl()
         _check(self.L.crt_group_create(scene.h, self.width, self.height, C.cast(arr, C.c_void_p), len(self.devices), C.byref(self.h)))
         self.set_params(spp, P_RR, light_sample_n, seed, estimator)
 

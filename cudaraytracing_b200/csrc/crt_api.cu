@@ -605,6 +605,23 @@ int crt_render_get_rgb8(crt_render* r, uint8_t* out) {
     return resolve_to(r, nullptr, out);
     });
 }
+int crt_render_get_rgb8_device(crt_render* r, void* d_rgb8) {
+    return guarded("crt_render_get_rgb8_device", [&]() -> int {
+    CHECK_ARG(r && d_rgb8, "crt_render_get_rgb8_device: null argument");
+    CRT_CUDA(cudaSetDevice(r->scene->dev.device));
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, d_rgb8) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) ||
+        (at.type == cudaMemoryTypeDevice && at.device != r->scene->dev.device)) {
+        cudaGetLastError();
+        set_error("crt_render_get_rgb8_device: d_rgb8 is not device memory of the render's device " + std::to_string(r->scene->dev.device));
+        return CRT_ERR_INVALID;
+    }
+    int rc = resolve_device(wavefront_accum(r->wf), r->rs.width * r->rs.height, r->rs.spp, r->d_linear, (uint8_t*)d_rgb8, r->stream);
+    if (rc != CRT_OK) return rc;
+    CRT_CUDA(cudaStreamSynchronize(r->stream));
+    return CRT_OK;
+    });
+}
 int crt_render_save_png(crt_render* r, const char* path) {
     return guarded("crt_render_save_png", [&]() -> int {
     CHECK_ARG(r && path, "crt_render_save_png: null argument");
@@ -757,6 +774,16 @@ int crt_group_create(crt_scene* s, uint32_t width, uint32_t height, const int* d
             int rc = wavefront_create(g->scene_of(k), width, height, &g->wf[k]);
             if (rc != CRT_OK) return rc;
             CRT_CUDA(cudaStreamCreateWithFlags(&g->streams[k], cudaStreamNonBlocking));
+            // the first launch of a kernel on a device loads its code (CUDA loads modules lazily; a cold process spent ~0.2 s of
+            // its first 4K frame on the second GPU doing that while the first one waited for the shared host thread): one work
+            // item through the whole pipeline now, on every device, so that the first run_view starts warm
+            RenderSettings warm = g->rs;
+            warm.width = width; warm.height = height; warm.spp = 1; warm.light_sample_n = 1;
+            warm.range_set = true; warm.work_begin = 0; warm.work_end = 1;
+            const float eye0[3] = {0, 0, 0}, M0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            crt_render_stats ws;
+            rc = wavefront_render(g->wf[k], g->scene_of(k), warm, eye0, M0, 1.0f, g->streams[k], &ws);
+            if (rc != CRT_OK) return rc;
         }
         CRT_CUDA(cudaSetDevice(devices[0]));
         CRT_CUDA(cudaMalloc(&g->d_linear, sizeof(float) * 3 * (size_t)width * height));

@@ -5,6 +5,9 @@
 
 #include <chrono>
 #include <cmath>
+#include <ctime>
+#include <iostream>
+#include <sstream>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,11 +44,75 @@ static void resolve(const std::string& obj, const std::string& mtl, const std::s
 }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// The reference's window without the window (src/main.cu:288-378): its widgets as commands read from stdin, the scene and the
+// render object resident between frames as in its event loop. "render" is the Render button (main.cu:367-377: inverse view matrix
+// from the current eye / lookat / up, run_view, "render cost"), "save" the Save button (main.cu:342-354: .tmp/<time>.png).
+static int run_session(crt_render* render, crt_config cfg) {
+    bool rendered = false;
+    std::string line;
+    auto fail = [](const char* what) { printf("{\"error\": \"%s: %s\"}\n", what, crt_last_error()); fflush(stdout); };
+    while (std::getline(std::cin, line)) {
+        std::istringstream in(line);
+        std::string cmd;
+        if (!(in >> cmd) || cmd[0] == '#') continue;
+        if (cmd == "quit" || cmd == "exit") break;
+        if (cmd == "eye" || cmd == "lookat" || cmd == "up") {
+            float v[3];
+            if (!(in >> v[0] >> v[1] >> v[2])) { printf("{\"error\": \"%s needs three numbers\"}\n", cmd.c_str()); fflush(stdout); continue; }
+            float* dst = cmd == "eye" ? cfg.eye_pos : cmd == "lookat" ? cfg.lookat : cfg.up;
+            memcpy(dst, v, sizeof(v));
+            printf("{\"%s\": [%g, %g, %g]}\n", cmd.c_str(), v[0], v[1], v[2]);
+        } else if (cmd == "spp" || cmd == "light_sample_n") {
+            long n = 0;
+            const long hi = cmd == "spp" ? 2048 : 64;                       // the sliders' ranges, main.cu:318,330
+            if (!(in >> n) || n < 1) { printf("{\"error\": \"%s needs a positive integer\"}\n", cmd.c_str()); fflush(stdout); continue; }
+            if (n > hi) fprintf(stderr, "crt: %s %ld is beyond the reference slider's range (%ld); accepted\n", cmd.c_str(), n, hi);
+            if (cmd == "spp") { cfg.spp = (uint32_t)n; crt_render_set_spp(render, cfg.spp); }
+            else { cfg.light_sample_n = (uint32_t)n; crt_render_set_light_sample_n(render, cfg.light_sample_n); }
+            printf("{\"%s\": %ld}\n", cmd.c_str(), n);
+        } else if (cmd == "p_rr" || cmd == "P_RR") {
+            float p = 0;
+            if (!(in >> p) || !(p >= 0.0f && p <= 1.0f)) { printf("{\"error\": \"p_rr needs a number in [0, 1]\"}\n"); fflush(stdout); continue; }
+            cfg.p_rr = p;
+            crt_render_set_p_rr(render, p);
+            printf("{\"p_rr\": %g}\n", p);
+        } else if (cmd == "render") {
+            float M[9];
+            crt_inverse_view_matrix(cfg.eye_pos, cfg.lookat, cfg.up, M);
+            const double t0 = now_ms();
+            if (crt_render_run_view(render, cfg.eye_pos, M, cfg.fov_y * (float)M_PI / 180.0f) != CRT_OK) { fail("run_view"); continue; }
+            const double t1 = now_ms();
+            crt_render_stats st;
+            crt_render_get_stats(render, &st);
+            rendered = true;
+            printf("{\"render_cost_s\": %.6f, \"render_ms\": %.3f, \"msamples_per_s\": %.2f, \"spp\": %u}\n", (t1 - t0) * 1e-3, st.ms_total,
+                   st.ms_total > 0 ? (double)st.samples / (st.ms_total * 1e3) : 0.0, cfg.spp);
+        } else if (cmd == "save") {
+            std::string path;
+            if (!(in >> path)) {
+                char stamp[64];
+                const time_t now = time(nullptr);
+                strftime(stamp, sizeof(stamp), "%Y-%m-%d-%H-%M-%S", localtime(&now));
+                mkdir(".tmp", 0755);
+                path = std::string(".tmp/") + stamp + ".png";
+            }
+            if (!rendered) { printf("{\"error\": \"save: nothing rendered yet\"}\n"); fflush(stdout); continue; }
+            if (crt_render_save_png(render, path.c_str()) != CRT_OK) { fail("save_png"); continue; }
+            printf("{\"saved\": \"%s\"}\n", path.c_str());
+        } else {
+            printf("{\"error\": \"unknown command %s\"}\n", cmd.c_str());
+        }
+        fflush(stdout);
+    }
+    return 0;
+}
+
 #define DIE_IF(rc, what) do { if ((rc) != CRT_OK) { fprintf(stderr, "crt: %s failed: %s\n", what, crt_last_error()); return 1; } } while (0)
 
 int main(int argc, char** argv) {
     std::string config = "config.json", out = "out.png", root = ".";
     std::string checkpoint;
+    bool session = false;
     long spp = -1, seed = -1, width = -1, height = -1, chunk_spp = 64, stop_after = -1;
     int estimator = -1, device = 0, builder = CRT_BUILDER_PLOC8, gpus = 1;
     for (int i = 1; i < argc; ++i) {
@@ -65,6 +132,7 @@ int main(int argc, char** argv) {
         else if (a == "--checkpoint") checkpoint = next();
         else if (a == "--chunk-spp") chunk_spp = atol(next());
         else if (a == "--stop-after") stop_after = atol(next());
+        else if (a == "--session") session = true;
         else if (a == "--help" || a == "-h") {
             printf("usage: crt --config config.json [--root DIR] [--out image.png] [--spp N] [--seed S]\n"
                    "           [--width W --height H] [--estimator compat|mis] [--builder lbvh|lbvh8|ploc|ploc8] [--device D] [--gpus N]\n"
@@ -72,7 +140,10 @@ int main(int argc, char** argv) {
                    "  --checkpoint: progressive render in chunks of N samples per pixel (default 64); FILE is rewritten after\n"
                    "                every chunk and, if it exists at start, the render resumes from it (bit-identical image).\n"
                    "  --gpus N:     devices D .. D+N-1 render shares of the samples (the built scene is copied device to device), one\n"
-                   "                NCCL reduce sums the accumulation buffers on device D; the image is the one a single GPU renders.\n");
+                   "                NCCL reduce sums the accumulation buffers on device D; the image is the one a single GPU renders.\n"
+                   "  --session:    the controls of the reference's window (src/main.cu:288-378) as commands on stdin, the scene staying\n"
+                   "                resident between frames: eye X Y Z | lookat X Y Z | up X Y Z | spp N | p_rr P | light_sample_n N |\n"
+                   "                render | save [FILE] (default .tmp/<time>.png) | quit. One JSON line per command on stdout.\n");
             return 0;
         } else { fprintf(stderr, "crt: unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -105,7 +176,7 @@ int main(int argc, char** argv) {
     const float fovy_rad = cfg.fov_y * (float)M_PI / 180.0f;
     if (gpus > 1) {
         // several GPUs behind one handle (crt_group): this thread drives all of them
-        if (!checkpoint.empty()) { fprintf(stderr, "crt: --checkpoint renders on one GPU (omit --gpus)\n"); return 2; }
+        if (!checkpoint.empty() || session) { fprintf(stderr, "crt: --checkpoint and --session render on one GPU (omit --gpus)\n"); return 2; }
         std::vector<int> devs;
         for (int k = 0; k < gpus; ++k) devs.push_back(device + k);
         crt_group* group = nullptr;
@@ -142,6 +213,12 @@ int main(int argc, char** argv) {
     crt_render_set_light_sample_n(render, cfg.light_sample_n);
     crt_render_set_seed(render, cfg.seed);
     DIE_IF(crt_render_set_estimator(render, (int)cfg.estimator), "set_estimator");
+    if (session) {
+        int rc = run_session(render, cfg);
+        crt_render_destroy(render);
+        crt_scene_destroy(scene);
+        return rc;
+    }
     double t3 = now_ms();
     crt_render_stats st;
     uint64_t samples_rendered = (uint64_t)cfg.width * cfg.height * cfg.spp, resumed_from = 0;

@@ -216,6 +216,11 @@ int crt_render_get_accum(crt_render* r, float* rgb);
 /* Render::get_frame_buffer, include/Render.cuh:495 — tone-mapped RGB8, top row first
  * (include/Render.cuh:350: 255 * pow(clamp(c,0,1), 0.6), truncated). */
 int crt_render_get_rgb8(crt_render* r, uint8_t* out);
+/* The display path of Render::run_view(..., cudaGraphicsResource*), include/Render.cuh:446-469 (kernel -> device_frame_buffer ->
+ * cudaMemcpy device to device into the mapped pixel buffer object), for a viewer that owns the GL side: the tone-mapped RGB8 frame
+ * is written straight into d_rgb8, a DEVICE buffer of width*height*3 bytes on the render's device (e.g. the pointer
+ * cudaGraphicsResourceGetMappedPointer returns for the viewer's PBO). Returns when the frame is in the buffer. */
+int crt_render_get_rgb8_device(crt_render* r, void* d_rgb8);
 /* Render::save_frame_buffer, include/Render.cuh:489-493 */
 int crt_render_save_png(crt_render* r, const char* path);
 int crt_render_get_stats(crt_render* r, crt_render_stats* out);
