@@ -871,7 +871,8 @@ int crt_group_run_view(crt_group* g, const float eye[3], const float inv_view[9]
     g->reduce_ms = 0;
     g->resolved = false;
     if (G > 1) {
-        const unsigned long long band_px = std::max<unsigned long long>((npix + kGroupBands - 1) / kGroupBands, 1ull << 16);
+        // a band is at least 2^20 pixels (25 MB): a collective costs ~20 us before it moves a byte, the 800x600 frames go in one piece
+        const unsigned long long band_px = std::max<unsigned long long>((npix + kGroupBands - 1) / kGroupBands, 1ull << 20);
         CRT_CUDA(cudaSetDevice(g->devices[0]));
         CRT_CUDA(cudaEventRecord(g->ev_r0, g->streams[0]));
         int band = 0;
