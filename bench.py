@@ -728,14 +728,17 @@ def c5_workload(ctx, steps, warmup, n_total=None, with_c4=False):
     pin_rays.copy_(rays[:nb])
     pin_t, pin_f = torch.empty(nb, dtype=torch.float32).pin_memory(), torch.empty(nb, dtype=torch.int32).pin_memory()
     host_rays = pin_rays.numpy()
-    scene.trace_rays(host_rays[: min(nb, 1000000)], crt.RAY_CLOSEST, out=(pin_t.numpy(), pin_f.numpy()))     # warm-up (chunk buffers)
+    for _ in range(max(1, min(warmup, 2))):               # warm-up at full size: chunk buffers, first touch of the result pages
+        scene.trace_rays(host_rays, crt.RAY_CLOSEST, out=(pin_t.numpy(), pin_f.numpy()))
     ctx.barrier()
+    e2e_calls = max(1, min(steps, 3))
     t0 = time.time()
-    ht, hf, _ = scene.trace_rays(host_rays, crt.RAY_CLOSEST, out=(pin_t.numpy(), pin_f.numpy()))
-    e2e_s = ctx.allmax([time.time() - t0])[0]
+    for _ in range(e2e_calls):
+        ht, hf, _ = scene.trace_rays(host_rays, crt.RAY_CLOSEST, out=(pin_t.numpy(), pin_f.numpy()))
+    e2e_s = ctx.allmax([(time.time() - t0) / e2e_calls])[0]
     pageable = np.array(host_rays[: min(nb, 8000000)])
     page_t, page_f = np.zeros(len(pageable), np.float32), np.zeros(len(pageable), np.int32)
-    scene.trace_rays(pageable[:1000000], crt.RAY_CLOSEST, out=(page_t, page_f))
+    scene.trace_rays(pageable, crt.RAY_CLOSEST, out=(page_t, page_f))
     t0 = time.time()
     scene.trace_rays(pageable, crt.RAY_CLOSEST, out=(page_t, page_f))
     pageable_s = ctx.allmax([time.time() - t0])[0]
@@ -768,7 +771,9 @@ def c5_workload(ctx, steps, warmup, n_total=None, with_c4=False):
             "e2e": {"value": round(e2e_rate, 1), "unit": "Mrays/s", "h2d_bytes_per_step": nb * 32, "d2h_bytes_per_step": nb * 8,
                     "pcie_frac": round(e2e_rate * 1e6 * 32 / 1e9 / ctx.world / pcie_gbs, 3),
                     "pageable_mrays_s": round(len(pageable) * ctx.world / pageable_s / 1e6, 1),
-                    "note": "crt_trace_rays with page-locked host buffers, %d rays per GPU; pcie_frac = 32 B per ray host-to-device (the 8 B per ray of "
+                    "calls": e2e_calls,
+                    "note": "crt_trace_rays with page-locked host buffers, %d rays per GPU, mean of the timed calls after a full-size warm-up call; "
+                            "pcie_frac = 32 B per ray host-to-device (the 8 B per ray of "
                             "results go the other way at the same time) against %.0f GB/s per direction of one PCIe gen5 x16 link (CRT_PCIE_GBS); "
                             "pageable_mrays_s: the same call with pageable numpy arrays (pinned staging + host-thread copies inside the library)" % (nb, pcie_gbs),
                     "parity": "first %d hits == oracle: %s" % (len(sample), parity)},

@@ -202,6 +202,7 @@ struct RayBatcher {
     int device = 0;
     int blocks = 0;
     uint32_t* fetch = nullptr;                  // two queue counters, 128 bytes apart (one per pipeline slot)
+    bool chunk_from_env = false;
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaStream_t st[2] = {nullptr, nullptr};
     // host-buffer path, allocated on first use
@@ -305,7 +306,12 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
 int trace_rays_host(RayBatcher* b, const DeviceScene& ds, const float* rays, uint64_t n, int mode, float* t_out, int32_t* face_out,
                     float* kernel_ms) {
     if (b->chunk == 0) {
-        uint64_t chunk = env_u32("CRT_BATCH_CHUNK", 4u << 20);          // 4 Mi rays: 128 MB in, 32 MB out per chunk
+        // 4 Mi rays (128 MB in, 32 MB out per chunk) suit the staged path (host threads copy a chunk while the previous one is on
+        // the link: 721 Mrays/s pageable, 674 at 2 Mi); page-locked caller buffers go in halves of that - nothing is staged, and
+        // the end of the pipeline (trace + results of the last chunk, not overlapped) is shorter: 1,616 vs 1,547 Mrays/s for 20 M
+        // rays, 1,676 vs 1,659 for 100 M (profiles/r02_s33_e2e_chunks.log). CRT_BATCH_CHUNK sets one size for both.
+        b->chunk_from_env = getenv("CRT_BATCH_CHUNK") != nullptr;
+        uint64_t chunk = env_u32("CRT_BATCH_CHUNK", 4u << 20);
         chunk = std::max<uint64_t>(1024, std::min<uint64_t>(chunk, 1ull << 28));
         for (int k = 0; k < 2; ++k) {
             CRT_CUDA(cudaMalloc(&b->d_rays[k], sizeof(float4) * 2 * chunk));
@@ -315,11 +321,11 @@ int trace_rays_host(RayBatcher* b, const DeviceScene& ds, const float* rays, uin
         b->chunk = chunk;
     }
     const bool in_place_in = is_page_locked(rays), in_place_t = is_page_locked(t_out), in_place_f = is_page_locked(face_out);
-    const uint64_t C = b->chunk;
+    const uint64_t C = in_place_in && !b->chunk_from_env ? b->chunk / 2 : b->chunk;
     for (int k = 0; k < 2; ++k) {
-        if (!in_place_in && !b->h_rays[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_rays[k], sizeof(float4) * 2 * C, cudaHostAllocDefault));
-        if (t_out && !in_place_t && !b->h_t[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_t[k], sizeof(float) * C, cudaHostAllocDefault));
-        if (face_out && !in_place_f && !b->h_face[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_face[k], sizeof(int) * C, cudaHostAllocDefault));
+        if (!in_place_in && !b->h_rays[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_rays[k], sizeof(float4) * 2 * b->chunk, cudaHostAllocDefault));
+        if (t_out && !in_place_t && !b->h_t[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_t[k], sizeof(float) * b->chunk, cudaHostAllocDefault));
+        if (face_out && !in_place_f && !b->h_face[k]) CRT_CUDA(cudaHostAlloc((void**)&b->h_face[k], sizeof(int) * b->chunk, cudaHostAllocDefault));
     }
     const uint64_t n_chunks = (n + C - 1) / C;
     float ms_total = 0;

@@ -195,3 +195,27 @@ def test_host_buffer_batches_are_chunked_and_exact(gpu, orc, monkeypatch):
             assert np.array_equal(f2, want_f) and np.array_equal(t2.view(np.uint32), want_t.view(np.uint32))
     t, f, _ = a.trace_rays(rays[:0], gpu.RAY_CLOSEST)
     assert len(t) == 0
+
+
+def test_default_chunks_page_locked_then_pageable_on_one_scene(gpu, monkeypatch):
+    """Without CRT_BATCH_CHUNK page-locked caller buffers go in half-size chunks and pageable ones in whole chunks through the same
+    staging buffers of the scene: mixed kinds of buffers, one scene, more rays than one chunk, the same hits every way."""
+    import torch
+    from tools import synthetic as sy
+    monkeypatch.delenv("CRT_BATCH_CHUNK", raising=False)
+    verts, mat, obj, mats = sy.c4_scene(33)
+    a = gpu.Scene().add_triangles(verts, mat, obj, mats)
+    a.set_BVH(2, builder=3)
+    n = (4 << 20) + (2 << 20) + 4321                                      # one whole chunk and a ragged rest; three half chunks
+    d_rays = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+    a.random_rays_device(d_rays.data_ptr(), n, start=11, key=0xC5, any_hit=False)
+    d_t, d_f = torch.empty(n, dtype=torch.float32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+    a.trace_rays_device(d_rays.data_ptr(), n, gpu.RAY_CLOSEST, d_t.data_ptr(), d_f.data_ptr())
+    want_t, want_f = d_t.cpu().numpy(), d_f.cpu().numpy()
+    pin_rays = d_rays.cpu().pin_memory()
+    pageable = np.array(pin_rays.numpy())
+    pin_t, pin_f = torch.empty(n, dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory()
+    # page-locked rays with pageable results first (staging for the results is sized here), then everything pageable, then all page-locked
+    for rays, out in ((pin_rays.numpy(), None), (pageable, None), (pin_rays.numpy(), (pin_t.numpy(), pin_f.numpy())), (pageable, (pin_t.numpy(), pin_f.numpy()))):
+        t, f, _ = a.trace_rays(rays, gpu.RAY_CLOSEST, out=out) if out is not None else a.trace_rays(rays, gpu.RAY_CLOSEST)
+        assert np.array_equal(f, want_f) and np.array_equal(t.view(np.uint32), want_t.view(np.uint32))
