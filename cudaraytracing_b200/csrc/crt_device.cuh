@@ -428,6 +428,7 @@ CRT_DEV void trace_persistent_queue(const SceneView& sc, uint32_t n, uint32_t* f
     typename Walker::Entry stack[Walker::kLocal];
     Walker wk;
     wk.init();
+    wk.configure(n);
     uint32_t idx = 0;
     V3 o = mk3(0, 0, 0), inv = mk3(0, 0, 0);
     float tlimit = 0.0f;
@@ -521,6 +522,7 @@ struct PairWalker {
     typedef int Entry;
     int sp, cur, qn;                                   // qn: queued leaves, the same value in every lane
     CRT_DEV void init() { sp = 0; cur = kDone; qn = 0; }
+    CRT_DEV void configure(uint32_t) {}
     CRT_DEV void start(bool live, V3) { sp = 0; cur = live ? 0 : kDone; }
     CRT_DEV bool walking() const { return cur != kDone; }
     CRT_DEV void stop() { cur = kDone; sp = 0; }

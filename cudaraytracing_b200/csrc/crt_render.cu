@@ -155,9 +155,11 @@ int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device
 // =============================================================================================
 // node-layout dispatch: WIDE = false: 64-byte child-pair nodes, true: 80-byte 8-wide compressed nodes
 // =============================================================================================
-template <int MODE, bool WIDE, typename Load, typename Done>
+// GATED: the 8-wide walker takes its second step of a turn only with enough lanes (WideWalkerGated, crt_wide.cuh)
+template <int MODE, bool WIDE, bool GATED = false, typename Load, typename Done>
 CRT_DEV void trace_queue(const SceneView& sc, uint32_t n, uint32_t* fetch, Load load, Done done) {
-    if (WIDE) trace_persistent_queue<MODE, WideWalker>(sc, n, fetch, load, done);
+    if (WIDE && GATED) trace_persistent_queue<MODE, WideWalkerGated>(sc, n, fetch, load, done);
+    else if (WIDE) trace_persistent_queue<MODE, WideWalker>(sc, n, fetch, load, done);
     else trace_persistent_queue<MODE, PairWalker>(sc, n, fetch, load, done);
 }
 template <int MODE, bool WIDE>
@@ -173,7 +175,7 @@ template <int MODE, bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_trace_batch(SceneView sc, const float4* __restrict__ rays, uint32_t n,
                                                      float* __restrict__ t_out, int* __restrict__ face_out,
                                                      uint32_t* __restrict__ fetch) {
-    trace_queue<MODE, WIDE>(
+    trace_queue<MODE, WIDE, MODE == 1>(
         sc, n, fetch,
         [&](uint32_t i, V3& o, V3& d, float& tmax) {
             const float4 ro = __ldg(rays + 2 * (size_t)i), rd = __ldg(rays + 2 * (size_t)i + 1);
@@ -583,7 +585,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_extend(SceneView sc, Counters* c, const float4* __restrict__ q_o,
                                                 const float4* __restrict__ q_d, float* __restrict__ hit_t,
                                                 int* __restrict__ hit_slot) {
-    trace_queue<0, WIDE>(
+    trace_queue<0, WIDE, true>(
         sc, c->n_cur, &c->fetch_extend,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
         [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });

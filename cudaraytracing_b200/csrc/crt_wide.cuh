@@ -218,7 +218,15 @@ CRT_DEV HitRec traverse_wide(const SceneView& sc, V3 o, V3 d, float tmax) {
 #ifndef CRT_WSSTACK
 #define CRT_WSSTACK 4
 #endif
-struct WideWalker {
+// MINLANES (template parameter of the walker): a second node step in a turn only while at least that many lanes still have a
+// node in hand; the others keep theirs for the next turn, when the refilled lanes step with them. 20 pays where rays are long -
+// k_extend 42.2 -> 41.1 ms per 4K spp-48 frame, any-hit batches of C5 +5.8 % - and costs where turns are few or rays mixed:
+// k_shadow +-0, closest-hit batches -1.3 %, the tail path tracer's small frames -5...9 % (profiles/r02_late_levers.md, r02_s37).
+#ifndef CRT_WQ_MINLANES
+#define CRT_WQ_MINLANES 20
+#endif
+template <int MINLANES>
+struct WideWalkerT {
     static constexpr int kFlush = CRT_WQFLUSH;
     static constexpr int kSteps = CRT_WQSTEPS;
     static constexpr int kCap = kFlush + 32 * 8 * kSteps;
@@ -229,7 +237,10 @@ struct WideWalker {
     typedef uint2 Entry;
     int sp;
     uint32_t g_base, g_bits, oinv;
-    CRT_DEV void init() { sp = 0; g_base = 0; g_bits = 0; oinv = 0; }
+    int min_lanes;
+    CRT_DEV void init() { sp = 0; g_base = 0; g_bits = 0; oinv = 0; min_lanes = 0; }
+    // queues of fewer than 2^22 rays (the shipped 800x600 frames) are bound by the latency of their rays, not by issue slots: no gate
+    CRT_DEV void configure(uint32_t n_rays) { min_lanes = MINLANES > 0 && n_rays >= (1u << 22) ? MINLANES : 0; }
     CRT_DEV void start(bool live, V3 inv) {
         oinv = wide_octant(inv);
         sp = 0;
@@ -246,6 +257,7 @@ struct WideWalker {
         const uint4* nodes = (const uint4*)sc.nodes;
 #pragma unroll
         for (int r = 0; r < kSteps; ++r) {
+            if (MINLANES > 0 && r > 0 && min_lanes > 0 && __popc(__ballot_sync(0xffffffffu, (g_bits & 0xffu) != 0u || sp > 0)) < min_lanes) break;
             if ((g_bits & 0xffu) == 0u && sp > 0) {
                 --sp;
                 const uint2 e = (kShared > 0 && sp < kShared) ? s_wstack[sp][threadIdx.x] : stack[sp - kShared];
@@ -282,5 +294,7 @@ struct WideWalker {
         }
     }
 };
+typedef WideWalkerT<0> WideWalker;                       // every lane steps kSteps times per turn
+typedef WideWalkerT<CRT_WQ_MINLANES> WideWalkerGated;
 
 }  // namespace crt
