@@ -585,7 +585,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(128, CRT_MINB) k_extend(SceneView sc, Counters* c, const float4* __restrict__ q_o,
                                                 const float4* __restrict__ q_d, float* __restrict__ hit_t,
                                                 int* __restrict__ hit_slot) {
-    trace_queue<0, WIDE, true>(
+    trace_queue<0, WIDE>(
         sc, c->n_cur, &c->fetch_extend,
         [&](uint32_t i, V3& o, V3& d, float& tmax) { o = mk3(q_o[i]); d = mk3(q_d[i]); tmax = FLT_MAX; return true; },
         [&](uint32_t i, const HitRec& h) { hit_t[i] = h.t; hit_slot[i] = h.slot; });

@@ -219,9 +219,10 @@ CRT_DEV HitRec traverse_wide(const SceneView& sc, V3 o, V3 d, float tmax) {
 #define CRT_WSSTACK 4
 #endif
 // MINLANES (template parameter of the walker): a second node step in a turn only while at least that many lanes still have a
-// node in hand; the others keep theirs for the next turn, when the refilled lanes step with them. 20 pays where rays are long -
-// k_extend 42.2 -> 41.1 ms per 4K spp-48 frame, any-hit batches of C5 +5.8 % - and costs where turns are few or rays mixed:
-// k_shadow +-0, closest-hit batches -1.3 %, the tail path tracer's small frames -5...9 % (profiles/r02_late_levers.md, r02_s37).
+// node in hand; the others keep theirs for the next turn, when the refilled lanes step with them. Used by the any-hit batch
+// kernel only (C5 any-hit +6.5 %). Everywhere else it was measured and left out (profiles/r02_late_levers.md, r02_s37 / s38 / s40):
+// k_shadow +-0, closest-hit batches -1.5 %, the tail path tracer's small frames -5...9 %, and k_extend gains on cornell-box
+// (42.1 -> 41.0 ms per 4K spp-48 frame) what it loses on the 10 M-triangle scene (C4 -1.3 %) and on veach-mis (-2 %).
 #ifndef CRT_WQ_MINLANES
 #define CRT_WQ_MINLANES 20
 #endif
