@@ -46,7 +46,7 @@ CRT_DEV V3 cross(V3 a, V3 b) {
 // warp; in k_shade that was 17 % of the instructions (profiles/r02_div_zero.md). The quotient is a itself (the zero keeps its sign),
 // so the division is given a harmless numerator and the result selected: same value, no call.
 CRT_DEV float div_by_pos(float a, float b) {
-#ifdef CRT_NO_DIV_GUARD                            // the plain division, for A/B measurements (tools/sessions/r02_s24.sh, r02_s35.sh)
+#ifdef CRT_NO_DIV_GUARD                            // the plain division, for A/B measurements (tools/sessions/log/r02_s24.sh, r02_s35.sh)
     return a / b;
 #endif
     const bool z = a == 0.0f;
