@@ -17,6 +17,7 @@ _LIB = None
 
 ESTIMATOR_COMPAT, ESTIMATOR_MIS = 0, 1
 RAY_CLOSEST, RAY_ANY = 0, 1
+RAY_SORTED = 0x100                      # flag: trace in (origin cell, direction octant) order, hits back in the caller's order
 BUILDER_LBVH, BUILDER_LBVH8, BUILDER_PLOC, BUILDER_PLOC8 = 0, 1, 2, 3     # bit 0: 8-wide nodes, bit 1: PLOC topology
 MAX_OBJ_PATHS, PATH_LEN = 16, 1024
 

@@ -323,7 +323,7 @@ int crt_trace_rays_device(crt_scene* s, const void* d_rays, uint64_t n, int mode
                           float* kernel_ms) {
     return guarded("crt_trace_rays_device", [&]() -> int {
     CHECK_ARG(s && (n == 0 || d_rays), "crt_trace_rays_device: null argument");
-    CHECK_ARG(mode == CRT_RAY_CLOSEST || mode == CRT_RAY_ANY, "crt_trace_rays_device: unknown mode");
+    CHECK_ARG((mode & ~CRT_RAY_SORTED) == CRT_RAY_CLOSEST || (mode & ~CRT_RAY_SORTED) == CRT_RAY_ANY, "crt_trace_rays_device: unknown mode");
     if (!s->built) { set_error("crt_trace_rays: BVH not built"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(s->dev.device));
     if (n == 0) { if (kernel_ms) *kernel_ms = 0; return CRT_OK; }
@@ -336,7 +336,7 @@ int crt_trace_rays_device(crt_scene* s, const void* d_rays, uint64_t n, int mode
 int crt_trace_rays(crt_scene* s, const float* rays, uint64_t n, int mode, float* t_out, int32_t* face_out, float* kernel_ms) {
     return guarded("crt_trace_rays", [&]() -> int {
     CHECK_ARG(s && (n == 0 || rays), "crt_trace_rays: null argument");
-    CHECK_ARG(mode == CRT_RAY_CLOSEST || mode == CRT_RAY_ANY, "crt_trace_rays: unknown mode");
+    CHECK_ARG((mode & ~CRT_RAY_SORTED) == CRT_RAY_CLOSEST || (mode & ~CRT_RAY_SORTED) == CRT_RAY_ANY, "crt_trace_rays: unknown mode");
     if (!s->built) { set_error("crt_trace_rays: BVH not built"); return CRT_ERR_STATE; }
     CRT_CUDA(cudaSetDevice(s->dev.device));
     if (n == 0) { if (kernel_ms) *kernel_ms = 0; return CRT_OK; }

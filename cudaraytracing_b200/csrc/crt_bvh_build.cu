@@ -184,6 +184,28 @@ __global__ void k_sort_scatter(const uint64_t* __restrict__ keys_in, const uint3
     }
 }
 
+// The same sort for other callers (ordered ray batches, crt_render.cu): the low 8 * passes bits of the keys.
+size_t radix_sort_hist_words(uint32_t n) { return 256 * (size_t)((n + kSortTile - 1) / kSortTile); }
+size_t radix_sort_scratch_words(uint32_t n) { return (radix_sort_hist_words(n) + kScanTile - 1) / kScanTile + 1; }
+cudaError_t radix_sort_pairs(uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, uint32_t n, int passes, uint32_t* ghist,
+                             uint32_t* scratch, cudaStream_t st, uint64_t** k_sorted, uint32_t** v_sorted) {
+    const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    uint64_t *kin = k0, *kout = k1;
+    uint32_t *vin = v0, *vout = v1;
+    for (int pass = 0; pass < passes && n > 0; ++pass) {
+        const int shift = pass * 8;
+        k_sort_hist<<<n_tiles, 256, 0, st>>>(kin, n, shift, ghist, n_tiles);
+        cudaError_t e = exclusive_scan_u32(ghist, ghist, 256 * n_tiles, scratch, nullptr, st);
+        if (e != cudaSuccess) return e;
+        k_sort_scatter<<<n_tiles, 256, 0, st>>>(kin, vin, kout, vout, n, shift, ghist, n_tiles);
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    *k_sorted = kin;
+    *v_sorted = vin;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // build kernels
 // ------------------------------------------------------------------------------------------

@@ -50,12 +50,22 @@ struct DeviceScene {
 int build_bvh_device(DeviceScene& ds, const float* d_verts, const float4* d_face_shade, uint32_t n, uint32_t thresh_n,
                      int builder, cudaStream_t st, float* build_ms);
 
+// The builder's stable LSD radix sort of (uint64 key, uint32 value) pairs, 8 bits per pass, on the low 8 * passes bits; k1 / v1 are
+// the ping-pong buffers, ghist / scratch hold radix_sort_hist_words(n) / radix_sort_scratch_words(n) uint32. The sorted arrays are
+// *k_sorted / *v_sorted (one of the two buffers each).
+size_t radix_sort_hist_words(uint32_t n);
+size_t radix_sort_scratch_words(uint32_t n);
+cudaError_t radix_sort_pairs(uint64_t* k0, uint64_t* k1, uint32_t* v0, uint32_t* v1, uint32_t n, int passes, uint32_t* ghist,
+                             uint32_t* scratch, cudaStream_t st, uint64_t** k_sorted, uint32_t** v_sorted);
+
 // Uploads materials and lights, builds the BVH. Leaves the device selected.
 int upload_scene(const HostScene& hs, uint32_t thresh_n, int builder, int device, DeviceScene& ds, float* build_ms);
 
 // Ray batches. rays: n * 2 float4 {o,tmax}{d,0}. A RayBatcher holds what a batch call needs besides the scene - queue
 // counters, events, two streams and, for host buffers, chunk-sized device buffers and pinned staging - for the life of
 // the scene handle (round 1 paid a cudaMalloc / cudaFree / event create per call).
+// mode: CRT_RAY_CLOSEST / CRT_RAY_ANY, optionally | CRT_RAY_SORTED (the batch, or each chunk of it, is traced in the order of
+// (Morton code of the origin's cell on a 128^3 grid over the scene, direction octant) and the hits are written back in the caller's order).
 struct RayBatcher;
 int ray_batcher_create(const DeviceScene& ds, RayBatcher** out);
 void ray_batcher_destroy(RayBatcher* b);

@@ -215,6 +215,19 @@ struct RayBatcher {
     float4* h_rays[2] = {nullptr, nullptr};     // pinned staging for pageable callers
     float* h_t[2] = {nullptr, nullptr};
     int* h_face[2] = {nullptr, nullptr};
+    // CRT_RAY_SORTED, allocated on first use and grown: keys / permutation (ping-pong), the ordered copy of the rays and of the hits
+    struct SortBufs {
+        uint64_t cap = 0;
+        uint64_t *k0 = nullptr, *k1 = nullptr;
+        uint32_t *v0 = nullptr, *v1 = nullptr, *ghist = nullptr, *scratch = nullptr;
+        float4* rays = nullptr;
+        float* t = nullptr;
+        int* face = nullptr;
+        void release() {
+            cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(ghist); cudaFree(scratch); cudaFree(rays); cudaFree(t); cudaFree(face);
+            *this = SortBufs();
+        }
+    } sort[2];
 };
 
 int ray_batcher_create(const DeviceScene& ds, RayBatcher** out) {
@@ -247,12 +260,72 @@ void ray_batcher_destroy(RayBatcher* b) {
         if (b->h_rays[k]) cudaFreeHost(b->h_rays[k]);
         if (b->h_t[k]) cudaFreeHost(b->h_t[k]);
         if (b->h_face[k]) cudaFreeHost(b->h_face[k]);
+        b->sort[k].release();
     }
     delete b;
 }
 
-static void launch_trace_batch(const RayBatcher* b, const DeviceScene& ds, const float4* d_rays, uint32_t cnt, int mode, float* t_o, int* f_o,
-                               uint32_t* fetch, cudaStream_t st) {
+// ---- CRT_RAY_SORTED: "warp-coherent ray sorting" as an option of the batch calls --------------------------------------------------
+// Key of a ray: Morton code of its origin's cell on a 128^3 grid over the scene's bounds, then the direction octant (24 bits, three
+// passes of the builder's radix sort); the rays are gathered in that order, traced, and the hits scattered back to the caller's order.
+// Off by default because it does not pay here: a PERFECT order, for free, makes the trace of C5 6-8 % faster (the kernels wait on
+// instruction issue, not on memory coherence), and the sort costs more than that (profiles/r02_late_levers.md).
+static constexpr int kRaySortCellBits = 7;
+CRT_DEV uint32_t spread3(uint32_t x) {                   // 0b abcdefg -> 0b a00b00c00d00e00f00g
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+__global__ void k_ray_keys(const float4* __restrict__ rays, uint32_t n, float lox, float loy, float loz, float sx, float sy, float sz,
+                           uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = __ldg(rays + 2 * (size_t)i), d = __ldg(rays + 2 * (size_t)i + 1);
+    const int hi = (1 << kRaySortCellBits) - 1;
+    const int cx = min(max((int)((o.x - lox) * sx), 0), hi), cy = min(max((int)((o.y - loy) * sy), 0), hi),
+              cz = min(max((int)((o.z - loz) * sz), 0), hi);
+    const uint32_t cell = spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
+    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    keys[i] = ((uint64_t)cell << 3) | oct;
+    vals[i] = i;
+}
+__global__ void k_gather_rays(const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n, float4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = perm[i];
+    out[2 * (size_t)i] = __ldg(rays + 2 * (size_t)j);
+    out[2 * (size_t)i + 1] = __ldg(rays + 2 * (size_t)j + 1);
+}
+__global__ void k_scatter_hits(const uint32_t* __restrict__ perm, uint32_t n, const float* __restrict__ t_in, const int* __restrict__ f_in,
+                               float* __restrict__ t_out, int* __restrict__ f_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = perm[i];
+    if (t_out) t_out[j] = t_in[i];
+    if (f_out) f_out[j] = f_in[i];
+}
+static int ensure_sort_bufs(RayBatcher::SortBufs& sb, uint64_t cnt) {
+    if (sb.cap >= cnt) return CRT_OK;
+    sb.release();
+    const uint32_t n = (uint32_t)cnt;
+    CRT_CUDA(cudaMalloc(&sb.k0, sizeof(uint64_t) * cnt));
+    CRT_CUDA(cudaMalloc(&sb.k1, sizeof(uint64_t) * cnt));
+    CRT_CUDA(cudaMalloc(&sb.v0, sizeof(uint32_t) * cnt));
+    CRT_CUDA(cudaMalloc(&sb.v1, sizeof(uint32_t) * cnt));
+    CRT_CUDA(cudaMalloc(&sb.ghist, sizeof(uint32_t) * radix_sort_hist_words(n)));
+    CRT_CUDA(cudaMalloc(&sb.scratch, sizeof(uint32_t) * radix_sort_scratch_words(n)));
+    CRT_CUDA(cudaMalloc(&sb.rays, sizeof(float4) * 2 * cnt));
+    CRT_CUDA(cudaMalloc(&sb.t, sizeof(float) * cnt));
+    CRT_CUDA(cudaMalloc(&sb.face, sizeof(int) * cnt));
+    sb.cap = cnt;
+    return CRT_OK;
+}
+
+static void launch_trace_kernel(const RayBatcher* b, const DeviceScene& ds, const float4* d_rays, uint32_t cnt, int mode, float* t_o, int* f_o,
+                                uint32_t* fetch, cudaStream_t st) {
     cudaMemsetAsync(fetch, 0, sizeof(uint32_t), st);
     if (mode == CRT_RAY_CLOSEST) {
         if (ds.wide) k_trace_batch<0, true><<<b->blocks, 128, 0, st>>>(ds.view(), d_rays, cnt, t_o, f_o, fetch);
@@ -263,14 +336,43 @@ static void launch_trace_batch(const RayBatcher* b, const DeviceScene& ds, const
     }
 }
 
+// slot: which of the batcher's two sets of ordering buffers (one per pipeline stream)
+static int launch_trace_batch(RayBatcher* b, const DeviceScene& ds, const float4* d_rays, uint32_t cnt, int mode, float* t_o, int* f_o,
+                              uint32_t* fetch, cudaStream_t st, int slot = 0) {
+    const int kind = mode & ~CRT_RAY_SORTED;
+    if (!(mode & CRT_RAY_SORTED) || cnt == 0) {
+        launch_trace_kernel(b, ds, d_rays, cnt, kind, t_o, f_o, fetch, st);
+        return CRT_OK;
+    }
+    RayBatcher::SortBufs& sb = b->sort[slot];
+    int rc = ensure_sort_bufs(sb, cnt);
+    if (rc != CRT_OK) return rc;
+    const float cells = (float)(1 << kRaySortCellBits);
+    float sc[3];
+    for (int a = 0; a < 3; ++a) {
+        const float ext = ds.bounds[3 + a] - ds.bounds[a];
+        sc[a] = ext > 0.0f ? cells / ext : 0.0f;
+    }
+    const uint32_t nb = (cnt + 255) / 256;
+    k_ray_keys<<<nb, 256, 0, st>>>(d_rays, cnt, ds.bounds[0], ds.bounds[1], ds.bounds[2], sc[0], sc[1], sc[2], sb.k0, sb.v0);
+    uint64_t* ks = nullptr;
+    uint32_t* perm = nullptr;
+    CRT_CUDA(radix_sort_pairs(sb.k0, sb.k1, sb.v0, sb.v1, cnt, (3 * kRaySortCellBits + 3 + 7) / 8, sb.ghist, sb.scratch, st, &ks, &perm));
+    k_gather_rays<<<nb, 256, 0, st>>>(d_rays, perm, cnt, sb.rays);
+    launch_trace_kernel(b, ds, sb.rays, cnt, kind, sb.t, sb.face, fetch, st);
+    k_scatter_hits<<<nb, 256, 0, st>>>(perm, cnt, sb.t, sb.face, t_o, f_o);
+    return CRT_OK;
+}
+
 int trace_rays_device(RayBatcher* b, const DeviceScene& ds, const float4* d_rays, uint64_t n, int mode, float* d_t, int* d_face,
                       cudaStream_t st, float* kernel_ms) {
-    const uint64_t chunk = 1ull << 30;                   // queue indices are 32-bit
+    const uint64_t chunk = (mode & CRT_RAY_SORTED) ? 1ull << 27 : 1ull << 30;   // queue indices are 32-bit; ordering buffers are ~65 B per ray
     float ms_total = 0;
     for (uint64_t off = 0; off < n; off += chunk) {
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, n - off);
         CRT_CUDA(cudaEventRecord(b->ev_a[0], st));
-        launch_trace_batch(b, ds, d_rays + 2 * off, cnt, mode, d_t ? d_t + off : nullptr, d_face ? d_face + off : nullptr, b->fetch, st);
+        int rc = launch_trace_batch(b, ds, d_rays + 2 * off, cnt, mode, d_t ? d_t + off : nullptr, d_face ? d_face + off : nullptr, b->fetch, st);
+        if (rc != CRT_OK) return rc;
         CRT_CUDA(cudaGetLastError());
         CRT_CUDA(cudaEventRecord(b->ev_b[0], st));
         CRT_CUDA(cudaStreamSynchronize(st));
@@ -350,7 +452,7 @@ int trace_rays_host(RayBatcher* b, const DeviceScene& ds, const float* rays, uin
         if (!in_place_in) { parallel_memcpy(b->h_rays[s], src, sizeof(float) * 8 * cnt); src = (const float*)b->h_rays[s]; }
         CRT_CUDA(cudaMemcpyAsync(b->d_rays[s], src, sizeof(float) * 8 * cnt, cudaMemcpyHostToDevice, b->st[s]));
         CRT_CUDA(cudaEventRecord(b->ev_a[s], b->st[s]));
-        launch_trace_batch(b, ds, b->d_rays[s], (uint32_t)cnt, mode, b->d_t[s], b->d_face[s], b->fetch + 32 * s, b->st[s]);
+        { int rc = launch_trace_batch(b, ds, b->d_rays[s], (uint32_t)cnt, mode, b->d_t[s], b->d_face[s], b->fetch + 32 * s, b->st[s], s); if (rc != CRT_OK) return rc; }
         CRT_CUDA(cudaGetLastError());
         CRT_CUDA(cudaEventRecord(b->ev_b[s], b->st[s]));
         if (t_out) CRT_CUDA(cudaMemcpyAsync(in_place_t ? t_out + off : b->h_t[s], b->d_t[s], sizeof(float) * cnt, cudaMemcpyDeviceToHost, b->st[s]));

@@ -71,6 +71,10 @@ typedef enum crt_estimator { CRT_ESTIMATOR_COMPAT = 0, CRT_ESTIMATOR_MIS = 1 } c
  * (DESIGN.md "BVH build"). Node layouts, leaf rule and exports are those of LBVH / LBVH8. */
 typedef enum crt_builder { CRT_BUILDER_LBVH = 0, CRT_BUILDER_LBVH8 = 1, CRT_BUILDER_PLOC = 2, CRT_BUILDER_PLOC8 = 3 } crt_builder;
 typedef enum crt_ray_mode { CRT_RAY_CLOSEST = 0, CRT_RAY_ANY = 1 } crt_ray_mode;
+/* Flag to OR into a ray mode: trace the batch (each chunk of a host-buffer batch) in the order of (Morton code of the origin's cell
+ * on a 128^3 grid over the scene, direction octant) - "warp-coherent ray sorting" - and write the hits back in the caller's order. The
+ * results are the same; on this hardware the order buys less than the sort costs (profiles/r02_late_levers.md), so it is off unless asked for. */
+#define CRT_RAY_SORTED 0x100
 
 /* 64-byte BVH node as exported by crt_scene_export_bvh (DESIGN.md "Layout"). */
 typedef struct crt_bvh_node {

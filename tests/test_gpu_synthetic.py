@@ -219,3 +219,37 @@ def test_default_chunks_page_locked_then_pageable_on_one_scene(gpu, monkeypatch)
     for rays, out in ((pin_rays.numpy(), None), (pageable, None), (pin_rays.numpy(), (pin_t.numpy(), pin_f.numpy())), (pageable, (pin_t.numpy(), pin_f.numpy()))):
         t, f, _ = a.trace_rays(rays, gpu.RAY_CLOSEST, out=out) if out is not None else a.trace_rays(rays, gpu.RAY_CLOSEST)
         assert np.array_equal(f, want_f) and np.array_equal(t.view(np.uint32), want_t.view(np.uint32))
+
+
+def test_sorted_batches_give_the_same_hits(gpu, monkeypatch):
+    """CRT_RAY_SORTED: the batch is traced in (origin cell, direction octant) order and the hits come back in the caller's order -
+    the same hits as without the flag, through the device-buffer call, the chunked host-buffer call (both pipeline slots, a ragged
+    last chunk) and for a batch smaller than one sort tile."""
+    import torch
+    from tools import synthetic as sy
+    monkeypatch.setenv("CRT_BATCH_CHUNK", "8192")
+    verts, mat, obj, mats = sy.c4_scene(65)
+    a = gpu.Scene().add_triangles(verts, mat, obj, mats)
+    a.set_BVH(2, builder=3)
+    for n in (8192 * 4 + 777, 300):
+        for any_hit, mode in ((False, gpu.RAY_CLOSEST), (True, gpu.RAY_ANY)):
+            d_rays = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+            a.random_rays_device(d_rays.data_ptr(), n, start=3, key=0xC5, any_hit=any_hit)
+            t0, f0 = torch.empty(n, dtype=torch.float32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+            t1, f1 = torch.full((n,), -7.0, dtype=torch.float32, device="cuda"), torch.full((n,), -7, dtype=torch.int32, device="cuda")
+            a.trace_rays_device(d_rays.data_ptr(), n, mode, t0.data_ptr(), f0.data_ptr())
+            ms = a.trace_rays_device(d_rays.data_ptr(), n, mode | gpu.RAY_SORTED, t1.data_ptr(), f1.data_ptr())
+            assert ms > 0
+            t0h, f0h, t1h, f1h = t0.cpu().numpy(), f0.cpu().numpy(), t1.cpu().numpy(), f1.cpu().numpy()
+            assert (f0h >= 0).any() and (f0h < 0).any()
+            if mode == gpu.RAY_CLOSEST:
+                assert np.array_equal(f1h, f0h) and np.array_equal(t1h.view(np.uint32), t0h.view(np.uint32))
+            else:
+                assert np.array_equal(f1h >= 0, f0h >= 0)
+            ht, hf, _ = a.trace_rays(d_rays.cpu().numpy(), mode | gpu.RAY_SORTED)          # chunks of 8192 on two streams
+            if mode == gpu.RAY_CLOSEST:
+                assert np.array_equal(hf, f0h) and np.array_equal(ht.view(np.uint32), t0h.view(np.uint32))
+            else:
+                assert np.array_equal(hf >= 0, f0h >= 0)
+    with pytest.raises(gpu.CrtError):
+        a.trace_rays(np.zeros((4, 8), np.float32), 0x200)

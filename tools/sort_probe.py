@@ -34,6 +34,9 @@ def main():
             return best
         ms = run(rays)
         print("%s unordered: %.3f ms = %.1f Mrays/s" % (name, ms, n / ms / 1e3), flush=True)
+        if hasattr(crt, "RAY_SORTED"):                # the product's own ordering (key kernel + radix sort + gather + scatter inside the timed call)
+            best = min(scene.trace_rays_device(rays.data_ptr(), n, mode | crt.RAY_SORTED, t_out.data_ptr(), f_out.data_ptr(), st) for _ in range(4))
+            print("%s CRT_RAY_SORTED (sort inside the call): %.3f ms = %.1f Mrays/s" % (name, best, n / best / 1e3), flush=True)
         if os.environ.get("SP_ONLY_UNORDERED"):
             continue
         lo = rays[:, 0:3].min(0).values
